@@ -1,0 +1,16 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY (see orc_math.hpp header).  Parity unpinned.
+#pragma once
+#include "orc_bvh.hpp"
+
+namespace orc {
+
+void pixel_table(int w, int h, int32_t* indexToPixel, int32_t* pixelToIndex);                 // PixelTable.cpp:57-141
+void raygen_primary(Ray* rays, int32_t* idToSlot, int32_t* slotToID, V3 origin, const M4& nscreenToWorld,
+                    int w, int h, float maxDist, uint32_t randomSeed);                          // RayGen.cpp:76-112
+void raygen_ao(Ray* outRays, int32_t* outIDToSlot, int32_t* outSlotToID,
+               const Ray* inRays, const RayResult* inResults, const V3* normals,
+               int firstInputSlot, int numInputRays, int numSamples, float maxDist, uint32_t randomSeed);  // RayGenKernels.cu:129-236
+int  count_hits(const RayResult* results, int n);                                              // RendererKernels.cu:174-224
+void tri_normals(const Scene& sc, V3* out);                                                    // Scene.cpp:112
+
+} // namespace orc
