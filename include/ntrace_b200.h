@@ -1,0 +1,117 @@
+/* ntrace_b200 — C ABI of the B200-native tracing / BVH-build path (libntrace_b200.so).
+ *
+ * This is the drop-in boundary for NTrace's tracing path.  The reference has no FFI; its
+ * de-facto operator API is the host virtual interface FW::CudaVirtualTracer
+ * (src/rt/cuda/CudaVirtualTracer.hpp:11-26) plus the kernel plug-in ABI of
+ * src/rt/kernels/CudaTracerKernels.hpp:69-112.  Each entry point below names the reference
+ * interface it replaces.  INTEGRATION.md shows the binding a reference maintainer would add.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on error; nt_last_error() gives the message
+ *     (reference: sticky setError/getError, src/framework/base/Defs.hpp:143-147);
+ *   - no exceptions cross the boundary; all pointers are caller-owned and borrowed for the call;
+ *   - pointers may be HOST or DEVICE addresses (the reference's FW::Buffer migrates lazily,
+ *     src/framework/gpu/Buffer.hpp:107-113); the library detects which with
+ *     cudaPointerGetAttributes and stages host buffers through its own device buffers;
+ *   - calls are synchronous: when a call returns its outputs are complete
+ *     (reference: CudaKernel::launchTimed syncs, src/framework/gpu/CudaKernel.cpp:188-221);
+ *   - one device per process (reference: one CUDA context, CudaModule.hpp:92-97); multi-GPU runs
+ *     use one process per GPU and replicate the BVH (nt_bvh_device_ptrs + NCCL broadcast in the host);
+ *   - not re-entrant: one caller thread at a time (guarded by an internal mutex);
+ *   - there is NO CPU fallback: without a CUDA device every call fails with an error.
+ */
+#ifndef NTRACE_B200_H
+#define NTRACE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* BVHLayout values — identical to src/rt/kernels/CudaTracerKernels.hpp:52-63 */
+#define NT_LAYOUT_AOS_AOS  0
+#define NT_LAYOUT_AOS_SOA  1
+#define NT_LAYOUT_SOA_AOS  2
+#define NT_LAYOUT_SOA_SOA  3
+#define NT_LAYOUT_COMPACT  4
+#define NT_LAYOUT_COMPACT2 5
+#define NT_LAYOUT_CPU      6
+
+/* builders accepted by nt_bvh_build — HLBVHBuilder.cpp:44-47 (LBVH when !hlbvh or hlbvhBits == 10) */
+#define NT_BUILDER_LBVH  0
+#define NT_BUILDER_HLBVH 1
+
+/* ---- lifetime / device ------------------------------------------------------------------- */
+/* CudaModule::staticInit (src/framework/gpu/CudaModule.cpp:311): select the device, create the stream. */
+int nt_init(int device_ordinal);
+void nt_shutdown(void);
+/* setError/getError (src/framework/base/Defs.hpp:143-147). Thread-local, never NULL. */
+const char* nt_last_error(void);
+/* number of this library's kernel launches since nt_init (bench.py's gpu_launches). */
+int64_t nt_launch_count(void);
+
+/* ---- kernel selection: CudaBVHTracer::setKernel + queryConfig (CudaBVHTracer.cpp:52-84) --- */
+/* Names: "b200_persistent_speculative_while_while" (default), "b200_speculative_while_while",
+ * and the reference's kernel file names as aliases: "fermi_speculative_while_while" (Compact),
+ * "kepler_dynamic_fetch" (Compact2).  Unknown names fail. */
+int nt_set_kernel(const char* name);
+/* CudaBVHTracer::getDesiredBVHLayout -> BVHLayout of the selected kernel. */
+int nt_desired_layout(void);
+/* KernelConfig {bvhLayout, blockWidth, blockHeight, usePersistentThreads} (CudaTracerKernels.hpp:69-75). */
+int nt_kernel_config(int32_t out4[4]);
+
+/* ---- BVH: CudaAS / CudaBVH buffers (src/rt/cuda/CudaBVH.hpp:137-152) ----------------------- */
+/* setBVH(CudaAS*): copy the three CudaBVH buffers (node, triWoop, triIndex) to the device. */
+int nt_bvh_upload(int layout, const void* nodes, size_t nodeBytes,
+                  const void* woop, size_t woopBytes,
+                  const int32_t* triIndex, size_t idxBytes);
+/* allocate an empty device BVH of the given sizes (replica side of a broadcast). */
+int nt_bvh_alloc(int layout, size_t nodeBytes, size_t woopBytes, size_t idxBytes);
+/* HLBVHBuilder(scene, platform, HLBVHParams) (src/rt/bvh/HLBVH/HLBVHBuilder.hpp:25-41):
+ * GPU LBVH/HLBVH build straight into the Compact traversal layout.  outGpuSeconds = CUDA-event
+ * time of the whole pipeline (reference: m_gpuTime, HLBVHBuilder.cpp:571). */
+int nt_bvh_build(int builder, const float* vtxPos, int numVerts,
+                 const int32_t* triVtxIndex, int numTris,
+                 const float bboxLo[3], const float bboxHi[3],
+                 int hlbvhBits, int leafSize, float epsilon,
+                 float* outGpuSeconds);
+/* sizes[3] = bytes of (nodes, woop, triIndex); layout of the resident BVH in *outLayout. */
+int nt_bvh_sizes(size_t sizes[3], int* outLayout);
+/* CudaBVH::serialize source buffers (CudaBVH.cpp:105-125): copy the device BVH out (host or device dst). */
+int nt_bvh_download(void* nodes, void* woop, int32_t* triIndex);
+/* device addresses of the three buffers, for the host's NCCL broadcast (NEW). */
+int nt_bvh_device_ptrs(void* ptrs[3]);
+/* intermediate products of the last nt_bvh_build, for parity tests: sorted Morton keys and the
+ * triangle order (reference buffers triMorton / triIdx, HLBVHBuilder.cpp:497-508). */
+int nt_bvh_build_debug(uint32_t* sortedKeys, int32_t* sortedIdx, int numTris);
+
+/* ---- trace: CudaBVHTracer::traceBatch(RayBuffer&) (CudaBVHTracer.cpp:88-168) --------------- */
+/* rays: N x {float3 origin, float tmin, float3 dir, float tmax} (src/rt/Util.hpp:62-71);
+ * results: N x {int id, float t, float u, float v} (Util.hpp:77-87; kernels store int4, CudaTracerKernels.hpp:222).
+ * needClosestHit == 0 -> any-hit.  outSeconds = CUDA-event time around the kernel only. */
+int nt_trace_batch(const float* rays, int32_t* results, int numRays, int needClosestHit,
+                   float* outSeconds);
+
+/* ---- ray generation: FW::RayGen (src/rt/ray/RayGen.cpp) ------------------------------------ */
+/* RayGen::primary (RayGen.cpp:45-74): slot i -> pixel PixelTable[i]; idToSlot / slotToID may be NULL. */
+int nt_raygen_primary(float* rays, int32_t* idToSlot, int32_t* slotToID,
+                      const float origin[3], const float nscreenToWorld[16],
+                      int w, int h, float maxDist, uint32_t randomSeed);
+/* RayGen::ao (RayGen.cpp:198-232): numSamples rays per input slot in [first, first+numInputRays);
+ * diffuse = same call with maxDist = camera far and closest-hit tracing (Renderer.cpp:533-538). */
+int nt_raygen_ao(float* outRays, int32_t* outIDToSlot, int32_t* outSlotToID,
+                 const float* inRays, const int32_t* inResults, const float* triNormals,
+                 int firstInputSlot, int numInputRays, int numSamples,
+                 float maxDist, uint32_t randomSeed);
+/* countHitsKernel (RendererKernels.cu:174-224, Renderer.cpp:693-705): results with id >= 0. */
+int nt_count_hits(const int32_t* results, int numRays, int* outHits);
+/* Scene::triNormal (src/rt/Scene.cpp:112): normalize(cross(v1 - v0, v2 - v0)) per triangle. */
+int nt_tri_normals(const float* vtxPos, int numVerts, const int32_t* triVtxIndex, int numTris,
+                   float* outNormals);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NTRACE_B200_H */

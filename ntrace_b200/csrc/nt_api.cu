@@ -1,0 +1,488 @@
+// ntrace_b200 — implementation of the C ABI declared in include/ntrace_b200.h.
+//
+// Host-side behaviour mirrors the reference tracer object:
+//   CudaBVHTracer::setKernel / getDesiredBVHLayout / setBVH / traceBatch
+//     (src/rt/cuda/CudaBVHTracer.cpp:52-168), errors as in :92-101 ("No BVH!", "Incorrect BVH layout!"),
+//   FW::Buffer's lazy host<->device migration (src/framework/gpu/Buffer.hpp:107-113) becomes
+//   explicit staging of host pointers through grow-only device buffers.
+#include "../../include/ntrace_b200.h"
+#include "nt_common.cuh"
+
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+namespace nt {
+
+static thread_local std::string t_error;
+
+void set_error(const std::string& msg) { t_error = msg; }
+
+bool check_cuda(cudaError_t e, const char* what, const char* file, int line)
+{
+    if (e == cudaSuccess) return true;
+    char buf[512];
+    snprintf(buf, sizeof(buf), "CUDA error %d (%s) at %s:%d in %s", (int)e, cudaGetErrorString(e), file, line, what);
+    set_error(buf);
+    cudaGetLastError();   // clear the sticky launch error so later calls can proceed
+    return false;
+}
+
+cudaError_t DevBuf::reserve(size_t bytes)
+{
+    if (bytes <= cap) return cudaSuccess;
+    if (p) { cudaError_t e = cudaFree(p); p = nullptr; cap = 0; if (e != cudaSuccess) return e; }
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) { p = nullptr; cap = 0; return e; }
+    cap = want;
+    return cudaSuccess;
+}
+void DevBuf::release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+
+namespace {
+
+struct Context {
+    bool inited = false;
+    int device = 0, numSMs = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t evA = nullptr, evB = nullptr;
+    int64_t launches = 0;
+
+    int kernel = Kernel_PersistentSpeculative;
+    int kernelLayout = Layout_Compact;
+
+    // resident BVH
+    DevBuf nodes, woop, triIndex;
+    size_t nodeBytes = 0, woopBytes = 0, idxBytes = 0;
+    int bvhLayout = Layout_Max;
+    bool haveBVH = false;
+    DevBuf sortedKeys, sortedIdx;
+    int builtTris = 0;
+
+    // staging
+    DevBuf stRays, stResults, stA, stB, stC, stD, stE;
+    DevBuf counters;          // [0] warp counter, [1] hit counter
+    DevBuf pixelTable; int ptW = 0, ptH = 0;
+    DevBuf sceneVerts, sceneTris;
+};
+
+Context g;
+std::mutex g_mutex;
+
+bool is_device_ptr(const void* p)
+{
+    if (!p) return false;
+    cudaPointerAttributes at;
+    cudaError_t e = cudaPointerGetAttributes(&at, p);
+    if (e != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+}
+
+// device view of a caller buffer that the call only reads
+int stage_in(const void* src, size_t bytes, DevBuf& st, const void** out)
+{
+    if (bytes == 0 || !src) { *out = nullptr; return 0; }
+    if (is_device_ptr(src)) { *out = src; return 0; }
+    NT_CUDA(st.reserve(bytes));
+    NT_CUDA(cudaMemcpyAsync(st.p, src, bytes, cudaMemcpyHostToDevice, g.stream));
+    *out = st.p;
+    return 0;
+}
+// device view of a caller buffer that the call writes; `*hostDst` is set when a copy-back is due
+int stage_out(void* dst, size_t bytes, DevBuf& st, void** out, void** hostDst)
+{
+    *hostDst = nullptr;
+    if (bytes == 0 || !dst) { *out = nullptr; return 0; }
+    if (is_device_ptr(dst)) { *out = dst; return 0; }
+    NT_CUDA(st.reserve(bytes));
+    *out = st.p;
+    *hostDst = dst;
+    return 0;
+}
+int copy_back(void* hostDst, const void* dev, size_t bytes)
+{
+    if (hostDst && bytes) NT_CUDA(cudaMemcpyAsync(hostDst, dev, bytes, cudaMemcpyDeviceToHost, g.stream));
+    return 0;
+}
+
+int require_init()
+{
+    if (!g.inited) { set_error("ntrace_b200: nt_init() has not been called (no CUDA device selected; there is no CPU fallback)"); return 1; }
+    return 0;
+}
+
+// index -> pixel table: 8x8 blocks in Morton order, Morton order inside a block, then the bottom
+// stripe column by column and the right stripe row by row (reference behaviour: PixelTable.cpp:57-141).
+void build_pixel_table(int w, int h, std::vector<int>& tab)
+{
+    tab.resize((size_t)w * h);
+    size_t n = 0;
+    const int bw = w & ~7, bh = h & ~7;
+    int side = 1;
+    while (side * 8 < bw || side * 8 < bh) side <<= 1;   // power-of-two block grid covering the bulk
+    auto compact1by1 = [](unsigned v) {
+        v &= 0x55555555u; v = (v | (v >> 1)) & 0x33333333u; v = (v | (v >> 2)) & 0x0f0f0f0fu;
+        v = (v | (v >> 4)) & 0x00ff00ffu; v = (v | (v >> 8)) & 0x0000ffffu; return (int)v;
+    };
+    if (bw > 0 && bh > 0)
+        for (unsigned code = 0; code < (unsigned)side * (unsigned)side; code++) {
+            const int bx = compact1by1(code), by = compact1by1(code >> 1);
+            if (bx * 8 >= bw || by * 8 >= bh) continue;
+            for (unsigned in = 0; in < 64; in++) {
+                const int ix = compact1by1(in), iy = compact1by1(in >> 1);
+                tab[n++] = (by * 8 + iy) * w + (bx * 8 + ix);
+            }
+        }
+    for (int x = 0; x < bw; x++) for (int y = bh; y < h; y++) tab[n++] = x + y * w;
+    for (int y = 0; y < h; y++) for (int x = bw; x < w; x++) tab[n++] = x + y * w;
+}
+
+int ensure_pixel_table(int w, int h)
+{
+    if (g.ptW == w && g.ptH == h && g.pixelTable.p) return 0;
+    std::vector<int> tab;
+    build_pixel_table(w, h, tab);
+    NT_CUDA(g.pixelTable.reserve(tab.size() * sizeof(int)));
+    NT_CUDA(cudaMemcpyAsync(g.pixelTable.p, tab.data(), tab.size() * sizeof(int), cudaMemcpyHostToDevice, g.stream));
+    NT_CUDA(cudaStreamSynchronize(g.stream));
+    g.ptW = w; g.ptH = h;
+    return 0;
+}
+
+} // namespace
+} // namespace nt
+
+using namespace nt;
+
+extern "C" {
+
+int nt_init(int device_ordinal)
+{
+    std::lock_guard<std::mutex> lock(g_mutex);
+    if (g.inited && g.device == device_ordinal) return 0;
+    if (g.inited) { set_error("ntrace_b200: already initialised on another device; call nt_shutdown() first"); return 1; }
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count <= 0) {
+        cudaGetLastError();
+        set_error("ntrace_b200: no CUDA device available (this library has no CPU fallback)");
+        return 1;
+    }
+    if (device_ordinal < 0 || device_ordinal >= count) { set_error("ntrace_b200: invalid device ordinal"); return 1; }
+    NT_CUDA(cudaSetDevice(device_ordinal));
+    cudaDeviceProp prop;
+    NT_CUDA(cudaGetDeviceProperties(&prop, device_ordinal));
+    if (prop.major < 10) {
+        char buf[256];
+        snprintf(buf, sizeof(buf), "ntrace_b200: device %d is sm_%d%d; this library is built for sm_100a only", device_ordinal, prop.major, prop.minor);
+        set_error(buf);
+        return 1;
+    }
+    g.device = device_ordinal;
+    g.numSMs = prop.multiProcessorCount;
+    NT_CUDA(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
+    NT_CUDA(cudaEventCreate(&g.evA));
+    NT_CUDA(cudaEventCreate(&g.evB));
+    NT_CUDA(g.counters.reserve(64));
+    NT_CUDA(cudaMemsetAsync(g.counters.p, 0, 64, g.stream));
+    NT_CUDA(cudaStreamSynchronize(g.stream));
+    g.launches = 0;
+    g.inited = true;
+    return 0;
+}
+
+void nt_shutdown(void)
+{
+    std::lock_guard<std::mutex> lock(g_mutex);
+    if (!g.inited) return;
+    cudaSetDevice(g.device);
+    cudaStreamSynchronize(g.stream);
+    DevBuf* bufs[] = {&g.nodes, &g.woop, &g.triIndex, &g.sortedKeys, &g.sortedIdx, &g.stRays, &g.stResults, &g.stA, &g.stB,
+                      &g.stC, &g.stD, &g.stE, &g.counters, &g.pixelTable, &g.sceneVerts, &g.sceneTris};
+    for (DevBuf* b : bufs) b->release();
+    cudaEventDestroy(g.evA); cudaEventDestroy(g.evB);
+    cudaStreamDestroy(g.stream);
+    g = Context();
+}
+
+const char* nt_last_error(void) { return t_error.c_str(); }
+
+int64_t nt_launch_count(void) { return g.launches; }
+
+int nt_set_kernel(const char* name)
+{
+    std::lock_guard<std::mutex> lock(g_mutex);
+    if (!name) { set_error("ntrace_b200: null kernel name"); return 1; }
+    struct Entry { const char* name; int kernel; int layout; };
+    static const Entry table[] = {
+        {"b200_persistent_speculative_while_while", Kernel_PersistentSpeculative, Layout_Compact},
+        {"b200_speculative_while_while", Kernel_PlainSpeculative, Layout_Compact},
+        {"b200_persistent_speculative_while_while_compact2", Kernel_PersistentSpeculative, Layout_Compact2},
+        // reference kernel file names (src/rt/kernels/*.cu) accepted as aliases with their layouts
+        {"fermi_speculative_while_while", Kernel_PlainSpeculative, Layout_Compact},
+        {"kepler_dynamic_fetch", Kernel_PersistentSpeculative, Layout_Compact2},
+    };
+    for (const Entry& e : table)
+        if (strcmp(e.name, name) == 0) { g.kernel = e.kernel; g.kernelLayout = e.layout; return 0; }
+    set_error(std::string("ntrace_b200: unknown kernel '") + name + "'");
+    return 1;
+}
+
+int nt_desired_layout(void) { return g.kernelLayout; }
+
+int nt_kernel_config(int32_t out4[4])
+{
+    KernelConfig c = trace_kernel_config(g.kernel, g.kernelLayout);
+    out4[0] = c.bvhLayout; out4[1] = c.blockWidth; out4[2] = c.blockHeight; out4[3] = c.usePersistentThreads;
+    return 0;
+}
+
+int nt_bvh_alloc(int layout, size_t nodeBytes, size_t woopBytes, size_t idxBytes)
+{
+    std::lock_guard<std::mutex> lock(g_mutex);
+    if (require_init()) return 1;
+    if (layout != Layout_Compact && layout != Layout_Compact2) { set_error("ntrace_b200: only BVHLayout_Compact / Compact2 are supported"); return 1; }
+    if (nodeBytes < 64 || nodeBytes % 64 || woopBytes % 16 || idxBytes * 4 != woopBytes) {
+        set_error("ntrace_b200: inconsistent CudaBVH buffer sizes (nodes multiple of 64 B, woop of 16 B, one index per woop float4)");
+        return 1;
+    }
+    NT_CUDA(g.nodes.reserve(nodeBytes));
+    NT_CUDA(g.woop.reserve(woopBytes));
+    NT_CUDA(g.triIndex.reserve(idxBytes));
+    g.nodeBytes = nodeBytes; g.woopBytes = woopBytes; g.idxBytes = idxBytes;
+    g.bvhLayout = layout;
+    g.haveBVH = true;
+    g.builtTris = 0;
+    return 0;
+}
+
+int nt_bvh_upload(int layout, const void* nodes, size_t nodeBytes, const void* woop, size_t woopBytes,
+                  const int32_t* triIndex, size_t idxBytes)
+{
+    if (!nodes || !woop || !triIndex) { set_error("ntrace_b200: null BVH buffer"); return 1; }
+    if (nt_bvh_alloc(layout, nodeBytes, woopBytes, idxBytes)) return 1;
+    std::lock_guard<std::mutex> lock(g_mutex);
+    NT_CUDA(cudaMemcpyAsync(g.nodes.p, nodes, nodeBytes, cudaMemcpyDefault, g.stream));
+    NT_CUDA(cudaMemcpyAsync(g.woop.p, woop, woopBytes, cudaMemcpyDefault, g.stream));
+    NT_CUDA(cudaMemcpyAsync(g.triIndex.p, triIndex, idxBytes, cudaMemcpyDefault, g.stream));
+    NT_CUDA(cudaStreamSynchronize(g.stream));
+    return 0;
+}
+
+int nt_bvh_build(int builder, const float* vtxPos, int numVerts, const int32_t* triVtxIndex, int numTris,
+                 const float bboxLo[3], const float bboxHi[3], int hlbvhBits, int leafSize, float epsilon,
+                 float* outGpuSeconds)
+{
+    std::lock_guard<std::mutex> lock(g_mutex);
+    if (require_init()) return 1;
+    if (!vtxPos || !triVtxIndex || numVerts <= 0 || numTris <= 0) { set_error("ntrace_b200: empty scene"); return 1; }
+    if (leafSize < 1) { set_error("ntrace_b200: leafSize must be >= 1"); return 1; }
+    if (builder != NT_BUILDER_LBVH && builder != NT_BUILDER_HLBVH) { set_error("ntrace_b200: unknown builder"); return 1; }
+    const void *dV, *dT;
+    if (stage_in(vtxPos, (size_t)numVerts * 12, g.sceneVerts, &dV)) return 1;
+    if (stage_in(triVtxIndex, (size_t)numTris * 12, g.sceneTris, &dT)) return 1;
+    BuildParams p;
+    p.builder = builder; p.hlbvhBits = hlbvhBits; p.leafSize = leafSize; p.epsilon = epsilon;
+    for (int i = 0; i < 3; i++) { p.lo[i] = bboxLo[i]; p.hi[i] = bboxHi[i]; }
+    BuildOutput out;
+    out.nodes = &g.nodes; out.woop = &g.woop; out.triIndex = &g.triIndex;
+    out.sortedKeys = &g.sortedKeys; out.sortedIdx = &g.sortedIdx;
+    out.nodeBytes = out.woopBytes = out.idxBytes = 0;
+    g.haveBVH = false;
+    NT_CUDA(cudaEventRecord(g.evA, g.stream));
+    int launches = 0;
+    std::string err;
+    cudaError_t e = build_bvh_device((const float*)dV, numVerts, (const int*)dT, numTris, p, out, g.stream, g.numSMs, &launches, &err);
+    g.launches += launches;
+    if (e != cudaSuccess) {
+        if (!err.empty()) { set_error("ntrace_b200: " + err); cudaGetLastError(); return 1; }
+        NT_CUDA(e);
+    }
+    NT_CUDA(cudaEventRecord(g.evB, g.stream));
+    NT_CUDA(cudaEventSynchronize(g.evB));
+    float ms = 0.0f;
+    NT_CUDA(cudaEventElapsedTime(&ms, g.evA, g.evB));
+    if (outGpuSeconds) *outGpuSeconds = ms * 1.0e-3f;
+    g.nodeBytes = out.nodeBytes; g.woopBytes = out.woopBytes; g.idxBytes = out.idxBytes;
+    g.bvhLayout = Layout_Compact;           // HLBVHBuilder output is Compact only (HLBVHBuilder.cpp:33)
+    g.haveBVH = true;
+    g.builtTris = numTris;
+    return 0;
+}
+
+int nt_bvh_sizes(size_t sizes[3], int* outLayout)
+{
+    std::lock_guard<std::mutex> lock(g_mutex);
+    if (require_init()) return 1;
+    if (!g.haveBVH) { set_error("CudaBVHTracer: No BVH!"); return 1; }
+    sizes[0] = g.nodeBytes; sizes[1] = g.woopBytes; sizes[2] = g.idxBytes;
+    if (outLayout) *outLayout = g.bvhLayout;
+    return 0;
+}
+
+int nt_bvh_download(void* nodes, void* woop, int32_t* triIndex)
+{
+    std::lock_guard<std::mutex> lock(g_mutex);
+    if (require_init()) return 1;
+    if (!g.haveBVH) { set_error("CudaBVHTracer: No BVH!"); return 1; }
+    if (nodes) NT_CUDA(cudaMemcpyAsync(nodes, g.nodes.p, g.nodeBytes, cudaMemcpyDefault, g.stream));
+    if (woop) NT_CUDA(cudaMemcpyAsync(woop, g.woop.p, g.woopBytes, cudaMemcpyDefault, g.stream));
+    if (triIndex) NT_CUDA(cudaMemcpyAsync(triIndex, g.triIndex.p, g.idxBytes, cudaMemcpyDefault, g.stream));
+    NT_CUDA(cudaStreamSynchronize(g.stream));
+    return 0;
+}
+
+int nt_bvh_device_ptrs(void* ptrs[3])
+{
+    std::lock_guard<std::mutex> lock(g_mutex);
+    if (require_init()) return 1;
+    if (!g.haveBVH) { set_error("CudaBVHTracer: No BVH!"); return 1; }
+    ptrs[0] = g.nodes.p; ptrs[1] = g.woop.p; ptrs[2] = g.triIndex.p;
+    return 0;
+}
+
+int nt_bvh_build_debug(uint32_t* sortedKeys, int32_t* sortedIdx, int numTris)
+{
+    std::lock_guard<std::mutex> lock(g_mutex);
+    if (require_init()) return 1;
+    if (g.builtTris <= 0 || numTris != g.builtTris) { set_error("ntrace_b200: no GPU build of that size is resident"); return 1; }
+    if (sortedKeys) NT_CUDA(cudaMemcpyAsync(sortedKeys, g.sortedKeys.p, (size_t)numTris * 4, cudaMemcpyDefault, g.stream));
+    if (sortedIdx) NT_CUDA(cudaMemcpyAsync(sortedIdx, g.sortedIdx.p, (size_t)numTris * 4, cudaMemcpyDefault, g.stream));
+    NT_CUDA(cudaStreamSynchronize(g.stream));
+    return 0;
+}
+
+int nt_trace_batch(const float* rays, int32_t* results, int numRays, int needClosestHit, float* outSeconds)
+{
+    std::lock_guard<std::mutex> lock(g_mutex);
+    if (outSeconds) *outSeconds = 0.0f;
+    if (require_init()) return 1;
+    if (numRays == 0) return 0;                                        // CudaBVHTracer.cpp:92-94
+    if (numRays < 0 || !rays || !results) { set_error("ntrace_b200: invalid ray batch"); return 1; }
+    if (!g.haveBVH) { set_error("CudaBVHTracer: No BVH!"); return 1; }                          // :98-99
+    if (g.bvhLayout != g.kernelLayout) { set_error("CudaBVHTracer: Incorrect BVH layout!"); return 1; }  // :100-101
+
+    const void* dRays; void* dRes; void* hostRes;
+    if (stage_in(rays, (size_t)numRays * 32, g.stRays, &dRays)) return 1;
+    if (stage_out(results, (size_t)numRays * 16, g.stResults, &dRes, &hostRes)) return 1;
+
+    TraceLaunch a;
+    a.kernel = g.kernel; a.layout = g.kernelLayout; a.numRays = numRays; a.anyHit = needClosestHit ? 0 : 1;
+    a.rays = (const float4*)dRays; a.results = (int4*)dRes;
+    a.nodes = g.nodes.as<float4>(); a.woop = g.woop.as<float4>(); a.triIndices = g.triIndex.as<int>();
+    a.warpCounter = g.counters.as<int>(); a.numSMs = g.numSMs; a.stream = g.stream;
+
+    // the counter reset is issued before the first event so the timed interval is the kernel only
+    NT_CUDA(cudaMemsetAsync(a.warpCounter, 0, sizeof(int), g.stream));
+    NT_CUDA(cudaEventRecord(g.evA, g.stream));
+    int launches = 0;
+    NT_CUDA(launch_trace(a, &launches));
+    NT_CUDA(cudaEventRecord(g.evB, g.stream));
+    g.launches += launches;
+    if (copy_back(hostRes, dRes, (size_t)numRays * 16)) return 1;
+    NT_CUDA(cudaStreamSynchronize(g.stream));
+    float ms = 0.0f;
+    NT_CUDA(cudaEventElapsedTime(&ms, g.evA, g.evB));
+    if (outSeconds) *outSeconds = ms * 1.0e-3f;
+    return 0;
+}
+
+int nt_raygen_primary(float* rays, int32_t* idToSlot, int32_t* slotToID, const float origin[3],
+                      const float nscreenToWorld[16], int w, int h, float maxDist, uint32_t randomSeed)
+{
+    std::lock_guard<std::mutex> lock(g_mutex);
+    if (require_init()) return 1;
+    if (w <= 0 || h <= 0 || !rays) { set_error("ntrace_b200: invalid primary ray request"); return 1; }
+    if (ensure_pixel_table(w, h)) return 1;
+    const size_t n = (size_t)w * h;
+    void *dRays, *hRays, *dI2S, *hI2S, *dS2I, *hS2I;
+    if (stage_out(rays, n * 32, g.stRays, &dRays, &hRays)) return 1;
+    if (stage_out(idToSlot, n * 4, g.stA, &dI2S, &hI2S)) return 1;
+    if (stage_out(slotToID, n * 4, g.stB, &dS2I, &hS2I)) return 1;
+    PrimaryArgs a;
+    a.rays = (float4*)dRays; a.idToSlot = (int*)dI2S; a.slotToID = (int*)dS2I;
+    for (int i = 0; i < 3; i++) a.origin[i] = origin[i];
+    for (int i = 0; i < 16; i++) a.n2w[i] = nscreenToWorld[i];
+    a.w = w; a.h = h; a.maxDist = maxDist; a.seed = randomSeed;
+    NT_CUDA(launch_raygen_primary(a, g.pixelTable.as<int>(), g.stream));
+    g.launches += 1;
+    if (copy_back(hRays, dRays, n * 32) || copy_back(hI2S, dI2S, n * 4) || copy_back(hS2I, dS2I, n * 4)) return 1;
+    NT_CUDA(cudaStreamSynchronize(g.stream));
+    return 0;
+}
+
+int nt_raygen_ao(float* outRays, int32_t* outIDToSlot, int32_t* outSlotToID, const float* inRays,
+                 const int32_t* inResults, const float* triNormals, int firstInputSlot, int numInputRays,
+                 int numSamples, float maxDist, uint32_t randomSeed)
+{
+    std::lock_guard<std::mutex> lock(g_mutex);
+    if (require_init()) return 1;
+    if (numInputRays == 0) return 0;
+    if (numInputRays < 0 || numSamples <= 0 || firstInputSlot < 0 || !outRays || !inRays || !inResults || !triNormals) {
+        set_error("ntrace_b200: invalid AO ray request");
+        return 1;
+    }
+    if (is_device_ptr(inRays) != is_device_ptr(inResults)) { set_error("ntrace_b200: inRays and inResults must live on the same side"); return 1; }
+    const size_t nOut = (size_t)numInputRays * numSamples;
+    if (nOut > 0x3fffffffull) { set_error("ntrace_b200: AO batch too large"); return 1; }
+    // host inputs: only the [first, first+count) window is staged, so the device slot base becomes 0
+    const void *dInRays, *dInRes;
+    int first = firstInputSlot;
+    if (!is_device_ptr(inRays)) {
+        if (stage_in(inRays + (size_t)firstInputSlot * 8, (size_t)numInputRays * 32, g.stC, &dInRays)) return 1;
+        if (stage_in(inResults + (size_t)firstInputSlot * 4, (size_t)numInputRays * 16, g.stD, &dInRes)) return 1;
+        first = 0;
+    } else { dInRays = inRays; dInRes = inResults; }
+    const void* dNormals = triNormals;
+    if (!is_device_ptr(triNormals)) { set_error("ntrace_b200: triNormals must be a device pointer (use nt_tri_normals with a device output)"); return 1; }
+    void *dOut, *hOut, *dA, *hA, *dB, *hB;
+    if (stage_out(outRays, nOut * 32, g.stRays, &dOut, &hOut)) return 1;
+    if (stage_out(outIDToSlot, nOut * 4, g.stA, &dA, &hA)) return 1;
+    if (stage_out(outSlotToID, nOut * 4, g.stB, &dB, &hB)) return 1;
+    AOArgs a;
+    a.outRays = (float4*)dOut; a.outIDToSlot = (int*)dA; a.outSlotToID = (int*)dB;
+    a.inRays = (const float4*)dInRays; a.inResults = (const int4*)dInRes; a.normals = (const float*)dNormals;
+    a.firstInputSlot = first; a.numInputRays = numInputRays; a.numSamples = numSamples; a.maxDist = maxDist; a.seed = randomSeed;
+    NT_CUDA(launch_raygen_ao(a, g.stream));
+    g.launches += 1;
+    if (copy_back(hOut, dOut, nOut * 32) || copy_back(hA, dA, nOut * 4) || copy_back(hB, dB, nOut * 4)) return 1;
+    NT_CUDA(cudaStreamSynchronize(g.stream));
+    return 0;
+}
+
+int nt_count_hits(const int32_t* results, int numRays, int* outHits)
+{
+    std::lock_guard<std::mutex> lock(g_mutex);
+    if (require_init()) return 1;
+    if (!outHits) { set_error("ntrace_b200: null output"); return 1; }
+    *outHits = 0;
+    if (numRays == 0) return 0;
+    if (numRays < 0 || !results) { set_error("ntrace_b200: invalid result buffer"); return 1; }
+    const void* dRes;
+    if (stage_in(results, (size_t)numRays * 16, g.stResults, &dRes)) return 1;
+    int* counter = g.counters.as<int>() + 1;
+    NT_CUDA(launch_count_hits((const int4*)dRes, numRays, counter, g.stream));
+    g.launches += 1;
+    NT_CUDA(cudaMemcpyAsync(outHits, counter, sizeof(int), cudaMemcpyDeviceToHost, g.stream));
+    NT_CUDA(cudaStreamSynchronize(g.stream));
+    return 0;
+}
+
+int nt_tri_normals(const float* vtxPos, int numVerts, const int32_t* triVtxIndex, int numTris, float* outNormals)
+{
+    std::lock_guard<std::mutex> lock(g_mutex);
+    if (require_init()) return 1;
+    if (!vtxPos || !triVtxIndex || !outNormals || numVerts <= 0 || numTris <= 0) { set_error("ntrace_b200: empty scene"); return 1; }
+    const void *dV, *dT; void *dN, *hN;
+    if (stage_in(vtxPos, (size_t)numVerts * 12, g.sceneVerts, &dV)) return 1;
+    if (stage_in(triVtxIndex, (size_t)numTris * 12, g.sceneTris, &dT)) return 1;
+    if (stage_out(outNormals, (size_t)numTris * 12, g.stE, &dN, &hN)) return 1;
+    NT_CUDA(launch_tri_normals((const float*)dV, (const int*)dT, numTris, (float*)dN, g.stream));
+    g.launches += 1;
+    if (copy_back(hN, dN, (size_t)numTris * 12)) return 1;
+    NT_CUDA(cudaStreamSynchronize(g.stream));
+    return 0;
+}
+
+} // extern "C"

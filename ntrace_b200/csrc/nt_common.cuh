@@ -1,0 +1,91 @@
+// ntrace_b200 — shared declarations for the sm_100a CUDA sources behind the C ABI (include/ntrace_b200.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+
+namespace nt {
+
+// Reference: src/rt/kernels/CudaTracerKernels.hpp:36-39, 52-63 (kept bit-identical: these values
+// are part of the CudaBVH data format the path exchanges with the host).
+enum : int { kEntrypointSentinel = 0x76543210 };
+enum BVHLayout : int {
+    Layout_AOS_AOS = 0, Layout_AOS_SOA, Layout_SOA_AOS, Layout_SOA_SOA,
+    Layout_Compact, Layout_Compact2, Layout_CPU, Layout_Max
+};
+
+struct KernelConfig { int bvhLayout, blockWidth, blockHeight, usePersistentThreads; };
+
+// thread-local sticky error string (reference: setError/getError, base/Defs.hpp:143-147)
+void set_error(const std::string& msg);
+bool check_cuda(cudaError_t e, const char* what, const char* file, int line);
+
+#define NT_CUDA(call)                                                          \
+    do {                                                                       \
+        if (!::nt::check_cuda((call), #call, __FILE__, __LINE__)) return 1;   \
+    } while (0)
+
+// ---- trace (nt_trace.cu) --------------------------------------------------------------------
+enum TraceKernelId : int {
+    Kernel_PersistentSpeculative = 0,   // persistent while-while, warp-level dynamic ray fetch, speculative leaf
+    Kernel_PlainSpeculative = 1,        // one thread per ray, speculative while-while (fermi-style launch shape)
+    Kernel_Count
+};
+
+struct TraceLaunch {
+    int kernel;               // TraceKernelId
+    int layout;               // Layout_Compact or Layout_Compact2
+    int numRays;
+    int anyHit;
+    const float4* rays;       // device, 2 x float4 per ray
+    int4* results;            // device, 1 x int4 per ray
+    const float4* nodes;      // device, 4 x float4 per node
+    const float4* woop;       // device
+    const int* triIndices;    // device
+    int* warpCounter;         // device, zeroed before launch (persistent kernels only)
+    int numSMs;
+    cudaStream_t stream;
+};
+cudaError_t launch_trace(const TraceLaunch& a, int* outNumLaunches);
+KernelConfig trace_kernel_config(int kernel, int layout);
+
+// ---- ray generation (nt_raygen.cu) ------------------------------------------------------------
+struct PrimaryArgs {
+    float4* rays; int* idToSlot; int* slotToID;
+    float origin[3]; float n2w[16]; int w, h; float maxDist; unsigned seed;
+};
+cudaError_t launch_raygen_primary(const PrimaryArgs& a, const int* indexToPixel, cudaStream_t s);
+struct AOArgs {
+    float4* outRays; int* outIDToSlot; int* outSlotToID;
+    const float4* inRays; const int4* inResults; const float* normals;
+    int firstInputSlot, numInputRays, numSamples; float maxDist; unsigned seed;
+};
+cudaError_t launch_raygen_ao(const AOArgs& a, cudaStream_t s);
+cudaError_t launch_count_hits(const int4* results, int numRays, int* dCounter, cudaStream_t s);
+cudaError_t launch_tri_normals(const float* verts, const int* tris, int numTris, float* out, cudaStream_t s);
+
+// ---- GPU LBVH / HLBVH builder (nt_build.cu) ---------------------------------------------------
+struct DevBuf {
+    void* p = nullptr; size_t cap = 0;
+    cudaError_t reserve(size_t bytes);      // grow-only (reference: RayBuffer::resize never shrinks, RayBuffer.cpp:41-45)
+    void release();
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct BuildParams {
+    int builder;              // 0 = LBVH, 1 = HLBVH
+    int hlbvhBits, leafSize; float epsilon;
+    float lo[3], hi[3];
+};
+struct BuildOutput {          // device buffers owned by the context
+    DevBuf* nodes; DevBuf* woop; DevBuf* triIndex;
+    size_t nodeBytes, woopBytes, idxBytes;
+    DevBuf* sortedKeys; DevBuf* sortedIdx;   // kept for nt_bvh_build_debug
+};
+// verts/tris are device pointers. Returns cudaSuccess and fills sizes; launches counted into *outLaunches.
+cudaError_t build_bvh_device(const float* dVerts, int numVerts, const int* dTris, int numTris,
+                             const BuildParams& p, BuildOutput& out, cudaStream_t stream,
+                             int numSMs, int* outLaunches, std::string* err);
+
+} // namespace nt

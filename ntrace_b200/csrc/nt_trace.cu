@@ -1,0 +1,278 @@
+// ntrace_b200 — BVH traversal kernels for sm_100a (B200).
+//
+// Replaces the reference's runtime-compiled trace_bvh kernels
+//   src/rt/kernels/fermi_speculative_while_while.cu:54-263   (semantics: speculative while-while, Compact)
+//   src/rt/kernels/kepler_dynamic_fetch.cu:61-321            (semantics: persistent warps, dynamic fetch)
+// behind the kernel ABI of src/rt/kernels/CudaTracerKernels.hpp:99-112 (TRACE_FUNC_BVH).
+//
+// Design (B200-first, no texture references, no video-instruction min/max, no local-memory stack):
+//  * persistent grid = SMs x resident CTAs; each warp pulls rays from one global counter with a
+//    single atomicAdd per refill (ballot + popc rank, leader broadcast with shfl);
+//  * nodes are 64 B (two child AABBs + two child links): fetched as 4 x ld.global.nc.v4 per lane;
+//    Woop triangles as up to 3 x ld.global.nc.v4 with the reference's early-outs;
+//  * traversal stack: top entries in shared memory laid out [entry][thread] (bank = lane, conflict
+//    free for any mix of depths), remainder spills to a per-thread local array (rarely touched);
+//  * slab test on FMNMX3 (3-input min/max exists on sm_100a);
+//  * speculative traversal: the first leaf a lane finds is postponed until no lane of the warp is
+//    still searching (reference: fermi...cu:176-187);
+//  * results are written once per ray when it terminates.
+//
+// Numerics: the ray/triangle test reproduces the host reference's Intersect::RayTriangleWoop
+// (src/rt/Util.cpp:99-127) operation for operation in IEEE fp32 (no FMA contraction, IEEE reciprocal), so
+// per-triangle hit decisions and the reported t/u/v are bit-identical to the CPU path traversing the same
+// buffers.  The slab test keeps the reference GPU form n*idir - ood (fermi...cu:120-145) with FMA: it only
+// decides which nodes are visited, never what a hit is.
+#include "nt_common.cuh"
+
+namespace nt {
+
+namespace {
+
+constexpr int kStackSize = 64;                 // reference: STACK_SIZE 64 (fermi...cu:41)
+constexpr int kDynamicFetchThreshold = 20;     // reference: kepler_dynamic_fetch.cu:43
+
+__device__ __forceinline__ float fmin3(float a, float b, float c) { float r; asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c)); return r; }
+__device__ __forceinline__ float fmax3(float a, float b, float c) { float r; asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c)); return r; }
+
+// span begin = max(min(a0,a1), min(b0,b1), min(c0,c1), d); span end = min(max.., d)
+__device__ __forceinline__ float span_begin(float a0, float a1, float b0, float b1, float c0, float c1, float d)
+{
+    return fmax3(fminf(a0, a1), fminf(b0, b1), fmaxf(fminf(c0, c1), d));
+}
+__device__ __forceinline__ float span_end(float a0, float a1, float b0, float b1, float c0, float c1, float d)
+{
+    return fmin3(fmaxf(a0, a1), fmaxf(b0, b1), fminf(fmaxf(c0, c1), d));
+}
+
+template <int LAYOUT>
+__device__ __forceinline__ const float4* node_ptr(const float4* nodes, int addr)
+{
+    // Compact: byte offset; Compact2: float4 index (CudaBVH.cpp:86,614)
+    if (LAYOUT == Layout_Compact2) return nodes + addr;
+    return reinterpret_cast<const float4*>(reinterpret_cast<const char*>(nodes) + addr);
+}
+
+template <int LAYOUT, int BLOCK, int SMEM_N, bool PERSISTENT>
+__global__ void __launch_bounds__(BLOCK)
+trace_kernel(int numRays, int anyHit,
+             const float4* __restrict__ rays, int4* __restrict__ results,
+             const float4* __restrict__ nodes, const float4* __restrict__ woop,
+             const int* __restrict__ triIndices, int* __restrict__ warpCounter)
+{
+    static_assert(SMEM_N >= 1 && SMEM_N <= kStackSize, "stack split");
+    __shared__ int s_stack[SMEM_N * BLOCK];
+    int l_stack[(kStackSize > SMEM_N) ? (kStackSize - SMEM_N) : 1];
+
+    const int tid = threadIdx.x;
+    const unsigned lane = tid & 31;
+    int* const sbase = s_stack + tid;
+
+#define NT_PUSH(v)  do { ++sp; if (sp < SMEM_N) sbase[sp * BLOCK] = (v); else l_stack[sp - SMEM_N] = (v); } while (0)
+#define NT_POP(dst) do { (dst) = (sp < SMEM_N) ? sbase[sp * BLOCK] : l_stack[sp - SMEM_N]; --sp; } while (0)
+
+    // Live state (registers).
+    int   rayidx = -1;
+    float origx = 0, origy = 0, origz = 0, dirx = 0, diry = 0, dirz = 0, tmin = 0;
+    float idirx = 0, idiry = 0, idirz = 0, oodx = 0, oody = 0, oodz = 0;
+    int   sp = 0;
+    int   leafAddr = 0;
+    int   nodeAddr = kEntrypointSentinel;
+    int   hitIndex = -1;
+    float hitT = 0, hitU = 0, hitV = 0;
+    bool  alive = true;
+
+    for (;;) {
+        // ---------------- ray fetch ----------------
+        const bool need = alive && (nodeAddr == kEntrypointSentinel);
+        if (PERSISTENT) {
+            // One atomicAdd per warp refill: rank the lanes that need a ray, the first of them
+            // reserves a contiguous range and broadcasts its base (reference: kepler...cu:96-115).
+            const unsigned needMask = __ballot_sync(0xffffffffu, need);
+            if (needMask) {
+                const int n = __popc(needMask);
+                const int rank = __popc(needMask & ((1u << lane) - 1u));
+                const int leader = __ffs(needMask) - 1;
+                int base = 0;
+                if ((int)lane == leader) base = atomicAdd(warpCounter, n);
+                base = __shfl_sync(0xffffffffu, base, leader);
+                if (need) rayidx = base + rank;
+            }
+        } else {
+            if (need) rayidx = (rayidx == -1) ? (int)(blockIdx.x * BLOCK + tid) : numRays;
+        }
+        if (need) {
+            if (rayidx >= numRays) { alive = false; rayidx = -1; }
+            else {
+                const float4 o = __ldcs(rays + rayidx * 2 + 0);
+                const float4 d = __ldcs(rays + rayidx * 2 + 1);
+                origx = o.x; origy = o.y; origz = o.z; tmin = o.w;
+                dirx = d.x; diry = d.y; dirz = d.z; hitT = d.w;
+                const float ooeps = exp2f(-80.0f);                      // fermi...cu:94-98
+                idirx = 1.0f / (fabsf(d.x) > ooeps ? d.x : copysignf(ooeps, d.x));
+                idiry = 1.0f / (fabsf(d.y) > ooeps ? d.y : copysignf(ooeps, d.y));
+                idirz = 1.0f / (fabsf(d.z) > ooeps ? d.z : copysignf(ooeps, d.z));
+                oodx = origx * idirx; oody = origy * idiry; oodz = origz * idirz;
+                sp = 0;
+                sbase[0] = kEntrypointSentinel;
+                leafAddr = 0;
+                nodeAddr = 0;
+                hitIndex = -1;
+                hitU = 0.0f; hitV = 0.0f;
+            }
+        }
+        if (!__any_sync(0xffffffffu, alive)) break;
+
+        // ---------------- traversal ----------------
+        while (nodeAddr != kEntrypointSentinel) {
+            // Inner nodes, until every lane still in this loop holds a postponed leaf.
+            while ((unsigned)nodeAddr < (unsigned)kEntrypointSentinel) {
+                const float4* ptr = node_ptr<LAYOUT>(nodes, nodeAddr);
+                const float4 n0xy = __ldg(ptr + 0);   // (c0.lo.x, c0.hi.x, c0.lo.y, c0.hi.y)
+                const float4 n1xy = __ldg(ptr + 1);   // (c1.lo.x, c1.hi.x, c1.lo.y, c1.hi.y)
+                const float4 nz   = __ldg(ptr + 2);   // (c0.lo.z, c0.hi.z, c1.lo.z, c1.hi.z)
+                const float4 cn   = __ldg(ptr + 3);   // (c0, c1, splitInfo, 0) as ints
+                int c0idx = __float_as_int(cn.x), c1idx = __float_as_int(cn.y);
+
+                const float c0lox = n0xy.x * idirx - oodx, c0hix = n0xy.y * idirx - oodx;
+                const float c0loy = n0xy.z * idiry - oody, c0hiy = n0xy.w * idiry - oody;
+                const float c0loz = nz.x * idirz - oodz,   c0hiz = nz.y * idirz - oodz;
+                const float c1loz = nz.z * idirz - oodz,   c1hiz = nz.w * idirz - oodz;
+                const float c0min = span_begin(c0lox, c0hix, c0loy, c0hiy, c0loz, c0hiz, tmin);
+                const float c0max = span_end  (c0lox, c0hix, c0loy, c0hiy, c0loz, c0hiz, hitT);
+                const float c1lox = n1xy.x * idirx - oodx, c1hix = n1xy.y * idirx - oodx;
+                const float c1loy = n1xy.z * idiry - oody, c1hiy = n1xy.w * idiry - oody;
+                const float c1min = span_begin(c1lox, c1hix, c1loy, c1hiy, c1loz, c1hiz, tmin);
+                const float c1max = span_end  (c1lox, c1hix, c1loy, c1hiy, c1loz, c1hiz, hitT);
+
+                const bool trav0 = (c0max >= c0min);
+                const bool trav1 = (c1max >= c1min);
+
+                if (!trav0 && !trav1) {
+                    NT_POP(nodeAddr);
+                } else {
+                    nodeAddr = trav0 ? c0idx : c1idx;
+                    if (trav0 && trav1) {
+                        if (c1min < c0min) { const int t = nodeAddr; nodeAddr = c1idx; c1idx = t; }
+                        NT_PUSH(c1idx);
+                    }
+                }
+
+                // First leaf => postpone and continue traversal.
+                if (nodeAddr < 0 && leafAddr >= 0) {
+                    leafAddr = nodeAddr;
+                    NT_POP(nodeAddr);
+                }
+
+                // All lanes have found a leaf => process them.
+                if (!__any_sync(__activemask(), leafAddr >= 0)) break;
+            }
+
+            // Postponed leaves: Woop test against each triangle until the terminator.
+            while (leafAddr < 0) {
+                for (int triAddr = ~leafAddr;; triAddr += 3) {
+                    const float4 v00 = __ldg(woop + triAddr);
+                    if (__float_as_int(v00.x) == (int)0x80000000) break;
+
+                    // Woop test in exactly the operation order of Intersect::RayTriangleWoop (Util.cpp:99-127),
+                    // every product and sum rounded separately (no FMA contraction) and an IEEE reciprocal, so
+                    // that each accept/reject decision is bit-identical to the host reference's.
+                    const float Oz = __fsub_rn(__fsub_rn(__fsub_rn(v00.w, __fmul_rn(origx, v00.x)), __fmul_rn(origy, v00.y)), __fmul_rn(origz, v00.z));
+                    const float dd = __fadd_rn(__fadd_rn(__fmul_rn(dirx, v00.x), __fmul_rn(diry, v00.y)), __fmul_rn(dirz, v00.z));
+                    const float t = __fmul_rn(Oz, __frcp_rn(dd));
+
+                    if (t > tmin && t < hitT) {
+                        const float4 v11 = __ldg(woop + triAddr + 1);
+                        const float Ou = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(v11.x, origx), __fmul_rn(v11.y, origy)), __fmul_rn(v11.z, origz)), v11.w);
+                        const float Du = __fadd_rn(__fadd_rn(__fmul_rn(v11.x, dirx), __fmul_rn(v11.y, diry)), __fmul_rn(v11.z, dirz));
+                        const float u = __fadd_rn(Ou, __fmul_rn(t, Du));
+                        if (u >= 0.0f) {
+                            const float4 v22 = __ldg(woop + triAddr + 2);
+                            const float Ov = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(v22.x, origx), __fmul_rn(v22.y, origy)), __fmul_rn(v22.z, origz)), v22.w);
+                            const float Dv = __fadd_rn(__fadd_rn(__fmul_rn(v22.x, dirx), __fmul_rn(v22.y, diry)), __fmul_rn(v22.z, dirz));
+                            const float v = __fadd_rn(Ov, __fmul_rn(t, Dv));
+                            if (v >= 0.0f && __fadd_rn(u, v) <= 1.0f) {
+                                hitT = t; hitU = u; hitV = v;
+                                hitIndex = triAddr;
+                                if (anyHit) { nodeAddr = kEntrypointSentinel; break; }
+                            }
+                        }
+                    }
+                }
+                // Another leaf was postponed => process it as well.
+                leafAddr = nodeAddr;
+                if (nodeAddr < 0) NT_POP(nodeAddr);
+            }
+
+            // Too few lanes left busy => leave and refill the idle ones (kepler...cu:310-311).
+            if (PERSISTENT && __popc(__activemask()) < kDynamicFetchThreshold) break;
+        }
+
+        // ---------------- result ----------------
+        if (rayidx >= 0 && nodeAddr == kEntrypointSentinel) {
+            int id = hitIndex;
+            if (id != -1) id = __ldg(triIndices + id);          // fermi...cu:260-261
+            __stcs(results + rayidx, make_int4(id, __float_as_int(hitT), __float_as_int(hitU), __float_as_int(hitV)));
+            if (PERSISTENT) rayidx = -1;
+        }
+        if (!PERSISTENT) break;
+    }
+#undef NT_PUSH
+#undef NT_POP
+}
+
+constexpr int kBlock = 128;
+constexpr int kSmemStack = 16;
+
+template <int LAYOUT, bool PERSISTENT>
+cudaError_t launch_one(const TraceLaunch& a, int* launches)
+{
+    auto kern = trace_kernel<LAYOUT, kBlock, kSmemStack, PERSISTENT>;
+    int grid;
+    if (PERSISTENT) {
+        static int blocksPerSM = 0;
+        if (!blocksPerSM) {
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 25);
+            if (e != cudaSuccess) return e;
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSM, kern, kBlock, 0);
+            if (e != cudaSuccess) return e;
+            if (blocksPerSM < 1) blocksPerSM = 1;
+        }
+        grid = a.numSMs * blocksPerSM;
+        const int needed = (a.numRays + kBlock - 1) / kBlock;
+        if (grid > needed) grid = needed;
+    } else {
+        grid = (a.numRays + kBlock - 1) / kBlock;
+    }
+    kern<<<grid, kBlock, 0, a.stream>>>(a.numRays, a.anyHit, a.rays, a.results, a.nodes, a.woop, a.triIndices, a.warpCounter);
+    if (launches) *launches = 1;
+    return cudaGetLastError();
+}
+
+} // namespace
+
+KernelConfig trace_kernel_config(int kernel, int layout)
+{
+    // reference: queryConfig() in every kernel file (e.g. fermi...cu:45-50)
+    KernelConfig c;
+    c.bvhLayout = layout;
+    c.blockWidth = 32;
+    c.blockHeight = kBlock / 32;
+    c.usePersistentThreads = (kernel == Kernel_PersistentSpeculative) ? 1 : 0;
+    return c;
+}
+
+cudaError_t launch_trace(const TraceLaunch& a, int* launches)
+{
+    if (a.numRays <= 0) { if (launches) *launches = 0; return cudaSuccess; }
+    const bool c2 = (a.layout == Layout_Compact2);
+    switch (a.kernel) {
+    case Kernel_PersistentSpeculative:
+        return c2 ? launch_one<Layout_Compact2, true>(a, launches) : launch_one<Layout_Compact, true>(a, launches);
+    case Kernel_PlainSpeculative:
+        return c2 ? launch_one<Layout_Compact2, false>(a, launches) : launch_one<Layout_Compact, false>(a, launches);
+    default:
+        return cudaErrorInvalidValue;
+    }
+}
+
+} // namespace nt

@@ -1,0 +1,424 @@
+"""Host-side mirror of the reference's operator interface for the tracing path.
+
+Same class and method names, argument meaning and error behaviour as the reference's C++ host
+(``namespace FW``), implemented on top of the C ABI (``capi``) with torch tensors as device
+memory.  Nothing here computes on the CPU: ray generation, BVH build and traversal all run in the
+CUDA library; this module only owns buffers and sequencing.
+
+Reference interfaces mirrored:
+  RayBuffer        src/rt/ray/RayBuffer.hpp:38-195, RayBuffer.cpp:38-62
+  CudaBVH / CudaAS src/rt/cuda/CudaBVH.hpp:137-152, CudaBVH.cpp:105-125 (stream ctor / serialize)
+  HLBVHBuilder     src/rt/bvh/HLBVH/HLBVHBuilder.hpp:25-41 (HLBVHParams, CudaBVH subclass)
+  CudaBVHTracer    src/rt/cuda/CudaVirtualTracer.hpp:11-26, CudaBVHTracer.cpp:52-168
+  RayGen           src/rt/ray/RayGen.cpp:45-74 (primary), :198-232 (ao), :582-600 (batching)
+  Scene            src/rt/Scene.cpp:38,101-117 (triVtxIndex, vtxPos, triNormal, bbox)
+  Renderer         src/rt/cuda/Renderer.cpp:138-305 (setParams/getCudaBVH), :405-579 (frame loop), :676-710
+"""
+from __future__ import annotations
+
+import io
+import struct
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import camera as _camera
+from . import capi
+from .capi import NtError
+
+BVHLayout_Compact = capi.LAYOUT_COMPACT
+BVHLayout_Compact2 = capi.LAYOUT_COMPACT2
+
+_torch = None
+
+
+def torch():
+    global _torch
+    if _torch is None:
+        import torch as t
+        _torch = t
+    return _torch
+
+
+_device_index = None
+
+
+def init(device: int = 0):
+    """CudaModule::staticInit: pick the device for this process (one GPU per process)."""
+    global _device_index
+    capi.init(device)
+    t = torch()
+    t.cuda.set_device(device)
+    _device_index = device
+
+
+def device():
+    if _device_index is None:
+        raise NtError("ntrace_b200.host.init() has not been called")
+    return torch().device("cuda", _device_index)
+
+
+def _sync():
+    # the library runs on its own stream and is synchronous; torch producers must be drained before a call
+    torch().cuda.synchronize()
+
+
+# --------------------------------------------------------------------------------------------------
+class RayBuffer:
+    """Rays (N x 8 f32), results (N x 4 i32) and the id<->slot maps; storage only grows."""
+
+    def __init__(self, n: int = 0, closest_hit: bool = True):
+        self._size = 0
+        self._cap = 0
+        self._rays = self._results = self._id2slot = self._slot2id = None
+        self._need_closest = closest_hit
+        self.resize(n)
+
+    def getSize(self) -> int:
+        return self._size
+
+    def resize(self, n: int):
+        if n < 0:
+            raise NtError("RayBuffer: negative size")
+        if n > self._cap:
+            t, dev = torch(), device()
+            cap = max(n, 1)
+            old = (self._rays, self._results, self._id2slot, self._slot2id)
+            self._rays = t.zeros((cap, 8), dtype=t.float32, device=dev)
+            self._results = t.zeros((cap, 4), dtype=t.int32, device=dev)
+            self._id2slot = t.zeros(cap, dtype=t.int32, device=dev)
+            self._slot2id = t.zeros(cap, dtype=t.int32, device=dev)
+            if old[0] is not None and self._size:
+                for new, o in zip((self._rays, self._results, self._id2slot, self._slot2id), old):
+                    new[: self._size].copy_(o[: self._size])
+            self._cap = cap
+        self._size = n
+
+    def setNeedClosestHit(self, c: bool):
+        self._need_closest = bool(c)
+
+    def getNeedClosestHit(self) -> bool:
+        return self._need_closest
+
+    # device views (torch tensors over the first getSize() slots)
+    def getRayBuffer(self):
+        return self._rays[: self._size]
+
+    def getResultBuffer(self):
+        return self._results[: self._size]
+
+    def getIDToSlotBuffer(self):
+        return self._id2slot[: self._size]
+
+    def getSlotToIDBuffer(self):
+        return self._slot2id[: self._size]
+
+    def setRays(self, rays_np):
+        """Upload host rays (N x 8 float32); ids become the identity."""
+        rays_np = np.ascontiguousarray(rays_np, dtype=np.float32).reshape(-1, 8)
+        self.resize(len(rays_np))
+        t = torch()
+        self._rays[: self._size].copy_(t.from_numpy(rays_np))
+        ar = t.arange(self._size, dtype=t.int32, device=device())
+        self._id2slot[: self._size].copy_(ar)
+        self._slot2id[: self._size].copy_(ar)
+
+    def rays_host(self) -> np.ndarray:
+        return self.getRayBuffer().cpu().numpy()
+
+    def results_host(self) -> np.ndarray:
+        return self.getResultBuffer().cpu().numpy()
+
+
+# --------------------------------------------------------------------------------------------------
+class Scene:
+    """Flat scene buffers the path needs: triVtxIndex, vtxPos, triNormal, bbox over vertices."""
+
+    def __init__(self, verts, tris):
+        t = torch()
+        self.verts_host = np.ascontiguousarray(verts, dtype=np.float32).reshape(-1, 3)
+        self.tris_host = np.ascontiguousarray(tris, dtype=np.int32).reshape(-1, 3)
+        self.vtxPos = t.from_numpy(self.verts_host).to(device())
+        self.triVtxIndex = t.from_numpy(self.tris_host).to(device())
+        self.triNormal = t.empty((len(self.tris_host), 3), dtype=t.float32, device=device())
+        _sync()
+        capi.tri_normals(self.vtxPos, self.triVtxIndex, self.triNormal)
+        self.bboxMin = self.verts_host.min(0).astype(np.float32)
+        self.bboxMax = self.verts_host.max(0).astype(np.float32)
+
+    def getNumTriangles(self) -> int:
+        return len(self.tris_host)
+
+    def getNumVertices(self) -> int:
+        return len(self.verts_host)
+
+    def getBBox(self):
+        return self.bboxMin, self.bboxMax
+
+
+# --------------------------------------------------------------------------------------------------
+class CudaBVH:
+    """The three CudaBVH buffers (nodes, triWoop, triIndex) plus the layout tag."""
+
+    def __init__(self, nodes=None, woop=None, tri_index=None, layout: int = BVHLayout_Compact):
+        self.layout = layout
+        self.nodes = None if nodes is None else np.ascontiguousarray(nodes).view(np.int32).reshape(-1)
+        self.woop = None if woop is None else np.ascontiguousarray(woop).view(np.int32).reshape(-1)
+        self.tri_index = None if tri_index is None else np.ascontiguousarray(tri_index, dtype=np.int32).reshape(-1)
+        self.resident = False        # True when the buffers live only in the library (GPU build)
+        self.gpu_seconds = 0.0
+
+    def getLayout(self) -> int:
+        return self.layout
+
+    def getNodeBuffer(self):
+        self._materialise()
+        return self.nodes
+
+    def getTriWoopBuffer(self):
+        self._materialise()
+        return self.woop
+
+    def getTriIndexBuffer(self):
+        self._materialise()
+        return self.tri_index
+
+    def _materialise(self):
+        if self.nodes is None and self.resident:
+            self.nodes, self.woop, self.tri_index, self.layout = capi.bvh_download()
+
+    # bvhcache format: S32 layout, then 3 x (S64 size, bytes)  (CudaBVH.cpp:105-125, Buffer.cpp:349-381)
+    def serialize(self, out: io.BufferedIOBase):
+        self._materialise()
+        out.write(struct.pack("<i", self.layout))
+        for b in (self.nodes, self.woop, self.tri_index):
+            raw = b.tobytes()
+            out.write(struct.pack("<q", len(raw)))
+            out.write(raw)
+
+    @staticmethod
+    def deserialize(inp: io.BufferedIOBase) -> "CudaBVH":
+        (layout,) = struct.unpack("<i", inp.read(4))
+        bufs = []
+        for _ in range(3):
+            (n,) = struct.unpack("<q", inp.read(8))
+            bufs.append(np.frombuffer(inp.read(n), dtype=np.int32).copy())
+        return CudaBVH(bufs[0], bufs[1], bufs[2], layout)
+
+
+@dataclass
+class HLBVHParams:
+    hlbvh: bool = True
+    hlbvhBits: int = 4
+    leafSize: int = 8
+    epsilon: float = 0.001
+
+
+class HLBVHBuilder(CudaBVH):
+    """GPU LBVH / HLBVH build straight into the Compact layout; the result stays on the device."""
+
+    def __init__(self, scene: Scene, params: HLBVHParams = HLBVHParams()):
+        super().__init__(layout=BVHLayout_Compact)
+        lbvh = (not params.hlbvh) or params.hlbvhBits == 10          # HLBVHBuilder.cpp:44-47
+        _sync()
+        self.gpu_seconds = capi.bvh_build(capi.BUILDER_LBVH if lbvh else capi.BUILDER_HLBVH, scene.vtxPos, scene.triVtxIndex,
+                                          scene.bboxMin, scene.bboxMax, params.hlbvhBits, params.leafSize, params.epsilon)
+        self.resident = True
+        self.num_tris = scene.getNumTriangles()
+
+    def getGPUTime(self) -> float:
+        return self.gpu_seconds
+
+
+# --------------------------------------------------------------------------------------------------
+class CudaBVHTracer:
+    """CudaVirtualTracer for BVHs: setKernel / getDesiredBVHLayout / setBVH / traceBatch."""
+
+    def __init__(self):
+        self._bvh = None
+        self._kernel = None
+        self.setKernel("b200_persistent_speculative_while_while")
+
+    def setKernel(self, name: str):
+        if name == self._kernel:
+            return
+        capi.set_kernel(name)
+        self._kernel = name
+        self._config = capi.kernel_config()
+
+    def getDesiredBVHLayout(self) -> int:
+        return capi.desired_layout()
+
+    def getKernelConfig(self) -> dict:
+        return dict(self._config)
+
+    def setBVH(self, bvh: CudaBVH):
+        self._bvh = bvh
+        if bvh is not None and not bvh.resident:
+            capi.bvh_upload(bvh.layout, bvh.nodes, bvh.woop, bvh.tri_index)
+
+    def traceBatch(self, rays: RayBuffer) -> float:
+        """Returns the kernel time in seconds (CUDA events around the launch only)."""
+        n = rays.getSize()
+        if n == 0:
+            return 0.0
+        if self._bvh is None:
+            raise NtError("CudaBVHTracer: No BVH!")
+        if self._bvh.getLayout() != self.getDesiredBVHLayout():
+            raise NtError("CudaBVHTracer: Incorrect BVH layout!")
+        _sync()
+        return capi.trace_batch(rays.getRayBuffer(), rays.getResultBuffer(), n, rays.getNeedClosestHit())
+
+
+# --------------------------------------------------------------------------------------------------
+class RayGen:
+    def __init__(self, maxBatchSize: int = 1 << 20):
+        self.m_maxBatchSize = maxBatchSize
+        self.m_aoStartIdx = 0
+
+    def primary(self, orays: RayBuffer, origin, nscreenToWorld, w: int, h: int, maxDist: float, randomSeed: int = 0):
+        orays.resize(w * h)
+        orays.setNeedClosestHit(True)
+        _sync()
+        capi.raygen_primary(orays.getRayBuffer(), orays.getIDToSlotBuffer(), orays.getSlotToIDBuffer(), origin, nscreenToWorld,
+                            w, h, maxDist, randomSeed)
+
+    def batching(self, numInputRays: int, numSamples: int, startIdx: int, newBatch: bool):
+        """RayGen::batching -> (continues, lo, hi, startIdx, newBatch)."""
+        if newBatch:
+            newBatch = False
+            startIdx = 0
+        if startIdx == numInputRays:
+            return False, 0, 0, startIdx, newBatch
+        lo = startIdx
+        hi = min(numInputRays, lo + self.m_maxBatchSize // numSamples)
+        return True, lo, hi, hi, newBatch
+
+    def ao(self, orays: RayBuffer, irays: RayBuffer, scene: Scene, numSamples: int, maxDist: float, newBatch: bool, randomSeed: int = 0):
+        """RayGen::ao -> (generated, newBatch).  Output needs any-hit only; the caller flips it for diffuse."""
+        ok, lo, hi, self.m_aoStartIdx, newBatch = self.batching(irays.getSize(), numSamples, self.m_aoStartIdx, newBatch)
+        if not ok:
+            return False, newBatch
+        orays.resize((hi - lo) * numSamples)
+        orays.setNeedClosestHit(False)
+        _sync()
+        capi.raygen_ao(orays.getRayBuffer(), orays.getIDToSlotBuffer(), orays.getSlotToIDBuffer(), irays.getRayBuffer(),
+                       irays.getResultBuffer(), scene.triNormal, lo, hi - lo, numSamples, maxDist, randomSeed)
+        return True, newBatch
+
+
+# --------------------------------------------------------------------------------------------------
+RayType_Primary, RayType_AO, RayType_Diffuse = "primary", "AO", "diffuse"
+
+# seed used when Raygen.random is false: the reference hashes Random(0).getU32() (a RANROT value);
+# both sides of every parity test use this constant instead.
+FIXED_AO_SEED = 0x9E3779B9
+
+
+@dataclass
+class RendererParams:
+    kernelName: str = "b200_persistent_speculative_while_while"
+    rayType: str = RayType_Primary
+    numSamples: int = 32
+    aoRadius: float = 5.0
+    sortSecondary: bool = False
+
+
+@dataclass
+class BuildSettings:
+    builder: str = "HLBVH"            # Renderer.builder: HLBVH | LBVH (GPU); prebuilt CudaBVH via setCudaBVH
+    hlbvh: HLBVHParams = field(default_factory=HLBVHParams)
+
+
+class Renderer:
+    """Frame/batch loop of the reference Renderer restricted to the tracing path."""
+
+    def __init__(self, build: BuildSettings = BuildSettings()):
+        self.m_raygen = RayGen(1 << 20)                               # Renderer.cpp:45
+        self.m_cudaTracer = CudaBVHTracer()
+        self.m_params = RendererParams()
+        self.m_build = build
+        self.m_scene = None
+        self.m_bvh = None
+        self.m_primaryRays = RayBuffer()
+        self.m_secondaryRays = RayBuffer()
+        self.m_cameraFar = 0.0
+        self.m_newBatch = True
+        self.m_batchRays = None
+        self.m_batchStart = 0
+
+    def setScene(self, scene: Scene):
+        self.m_scene = scene
+        self.m_bvh = None
+
+    def setParams(self, params: RendererParams):
+        self.m_params = params
+        self.m_cudaTracer.setKernel(params.kernelName)
+
+    def setCudaBVH(self, bvh: CudaBVH):
+        """Use a prebuilt CudaBVH (e.g. a bvhcache file or a CPU-built SplitBVH flattened by the caller)."""
+        self.m_bvh = bvh
+
+    def getCudaBVH(self) -> CudaBVH:
+        if self.m_bvh is not None:
+            return self.m_bvh
+        b = self.m_build.builder
+        if b == "HLBVH":
+            self.m_bvh = HLBVHBuilder(self.m_scene, self.m_build.hlbvh)     # Renderer.cpp:201-209
+        elif b == "LBVH":
+            p = HLBVHParams(False, 10, self.m_build.hlbvh.leafSize, self.m_build.hlbvh.epsilon)
+            self.m_bvh = HLBVHBuilder(self.m_scene, p)
+        else:
+            raise NtError(f"Unsupported BVH builder {b}")
+        return self.m_bvh
+
+    def beginFrame(self, cam: "_camera.Camera", w: int, h: int):
+        self.m_cudaTracer.setBVH(self.getCudaBVH())
+        n2w = _camera.nscreen_to_world(cam, w, h)
+        self.m_raygen.primary(self.m_primaryRays, cam.position, n2w, w, h, cam.far, 0)
+        if self.m_params.rayType != RayType_Primary:                   # Renderer.cpp:481-484
+            self.m_cudaTracer.traceBatch(self.m_primaryRays)
+        self.m_cameraFar = cam.far
+        self.m_newBatch = True
+        self.m_batchRays = None
+        self.m_batchStart = 0
+
+    def nextBatch(self) -> bool:
+        if self.m_batchRays is not None:
+            self.m_batchStart += self.m_batchRays.getSize()
+        self.m_batchRays = None
+        rt = self.m_params.rayType
+        if rt == RayType_Primary:
+            if not self.m_newBatch:
+                return False
+            self.m_newBatch = False
+            self.m_batchRays = self.m_primaryRays
+        elif rt == RayType_AO:
+            ok, self.m_newBatch = self.m_raygen.ao(self.m_secondaryRays, self.m_primaryRays, self.m_scene, self.m_params.numSamples,
+                                                  self.m_params.aoRadius, self.m_newBatch, FIXED_AO_SEED)
+            if not ok:
+                return False
+            self.m_batchRays = self.m_secondaryRays
+        elif rt == RayType_Diffuse:
+            ok, self.m_newBatch = self.m_raygen.ao(self.m_secondaryRays, self.m_primaryRays, self.m_scene, self.m_params.numSamples,
+                                                  self.m_cameraFar, self.m_newBatch, FIXED_AO_SEED)
+            if not ok:
+                return False
+            self.m_secondaryRays.setNeedClosestHit(True)
+            self.m_batchRays = self.m_secondaryRays
+        else:
+            raise NtError(f"unsupported ray type {rt}")
+        return True
+
+    def traceBatch(self) -> float:
+        if self.m_batchRays is None:
+            raise NtError("Renderer: no batch")
+        return self.m_cudaTracer.traceBatch(self.m_batchRays)
+
+    def getTotalNumRays(self) -> int:
+        """Rays counted by the benchmark: w*h for primary, primary hits x samples otherwise (Renderer.cpp:676-710)."""
+        if self.m_params.rayType == RayType_Primary:
+            return self.m_primaryRays.getSize()
+        _sync()
+        hits = capi.count_hits(self.m_primaryRays.getResultBuffer(), self.m_primaryRays.getSize())
+        return hits * self.m_params.numSamples

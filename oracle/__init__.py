@@ -230,19 +230,21 @@ class Canonical:
     boxes: np.ndarray       # [numInner, 12] node words 0..11 as floats
     leaf_sizes: np.ndarray  # [numLeaves], traversal order
     tris: np.ndarray        # concatenated leaf triangle ids, traversal order
+    woop: np.ndarray        # [numTris, 12] Woop rows of the leaf triangles, traversal order
 
 
 def canonical(nodes, woop, tri_index) -> Canonical:
     """Numbering-independent serialisation of a Compact tree."""
     nodes, woop, tri_index = _i32(nodes), _i32(woop), _i32(tri_index)
     sizes = np.zeros(3, dtype=np.int64)
-    lib().orc_canonical(_p(nodes), _p(woop), _p(tri_index), _p(sizes), None, None, None, None)
+    lib().orc_canonical(_p(nodes), _p(woop), _p(tri_index), _p(sizes), None, None, None, None, None)
     inner = np.zeros((sizes[0], 3), dtype=np.int32)
     boxes = np.zeros((sizes[0], 12), dtype=np.float32)
     ls = np.zeros(sizes[1], dtype=np.int32)
     tr = np.zeros(sizes[2], dtype=np.int32)
-    lib().orc_canonical(_p(nodes), _p(woop), _p(tri_index), _p(sizes), _p(inner), _p(boxes), _p(ls), _p(tr))
-    return Canonical(inner, boxes, ls, tr)
+    wo = np.zeros((sizes[2], 12), dtype=np.float32)
+    lib().orc_canonical(_p(nodes), _p(woop), _p(tri_index), _p(sizes), _p(inner), _p(boxes), _p(ls), _p(tr), _p(wo))
+    return Canonical(inner, boxes, ls, tr, wo)
 
 
 # ----------------------------------------------------------------------------------------------

@@ -166,7 +166,7 @@ void orc_lbvh_copy(void* p, void* nodes, void* woop, void* triIndex, uint32_t* s
 // canonical form of any Compact tree: call once with null outputs to get sizes
 // sizes: [numInner, numLeaves, numTris]
 void orc_canonical(const int32_t* nodes, const int32_t* woop, const int32_t* triIndex, int64_t* sizes,
-                   int32_t* inner, float* boxes, int32_t* leafSizes, int32_t* tris)
+                   int32_t* inner, float* boxes, int32_t* leafSizes, int32_t* tris, float* woopOut)
 {
     Canonical c;
     canonicalize(nodes, woop, triIndex, c);
@@ -175,6 +175,7 @@ void orc_canonical(const int32_t* nodes, const int32_t* woop, const int32_t* tri
     if (boxes) std::memcpy(boxes, c.boxes.data(), c.boxes.size() * 4);
     if (leafSizes) std::memcpy(leafSizes, c.leafSizes.data(), c.leafSizes.size() * 4);
     if (tris) std::memcpy(tris, c.tris.data(), c.tris.size() * 4);
+    if (woopOut) std::memcpy(woopOut, c.woop.data(), c.woop.size() * 4);
 }
 
 // ---------------- ray generation --------------------------------------------------------------

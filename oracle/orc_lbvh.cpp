@@ -451,7 +451,11 @@ int canon_rec(const int32_t* nodes, const int32_t* woop, const int32_t* triIndex
 {
     if (addr < 0) {
         int nt = 0;
-        for (int a = ~addr; (uint32_t)woop[a * 4] != 0x80000000u; a += 3) { out.tris.push_back(triIndex[a]); nt++; }
+        for (int a = ~addr; (uint32_t)woop[a * 4] != 0x80000000u; a += 3) {
+            out.tris.push_back(triIndex[a]);
+            for (int k = 0; k < 12; k++) out.woop.push_back(u2f((uint32_t)woop[a * 4 + k]));
+            nt++;
+        }
         out.leafSizes.push_back(nt);
         return nt;
     }

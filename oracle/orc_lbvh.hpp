@@ -42,6 +42,7 @@ struct Canonical {
     std::vector<float> boxes;        // 12 per inner node
     std::vector<int32_t> leafSizes;
     std::vector<int32_t> tris;
+    std::vector<float> woop;         // 12 per leaf triangle, traversal order
 };
 void canonicalize(const int32_t* nodes, const int32_t* woop, const int32_t* triIndex, Canonical& out);
 

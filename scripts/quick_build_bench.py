@@ -1,0 +1,28 @@
+"""Early measurement helper: GPU LBVH build time / Mtris/s for a few sizes. Usage: python scripts/quick_build_bench.py"""
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from ntrace_b200 import capi, host, scenes  # noqa: E402
+
+
+def main():
+    import torch
+    host.init(0)
+    for name, gen in [("room283k", lambda: scenes.room(283_000, 2)), ("soup1M", lambda: scenes.soup_uniform(1_000_000, 5)),
+                      ("soup10M", lambda: scenes.soup_uniform(10_000_000, 5))]:
+        v, t = gen()
+        lo, hi = scenes.bbox(v)
+        dv = torch.from_numpy(v).cuda(); dt = torch.from_numpy(t).cuda()
+        torch.cuda.synchronize()
+        for leaf in (8, 1):
+            ts = [capi.bvh_build(capi.BUILDER_LBVH, dv, dt, lo, hi, 10, leaf, 0.001) for _ in range(5)]
+            (nb, wb, ib), _ = capi.bvh_sizes()
+            print(f"{name} leaf={leaf}: {np.min(ts[1:]) * 1e3:.3f} ms best ({len(t) / np.min(ts[1:]) * 1e-6:.1f} Mtris/s), first {ts[0] * 1e3:.2f} ms, "
+                  f"nodes {nb // 64}, launches so far {capi.launch_count()}", flush=True)
+
+
+if __name__ == "__main__":
+    main()

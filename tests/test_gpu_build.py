@@ -1,0 +1,161 @@
+"""GPU parity of the LBVH builder against the CPU restatement of the reference HLBVHBuilder:
+Morton codes and sort order bit-exact, the (start, split, end) range tree identical (compared in the
+numbering-independent canonical form of SURVEY.md App. B-5), child boxes and Woop rows equal, SAH equal."""
+import numpy as np
+import pytest
+
+from ntrace_b200 import camera, capi, scenes
+
+pytestmark = pytest.mark.gpu
+
+
+def _gpu_build(gpu_host, verts, tris, lo, hi, leaf=8, eps=0.001):
+    sec = capi.bvh_build(capi.BUILDER_LBVH, np.ascontiguousarray(verts, np.float32), np.ascontiguousarray(tris, np.int32), lo, hi, 10, leaf, eps)
+    nodes, woop, idx, layout = capi.bvh_download()
+    assert layout == capi.LAYOUT_COMPACT
+    keys, order = capi.bvh_build_debug(len(tris))
+    return nodes, woop, idx, keys, order, sec
+
+
+def _assert_same_tree(orc, gpu, ref):
+    gn, gw, gi = gpu
+    cg = orc.canonical(gn, gw, gi)
+    cr = orc.canonical(ref.nodes, ref.woop, ref.tri_index)
+    assert np.array_equal(cg.inner, cr.inner), "range tree differs"
+    assert np.array_equal(cg.leaf_sizes, cr.leaf_sizes)
+    assert np.array_equal(cg.tris, cr.tris)
+    assert np.array_equal(cg.boxes, cr.boxes), "child boxes differ"          # value equality (-0 == +0)
+    assert np.array_equal(cg.woop.view(np.uint32), cr.woop.view(np.uint32)), "Woop rows differ"
+    assert len(gn) == len(ref.nodes) and len(gw) == len(ref.woop) and len(gi) == len(ref.tri_index)
+
+
+def _cells_scene(codes_xyz, reps):
+    """Tiny triangles centred in grid cells of a [0,1024]^3 box -> exact, chosen Morton codes."""
+    verts, tris = [], []
+    for (x, y, z), r in zip(codes_xyz, reps):
+        for k in range(r):
+            c = np.array([x + 0.5, y + 0.5, z + 0.5], np.float32)
+            d = np.float32(0.01 + 0.0001 * (k % 7))
+            base = len(verts)
+            verts += [c + (-d, -d, 0), c + (d, -d, 0), c + (0, d, 0)]
+            tris.append((base, base + 1, base + 2))
+    return np.array(verts, np.float32), np.array(tris, np.int32), np.zeros(3, np.float32), np.full(3, 1024.0, np.float32)
+
+
+def _demorton(code):
+    def compact(v):
+        r = 0
+        for i in range(10):
+            r |= ((v >> (3 * i)) & 1) << i
+        return r
+    return compact(code), compact(code >> 1), compact(code >> 2)
+
+
+@pytest.mark.parametrize("leaf", [1, 4, 8])
+def test_lbvh_matches_reference_restatement(gpu_host, orc, leaf):
+    verts, tris = scenes.room(20_000, seed=7, wall_frac=0.3)
+    lo, hi = scenes.bbox(verts)
+    nodes, woop, idx, keys, order, sec = _gpu_build(gpu_host, verts, tris, lo, hi, leaf)
+    ref = orc.lbvh_build(verts, tris, lo, hi, hlbvh=False, leaf_size=leaf, epsilon=0.001)
+    assert np.array_equal(np.sort(orc.morton(verts, tris, lo, hi)), keys)
+    assert np.array_equal(keys, ref.sorted_keys), "Morton codes / sort differ"
+    assert np.array_equal(order, ref.sorted_idx), "sort is not stable"
+    _assert_same_tree(orc, (nodes, woop, idx), ref)
+    sg, sr = orc.compact_sah(nodes, woop), orc.compact_sah(ref.nodes, ref.woop)
+    assert abs(sg["sah"] - sr["sah"]) <= 0.005 * sr["sah"]
+    assert sg["num_tris"] == len(tris)
+
+
+def test_lbvh_clustered_soup_with_duplicates(gpu_host, orc):
+    verts, tris = scenes.soup_uniform(60_000, seed=9, clustered=True)
+    lo, hi = scenes.bbox(verts)
+    # shrink precision so that many triangles share a cell: quantise against a much larger box
+    lo2, hi2 = lo - 40.0, hi + 40.0
+    nodes, woop, idx, keys, order, _ = _gpu_build(gpu_host, verts, tris, lo2, hi2, 4)
+    ref = orc.lbvh_build(verts, tris, lo2, hi2, hlbvh=False, leaf_size=4)
+    assert (np.diff(keys.astype(np.int64)) == 0).sum() > 1000, "test needs duplicate codes"
+    assert np.array_equal(keys, ref.sorted_keys) and np.array_equal(order, ref.sorted_idx)
+    _assert_same_tree(orc, (nodes, woop, idx), ref)
+
+
+@pytest.mark.parametrize("n,leaf", [(1, 8), (2, 8), (5, 8), (9, 8), (3, 1), (64, 1)])
+def test_lbvh_tiny_inputs(gpu_host, orc, n, leaf):
+    verts, tris = scenes.soup_uniform(n, seed=3)
+    lo, hi = scenes.bbox(verts)
+    nodes, woop, idx, keys, order, _ = _gpu_build(gpu_host, verts, tris, lo, hi, leaf)
+    ref = orc.lbvh_build(verts, tris, lo, hi, hlbvh=False, leaf_size=leaf)
+    _assert_same_tree(orc, (nodes, woop, idx), ref)
+
+
+def test_lbvh_all_identical_keys_median_rule(gpu_host, orc):
+    v, t, lo, hi = _cells_scene([(5, 6, 7)], [1000])
+    nodes, woop, idx, keys, order, _ = _gpu_build(gpu_host, v, t, lo, hi, 8)
+    assert len(np.unique(keys)) == 1
+    ref = orc.lbvh_build(v, t, lo, hi, hlbvh=False, leaf_size=8)
+    _assert_same_tree(orc, (nodes, woop, idx), ref)
+    c = orc.canonical(nodes, woop, idx)
+    assert (c.inner[:, 2] == -1).all()              # `level % 3` with level == -1
+
+
+def test_lbvh_forced_leaves_29_levels_down(gpu_host, orc):
+    # keys 0 (x M), 1, 2, 4, ..., 2^29: a radix chain 29 levels deep ending in a long duplicate run
+    cells = [_demorton(0)] + [_demorton(1 << j) for j in range(30)]
+    for m, leaf in [(100, 8), (37, 1)]:
+        v, t, lo, hi = _cells_scene(cells, [m] + [1] * 30)
+        nodes, woop, idx, keys, order, _ = _gpu_build(gpu_host, v, t, lo, hi, leaf)
+        assert keys[m] == 1 and keys[-1] == (1 << 29)
+        ref = orc.lbvh_build(v, t, lo, hi, hlbvh=False, leaf_size=leaf)
+        _assert_same_tree(orc, (nodes, woop, idx), ref)
+        assert orc.canonical(nodes, woop, idx).leaf_sizes.max() == m     # the forced leaf holds the whole run
+    # run entered 20 levels down, bisected for 9 more levels, then forced
+    cells = [_demorton(0)] + [_demorton(1 << j) for j in range(10, 30)]
+    v, t, lo, hi = _cells_scene(cells, [10_000] + [1] * 20)
+    nodes, woop, idx, keys, order, _ = _gpu_build(gpu_host, v, t, lo, hi, 4)
+    ref = orc.lbvh_build(v, t, lo, hi, hlbvh=False, leaf_size=4)
+    _assert_same_tree(orc, (nodes, woop, idx), ref)
+    assert orc.canonical(nodes, woop, idx).leaf_sizes.max() > 4
+
+
+def test_lbvh_planar_scene_zero_extent_axis(gpu_host, orc):
+    # all z equal: step.z == 0, the quantiser sees 0/0 (reference: calcMorton has no guard)
+    rng = np.random.default_rng(5)
+    n = 3000
+    c = rng.uniform(0, 10, size=(n, 2)).astype(np.float32)
+    verts = np.zeros((n * 3, 3), np.float32)
+    verts[0::3, :2] = c; verts[1::3, :2] = c + (0.1, 0); verts[2::3, :2] = c + (0, 0.1)
+    verts[:, 2] = 2.5
+    tris = np.arange(n * 3, dtype=np.int32).reshape(n, 3)
+    lo, hi = scenes.bbox(verts)
+    nodes, woop, idx, keys, order, _ = _gpu_build(gpu_host, verts, tris, lo, hi, 8)
+    ref = orc.lbvh_build(verts, tris, lo, hi, hlbvh=False, leaf_size=8)
+    assert np.array_equal(keys, ref.sorted_keys)
+    _assert_same_tree(orc, (nodes, woop, idx), ref)
+
+
+def test_gpu_built_bvh_traces_like_cpu(gpu_host, orc):
+    verts, tris = scenes.room(20_000, seed=7, wall_frac=0.3)
+    scene = gpu_host.Scene(verts, tris)
+    bvh = gpu_host.HLBVHBuilder(scene, gpu_host.HLBVHParams(False, 10, 8, 0.001))
+    assert bvh.getGPUTime() > 0
+    cam = camera.named_camera("conference")
+    w, h = 256, 192
+    tracer = gpu_host.CudaBVHTracer()
+    tracer.setBVH(bvh)
+    rays = gpu_host.RayBuffer()
+    gpu_host.RayGen().primary(rays, cam.position, camera.nscreen_to_world(cam, w, h), w, h, cam.far)
+    tracer.traceBatch(rays)
+    got = rays.results_host()
+    ref = orc.compact_trace(bvh.getNodeBuffer(), bvh.getTriWoopBuffer(), bvh.getTriIndexBuffer(), rays.rays_host(), True)
+    assert (got[:, 0] == ref[:, 0]).mean() >= 0.9999
+    brute = orc.brute_trace(verts, tris, rays.rays_host()[:4096], True)
+    assert (got[:4096, 0] == brute[:, 0]).mean() >= 0.999
+
+
+def test_hlbvh_builder_reports_unimplemented_loudly(gpu_host):
+    from ntrace_b200 import NtError
+    verts, tris = scenes.soup_uniform(100, seed=1)
+    lo, hi = scenes.bbox(verts)
+    try:
+        capi.bvh_build(capi.BUILDER_HLBVH, verts, tris, lo, hi, 4, 8, 0.001)
+    except NtError as e:
+        assert "HLBVH" in str(e)
