@@ -52,6 +52,17 @@ const char* nt_last_error(void);
 /* number of this library's kernel launches since nt_init (bench.py's gpu_launches). */
 int64_t nt_launch_count(void);
 
+/* CUDA-event timing on the library's stream (reference: CudaKernel::launchTimed brackets launches with
+ * cuEventRecord / cuEventElapsedTime, src/framework/gpu/CudaKernel.cpp:188-221).  slot in [0, 8). */
+int nt_event_record(int slot);
+/* waits for slotB, then returns the device time between the two records. */
+int nt_event_elapsed(int slotA, int slotB, float* outSeconds);
+/* Submission mode.  0 (default) = reference behaviour, every call returns with its outputs complete.
+ * 1 = deferred: nt_trace_batch on DEVICE buffers only enqueues (outSeconds = 0) and nt_synchronize() waits;
+ * calls with host buffers stay synchronous. */
+int nt_set_deferred(int enabled);
+int nt_synchronize(void);
+
 /* ---- kernel selection: CudaBVHTracer::setKernel + queryConfig (CudaBVHTracer.cpp:52-84) --- */
 /* Names: "b200_persistent_speculative_while_while" (default), "b200_speculative_while_while",
  * and the reference's kernel file names as aliases: "fermi_speculative_while_while" (Compact),

@@ -24,6 +24,7 @@ BUILDER_HLBVH = 1
 # every symbol include/ntrace_b200.h declares (checked by tests/test_abi.py)
 EXPORTS = [
     "nt_init", "nt_shutdown", "nt_last_error", "nt_launch_count",
+    "nt_event_record", "nt_event_elapsed", "nt_set_deferred", "nt_synchronize",
     "nt_set_kernel", "nt_desired_layout", "nt_kernel_config",
     "nt_bvh_upload", "nt_bvh_alloc", "nt_bvh_build", "nt_bvh_sizes", "nt_bvh_download",
     "nt_bvh_device_ptrs", "nt_bvh_build_debug",
@@ -98,6 +99,24 @@ def shutdown():
 
 def launch_count() -> int:
     return int(lib().nt_launch_count())
+
+
+def event_record(slot: int):
+    _check(lib().nt_event_record(C.c_int(slot)))
+
+
+def event_elapsed(a: int, b: int) -> float:
+    sec = C.c_float(0.0)
+    _check(lib().nt_event_elapsed(C.c_int(a), C.c_int(b), C.byref(sec)))
+    return float(sec.value)
+
+
+def set_deferred(enabled: bool):
+    _check(lib().nt_set_deferred(C.c_int(1 if enabled else 0)))
+
+
+def synchronize():
+    _check(lib().nt_synchronize())
 
 
 # ---- kernel selection -----------------------------------------------------------------------------

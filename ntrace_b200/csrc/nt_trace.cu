@@ -23,6 +23,7 @@
 // buffers.  The slab test keeps the reference GPU form n*idir - ood (fermi...cu:120-145) with FMA: it only
 // decides which nodes are visited, never what a hit is.
 #include "nt_common.cuh"
+#include <cstdlib>
 
 namespace nt {
 
@@ -221,31 +222,50 @@ trace_kernel(int numRays, int anyHit,
 }
 
 constexpr int kBlock = 128;
-constexpr int kSmemStack = 16;
+
+// Tuning knobs (defaults chosen from the ncu captures in profiles/; the NT_TRACE_* environment variables exist
+// for experiments only): entries of the traversal stack kept in shared memory, and the shared-memory carveout
+// that decides how many CTAs fit next to the L1.
+struct Tuning { int smemStack; int carveout; };
+Tuning tuning()
+{
+    static Tuning t = [] {
+        Tuning r{8, 20};
+        if (const char* e = getenv("NT_TRACE_SMEM")) r.smemStack = atoi(e);
+        if (const char* e = getenv("NT_TRACE_CARVEOUT")) r.carveout = atoi(e);
+        return r;
+    }();
+    return t;
+}
+
+template <int LAYOUT, int SMEM_N, bool PERSISTENT>
+cudaError_t launch_variant(const TraceLaunch& a, int* launches)
+{
+    auto kern = trace_kernel<LAYOUT, kBlock, SMEM_N, PERSISTENT>;
+    static int blocksPerSM = 0;
+    if (!blocksPerSM) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, tuning().carveout);
+        if (e != cudaSuccess) return e;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSM, kern, kBlock, 0);
+        if (e != cudaSuccess) return e;
+        if (blocksPerSM < 1) blocksPerSM = 1;
+    }
+    int grid = (a.numRays + kBlock - 1) / kBlock;
+    if (PERSISTENT && grid > a.numSMs * blocksPerSM) grid = a.numSMs * blocksPerSM;   // one resident wave
+    kern<<<grid, kBlock, 0, a.stream>>>(a.numRays, a.anyHit, a.rays, a.results, a.nodes, a.woop, a.triIndices, a.warpCounter);
+    if (launches) *launches = 1;
+    return cudaGetLastError();
+}
 
 template <int LAYOUT, bool PERSISTENT>
 cudaError_t launch_one(const TraceLaunch& a, int* launches)
 {
-    auto kern = trace_kernel<LAYOUT, kBlock, kSmemStack, PERSISTENT>;
-    int grid;
-    if (PERSISTENT) {
-        static int blocksPerSM = 0;
-        if (!blocksPerSM) {
-            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 25);
-            if (e != cudaSuccess) return e;
-            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSM, kern, kBlock, 0);
-            if (e != cudaSuccess) return e;
-            if (blocksPerSM < 1) blocksPerSM = 1;
-        }
-        grid = a.numSMs * blocksPerSM;
-        const int needed = (a.numRays + kBlock - 1) / kBlock;
-        if (grid > needed) grid = needed;
-    } else {
-        grid = (a.numRays + kBlock - 1) / kBlock;
+    switch (tuning().smemStack) {
+    case 4:  return launch_variant<LAYOUT, 4, PERSISTENT>(a, launches);
+    case 16: return launch_variant<LAYOUT, 16, PERSISTENT>(a, launches);
+    case 24: return launch_variant<LAYOUT, 24, PERSISTENT>(a, launches);
+    default: return launch_variant<LAYOUT, 8, PERSISTENT>(a, launches);
     }
-    kern<<<grid, kBlock, 0, a.stream>>>(a.numRays, a.anyHit, a.rays, a.results, a.nodes, a.woop, a.triIndices, a.warpCounter);
-    if (launches) *launches = 1;
-    return cudaGetLastError();
 }
 
 } // namespace

@@ -52,9 +52,16 @@ def test_primary_closest_hit_matches_oracle(gpu_host, orc, small_scene, kernel):
     rh = rays.rays_host()
     ref_flat = orc.compact_trace(nodes, woop, idx, rh, True)
     _check_closest(got, ref_flat)
-    # and against the reference's pointer-tree BVH::trace (Moller-Trumbore): ids, looser on ties
+    # and against the reference's pointer-tree BVH::trace (Moller-Trumbore on raw vertices).  Woop and
+    # Moller-Trumbore are different algorithms: on rays grazing a shared edge one can accept and the other
+    # reject (the reference's own two CPU tracers disagree with each other in exactly the same way, see
+    # tests/test_oracle_trace.py), so beyond ties a 1e-4 fraction of "crack" rays is tolerated here.
     ref_tree = cpu.trace(rh, True)
-    _check_closest(got, ref_tree, min_match=0.999)
+    same = got[:, 0] == ref_tree[:, 0]
+    assert same.mean() >= 0.9999, same.mean()
+    tg, tr = got[:, 1].view(np.float32), ref_tree[:, 1].view(np.float32)
+    hit = same & (ref_tree[:, 0] >= 0)
+    assert (np.abs(tg[hit] - tr[hit]) / np.abs(tr[hit])).max() <= 1e-5
 
 
 @pytest.mark.parametrize("kernel", KERNELS)

@@ -1,0 +1,107 @@
+"""Host-side logic that needs no GPU: camera codec and matrices, pixel table, batching, bvhcache format,
+slice partitioning, scene generators."""
+import io
+
+import numpy as np
+import pytest
+
+from ntrace_b200 import camera, multigpu, scenes
+
+
+def test_camera_signatures_decode_to_survey_values():
+    # SURVEY.md App. D (decoded with the codec of CameraControls.cpp:362-395,491-541)
+    c = camera.named_camera("conference")
+    assert np.allclose(c.position, [6.9742, 8.7685, 4.6396], atol=1e-4)
+    assert np.allclose(c.forward, [0.7818, 0.5406, -0.3107], atol=1e-4)
+    assert np.allclose(c.up, [0, 0, 1]) and abs(c.fov - 73.74) < 1e-2 and abs(c.near - 0.01) < 1e-6 and c.far == 100.0
+    f = camera.named_camera("fairyforest")
+    assert np.allclose(f.position, [0.0556, 0.2461, 0.5767], atol=1e-4) and abs(f.fov - 46.83) < 1e-2 and f.far == 500.0
+    s = camera.named_camera("sibenik")
+    assert np.allclose(s.position, [-19.1633, -1.5030, 4.6976], atol=1e-4)
+    m = camera.named_camera("sanmiguel")
+    assert np.allclose(m.forward, [0.0502, -0.0990, -0.9938], atol=1e-4) and abs(m.far - 126.0) < 0.01
+    with pytest.raises(ValueError):
+        camera.decode_signature("!!!")
+
+
+def test_nscreen_to_world_inverts_the_projection(orc):
+    cam = camera.named_camera("conference")
+    w, h = 1024, 768
+    n2w = camera.nscreen_to_world(cam, w, h)
+    clip = (camera.fit_to_view(w, h) @ camera.perspective(cam.fov, cam.near, cam.far) @ camera.world_to_camera(cam)).astype(np.float32)
+    assert np.allclose(n2w @ clip, np.eye(4), atol=2e-3)
+    assert np.allclose(n2w, orc.invert4(clip), rtol=1e-5, atol=1e-4)       # same cofactor formula as Math.hpp:1024-1045
+    assert abs(camera.fit_to_view(w, h)[0, 0] - 0.75) < 1e-7               # fov applies to the short side
+    # centre pixel ray points along the camera forward axis
+    rays, id2slot, slot2id = orc.raygen_primary(cam.position, n2w, 64, 48, cam.far)
+    n2w_small = camera.nscreen_to_world(cam, 64, 48)
+    rays, id2slot, slot2id = orc.raygen_primary(cam.position, n2w_small, 64, 48, cam.far)
+    mid = rays[id2slot[24 * 64 + 32], 4:7]
+    assert np.dot(mid, cam.forward / np.linalg.norm(cam.forward)) > 0.999
+
+
+@pytest.mark.parametrize("w,h", [(1024, 768), (64, 48), (100, 75), (37, 21), (8, 8), (7, 5)])
+def test_pixel_table_is_a_permutation_in_block_morton_order(orc, w, h):
+    i2p, p2i = orc.pixel_table(w, h)
+    assert sorted(i2p.tolist()) == list(range(w * h))
+    assert np.array_equal(p2i[i2p], np.arange(w * h))
+    if w >= 8 and h >= 8:
+        first = i2p[:64]
+        assert set((first % w).tolist()) == set(range(8)) and set((first // w).tolist()) == set(range(8))
+        assert first[0] == 0 and first[1] == 1 and first[2] == w and first[3] == w + 1    # Morton inside the block
+
+
+def test_batching_matches_reference_rule():
+    from ntrace_b200.host import RayGen
+    rg = RayGen(1 << 20)
+    n, spp = 786_432, 32
+    start, new, got = 0, True, []
+    while True:
+        ok, lo, hi, start, new = rg.batching(n, spp, start, new)
+        if not ok:
+            break
+        got.append((lo, hi))
+    assert got[0] == (0, 32768) and got[-1][1] == n and len(got) == 24
+    assert all(a[1] == b[0] for a, b in zip(got, got[1:]))
+    assert rg.batching(0, spp, 0, True)[0] is False
+
+
+def test_bvhcache_stream_format_roundtrip(orc):
+    from ntrace_b200.host import CudaBVH
+    verts, tris = scenes.soup_uniform(50, seed=2)
+    nodes, woop, idx = orc.CpuBVH(verts, tris, orc.BUILDER_SAH, 1, 1).compact()
+    b = CudaBVH(nodes, woop, idx, 4)
+    buf = io.BytesIO()
+    b.serialize(buf)
+    raw = buf.getvalue()
+    # S32 layout, then 3 x (S64 size, bytes), little endian (CudaBVH.cpp:105-125, Buffer.cpp:349-381)
+    assert int.from_bytes(raw[:4], "little") == 4
+    assert int.from_bytes(raw[4:12], "little") == nodes.nbytes
+    assert len(raw) == 4 + 3 * 8 + nodes.nbytes + woop.nbytes + idx.nbytes
+    c = CudaBVH.deserialize(io.BytesIO(raw))
+    assert c.layout == 4 and np.array_equal(c.nodes, nodes) and np.array_equal(c.woop, woop) and np.array_equal(c.tri_index, idx)
+
+
+@pytest.mark.parametrize("n,world", [(0, 4), (1, 4), (1_048_576, 8), (786_432, 3), (10, 16)])
+def test_slices_partition_the_batch(n, world):
+    parts = [multigpu.slice_for_rank(n, r, world) for r in range(world)]
+    assert parts[0][0] == 0 and parts[-1][1] == n
+    assert all(a[1] == b[0] for a, b in zip(parts, parts[1:]))
+    assert all(lo <= hi for lo, hi in parts)
+    with pytest.raises(ValueError):
+        multigpu.slice_for_rank(n, world, world)
+
+
+def test_scene_generators_are_exact_and_deterministic():
+    for gen, n in ((lambda: scenes.room(30_000, 2), 30_000), (lambda: scenes.teapot_in_stadium(20_000, 3), 20_000),
+                   (lambda: scenes.soup_uniform(1_000, 5), 1_000)):
+        v1, t1 = gen()
+        v2, t2 = gen()
+        assert len(t1) == n and t1.dtype == np.int32 and v1.dtype == np.float32
+        assert np.array_equal(v1, v2) and np.array_equal(t1, t2)
+        assert t1.min() >= 0 and t1.max() < len(v1)
+    v, t, cam = scenes.config_scene("conference")
+    assert len(t) == 283_000 and cam == "conference"
+    lo, hi = scenes.bbox(v)
+    c = camera.named_camera(cam)
+    assert (c.position > lo).all() and (c.position < hi).all()      # the reference camera sits inside the stand-in room
