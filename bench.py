@@ -32,6 +32,9 @@ W, H = 1024, 768                      # App.cpp:100, config.conf:5-6
 MAX_BATCH = 1 << 20                   # Renderer.cpp:45
 AO_RADIUS = 5.0                       # config.conf:38
 LEAF_SIZE, EPSILON = 8, 0.001         # Renderer.cpp:201-209
+# dram__bytes_read.sum + dram__bytes_write.sum per trace launch, from the ncu --set full captures of one primary, one AO
+# and one diffuse batch weighted by the 1 + 24 + 24 launches of a step (profiles/r1_summary.md)
+NCU_TRAFFIC_BYTES_PER_LAUNCH = 42.3e6
 METRIC = "Mrays/s (primary+AO+diffuse, counted rays / trace time, Conference stand-in 283K tris, 1024x768)"
 
 
@@ -271,7 +274,7 @@ def run_b200(args):
                     "steps": e2e_steps},
             "gpu_launches": launches_all,
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH,
                          "peak_source": peak_src,
                          "note": "algorithmic bytes (nodes+triangles fetched per ray, oracle-counted) over avg launch time; the BVH is L2-resident, "
                                  "so DRAM traffic is far below the algorithmic bytes and frac can exceed 1 (see profiles/)",
