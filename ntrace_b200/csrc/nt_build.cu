@@ -24,6 +24,8 @@
 //     node (atomicAdd + __threadfence), writing child boxes straight into the parent's node words.
 // One host readback (node / leaf counts, to size the output buffers) instead of one per level.
 #include "nt_common.cuh"
+#include <cooperative_groups.h>
+#include <cstring>
 
 namespace nt {
 
@@ -228,12 +230,19 @@ __global__ void __launch_bounds__(kSortThreads) radix_scatter_kernel(const uint*
 
 // ------------------------------------------------------------------------------------------------
 // Topology: one thread per gap g in [0, N-2] (between sorted positions g and g+1).
+//
+// `hb` = number of Morton bits the gap-parallel emitter owns: 30 for plain LBVH (whole array is one "cluster"),
+// 3*hlbvhBits for HLBVH, where gaps whose keys differ in a bit >= hb are cluster boundaries handled by the
+// top-level SAH stage and the per-cluster subtrees start at bit hb-1 (HLBVHBuilder.cpp:720, level arg :344).
 // ------------------------------------------------------------------------------------------------
 enum : uint { F_KEPT = 1u, F_LEFT_LEAF = 2u, F_RIGHT_LEAF = 4u, F_NEED_DEPTH = 8u };
 
+// parent codes: >= 0 : (parent gap)*2 + side ; -1 : global root (no parent) ; <= -3 : -3 - (topNode*2 + side)
+__device__ __forceinline__ int top_parent_code(int topNode, int side) { return -3 - (topNode * 2 + side); }
+
 __device__ __forceinline__ int topbit(uint x) { return 31 - __clz(x); }
 
-// smallest f <= from such that pred(K[f]) holds on [f, from]; pred is monotone (true near `from`)
+// smallest f <= from such that pred holds on [f, from]; pred is monotone (true near `from`)
 template <class Pred>
 __device__ __forceinline__ int gallop_left(int from, Pred pred)
 {
@@ -253,7 +262,9 @@ __device__ __forceinline__ int gallop_right(int from, int n, Pred pred)
     return good;
 }
 
-__global__ void __launch_bounds__(256) topology_kernel(const uint* __restrict__ K, int n, int leafSize,
+__global__ void __launch_bounds__(256) topology_kernel(const uint* __restrict__ K, int n, int leafSize, int hb,
+                                                        const uint* __restrict__ clusterOf,   // exclusive scan of cluster heads (HLBVH) or null
+                                                        const int* __restrict__ clsParent,    // per cluster: topNode*2+side (HLBVH) or null
                                                         int* __restrict__ nodeS, int* __restrict__ nodeE, int* __restrict__ parent,
                                                         uint* __restrict__ flags, int* __restrict__ rootGap)
 {
@@ -264,6 +275,7 @@ __global__ void __launch_bounds__(256) topology_kernel(const uint* __restrict__ 
     int s, e, b, par = -2;
     if (x) {
         b = topbit(x);
+        if (b >= hb) { nodeS[g] = g; nodeE[g] = g + 1; parent[g] = -2; flags[g] = 0; return; }   // cluster boundary
         s = gallop_left(g, [&](int i) { return ((__ldg(K + i) ^ kg) >> b) == 0u; });
         e = gallop_right(g + 1, n, [&](int i) { return ((__ldg(K + i) ^ kn) >> b) == 0u; }) + 1;
     } else {
@@ -278,26 +290,30 @@ __global__ void __launch_bounds__(256) topology_kernel(const uint* __restrict__ 
             else           { s = m; par = (m - 1) * 2 + 1; }
         }
     }
+    bool root = false;
     if (par == -2) {
-        // bounded by radix gaps: the one with the lower split bit is the parent
-        if (s == 0 && e == n) { par = -1; *rootGap = g; }
-        else if (s == 0) par = (e - 1) * 2 + 0;
-        else if (e == n) par = (s - 1) * 2 + 1;
-        else {
-            const int bl = topbit(__ldg(K + s - 1) ^ __ldg(K + s)), br = topbit(__ldg(K + e - 1) ^ __ldg(K + e));
-            par = (bl < br) ? (s - 1) * 2 + 1 : (e - 1) * 2 + 0;
+        // bounded by radix gaps: the one with the lower split bit is the parent; cluster boundaries (or the array
+        // ends) on both sides mean this node is the root of its cluster
+        const int bl = (s == 0) ? 32 : topbit(__ldg(K + s - 1) ^ __ldg(K + s));
+        const int br = (e == n) ? 32 : topbit(__ldg(K + e - 1) ^ __ldg(K + e));
+        if (bl >= hb && br >= hb) {
+            root = true;
+            if (clsParent) par = top_parent_code(0, 0) - clsParent[clusterOf[s]];   // -3 - (topNode*2+side)
+            else { par = -1; *rootGap = g; }
         }
+        else if (bl >= hb) par = (e - 1) * 2 + 0;
+        else if (br >= hb) par = (s - 1) * 2 + 1;
+        else par = (bl < br) ? (s - 1) * 2 + 1 : (e - 1) * 2 + 0;
     }
     const int split = g + 1;
-    const bool root = (par == -1);
     uint f = 0;
-    if ((e - s) > leafSize || root) {
+    if ((e - s) > leafSize || (root && !clsParent)) {
         f = F_KEPT;
         if (split - s <= leafSize) f |= F_LEFT_LEAF;
         if (e - split <= leafSize) f |= F_RIGHT_LEAF;
-        // A radix node splitting bit b sits at depth <= 29 - b, so only two kinds of node can be affected by the
-        // 29-level rule: duplicate-run nodes (b == -1; they may not exist at all if they are >= 30 levels down)
-        // and bit-0 nodes that would otherwise keep an inner child.
+        // A radix node splitting bit b sits at depth <= (hb-1) - b below its cluster root, so only two kinds of node
+        // can be affected by the level limit: duplicate-run nodes (b == -1; they may not exist at all if they are
+        // too deep) and bit-0 nodes that would otherwise keep an inner child.
         const bool bothLeaves = (f & (F_LEFT_LEAF | F_RIGHT_LEAF)) == (F_LEFT_LEAF | F_RIGHT_LEAF);
         if (b < 0 || (b == 0 && !bothLeaves)) f |= F_NEED_DEPTH;
     }
@@ -305,9 +321,9 @@ __global__ void __launch_bounds__(256) topology_kernel(const uint* __restrict__ 
     nodeS[g] = s; nodeE[g] = e; parent[g] = par; flags[g] = f;
 }
 
-// forced leaves 29 levels below the root (emitTreeKernel.cu:289-292 `oldLevel == 0`), then scan inputs:
+// forced leaves hb-1 levels below the cluster root (emitTreeKernel.cu:289-292 `oldLevel == 0`), then scan inputs:
 // pack[i].lo = gap i is an inner node, pack[i].hi = a leaf starts at sorted position i
-__global__ void __launch_bounds__(256) finalize_kernel(int n, const int* __restrict__ nodeS, const int* __restrict__ parent,
+__global__ void __launch_bounds__(256) finalize_kernel(int n, int hb, const int* __restrict__ nodeS, const int* __restrict__ parent,
                                                         uint* __restrict__ flags, uint* __restrict__ pack32)
 {
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
@@ -316,8 +332,8 @@ __global__ void __launch_bounds__(256) finalize_kernel(int n, const int* __restr
     if (f & F_NEED_DEPTH) {
         int depth = 0;
         for (int p = parent[g]; p >= 0; p = parent[p >> 1]) depth++;
-        if (depth >= 30) f &= ~(F_KEPT | F_LEFT_LEAF | F_RIGHT_LEAF);
-        else if (depth == 29) f |= F_LEFT_LEAF | F_RIGHT_LEAF;
+        if (depth >= hb) f &= ~(F_KEPT | F_LEFT_LEAF | F_RIGHT_LEAF);
+        else if (depth == hb - 1) f |= F_LEFT_LEAF | F_RIGHT_LEAF;
         flags[g] = f;
     }
     if (f & F_KEPT) {
@@ -327,7 +343,14 @@ __global__ void __launch_bounds__(256) finalize_kernel(int n, const int* __restr
     }
 }
 
-__device__ __forceinline__ int node_id(uint rank, uint rootRank, bool isRoot) { return isRoot ? 0 : (int)(rank < rootRank ? rank + 1 : rank); }
+// Final node numbering.  LBVH: gap nodes by scan rank with the root moved to slot 0.  HLBVH: the numTop top-level
+// nodes come first (root = top node 0), gap nodes follow in scan order.
+struct Numbering { int numTop; int rootGap; uint rootRank; };
+__device__ __forceinline__ int gap_node_id(const Numbering& nb, int g, uint rank)
+{
+    if (nb.numTop > 0) return nb.numTop + (int)rank;
+    return (g == nb.rootGap) ? 0 : (int)(rank < nb.rootRank ? rank + 1 : rank);
+}
 
 // leaf box = union of triangle vertices -/+ epsilon (calcLeaf, emitTreeKernel.cu:383-408)
 __device__ __forceinline__ void leaf_box(const float* __restrict__ verts, const int* __restrict__ tris, const int* __restrict__ idx,
@@ -350,42 +373,79 @@ __device__ __forceinline__ void store_child_box(float* node, int side, F3 lo, F3
     *reinterpret_cast<float2*>(node + 8 + 2 * side) = make_float2(lo.z, hi.z);
 }
 
+struct ClimbCtx {
+    int* nodes; const int* parent; const u64* ex; int* gapCounters;
+    const int* topParent; int* topCounters; Numbering nb;
+};
+
+// Bottom-up refit: node `curId` (both child boxes present) carries its box to its parent; whoever arrives second at a
+// node continues (one arrival counter per node).  parCode is the parent code of the current node.
+__device__ __forceinline__ void climb(const ClimbCtx& c, int curId, int parCode)
+{
+    for (;;) {
+        if (parCode == -1) return;
+        const float* cb = reinterpret_cast<const float*>(c.nodes + (size_t)curId * 16);
+        const float4 b0 = __ldcg(reinterpret_cast<const float4*>(cb));
+        const float4 b1 = __ldcg(reinterpret_cast<const float4*>(cb + 4));
+        const float4 bz = __ldcg(reinterpret_cast<const float4*>(cb + 8));
+        F3 lo, hi;
+        lo.x = fminf(b0.x, b1.x); hi.x = fmaxf(b0.y, b1.y);
+        lo.y = fminf(b0.z, b1.z); hi.y = fmaxf(b0.w, b1.w);
+        lo.z = fminf(bz.x, bz.z); hi.z = fmaxf(bz.y, bz.w);
+        int pid, side, next; int* counter;
+        if (parCode >= 0) {
+            const int pg = parCode >> 1; side = parCode & 1;
+            pid = gap_node_id(c.nb, pg, (uint)c.ex[pg]);
+            counter = c.gapCounters + pg; next = c.parent[pg];
+        } else {
+            const int code = -3 - parCode; side = code & 1;
+            pid = code >> 1;
+            counter = c.topCounters + pid; next = c.topParent[pid];
+        }
+        store_child_box(reinterpret_cast<float*>(c.nodes + (size_t)pid * 16), side, lo, hi);
+        __threadfence();
+        if (atomicAdd(counter, 1) == 0) return;
+        curId = pid; parCode = next;
+    }
+}
+
 __global__ void __launch_bounds__(256) emit_kernel(int n, const int* __restrict__ nodeS, const int* __restrict__ nodeE,
-                                                    const int* __restrict__ parent, const uint* __restrict__ flags,
-                                                    const u64* __restrict__ ex, const int* __restrict__ rootGapPtr,
+                                                    const uint* __restrict__ flags, const int* __restrict__ scalars,
                                                     const float* __restrict__ verts, const int* __restrict__ tris, const int* __restrict__ idx,
-                                                    float eps, int* __restrict__ nodes, int* __restrict__ counters)
+                                                    float eps, ClimbCtx c)
 {
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= n - 1) return;
     const uint f = flags[g];
     if (!(f & F_KEPT)) return;
-    const int rootGap = *rootGapPtr;
-    const uint rootRank = (uint)ex[rootGap];
-    const int id = node_id((uint)ex[g], rootRank, g == rootGap);
+    c.nb.rootGap = scalars[0];
+    c.nb.rootRank = (c.nb.numTop > 0) ? 0u : (uint)c.ex[c.nb.rootGap];
+    const int id = gap_node_id(c.nb, g, (uint)c.ex[g]);
     const int s = nodeS[g], e = nodeE[g], split = g + 1;
-    int* node = nodes + (size_t)id * 16;
+    int* node = c.nodes + (size_t)id * 16;
     float* nodef = reinterpret_cast<float*>(node);
 
     const int b = (int)((f >> 8) & 0xffu) - 1;
     node[14] = (b < 0) ? -1 : (b % 3);           // `level % 3` with C remainder semantics (emitTreeKernel.cu:378)
     node[15] = 0;
-    const int par = parent[g];
+    const int par = c.parent[g];
     if (par >= 0) {
         const int pg = par >> 1;
-        const int pid = node_id((uint)ex[pg], rootRank, pg == rootGap);
-        nodes[(size_t)pid * 16 + 12 + (par & 1)] = id * 64;        // byte offset (Compact)
+        c.nodes[(size_t)gap_node_id(c.nb, pg, (uint)c.ex[pg]) * 16 + 12 + (par & 1)] = id * 64;     // byte offset (Compact)
+    } else if (par <= -3) {
+        const int code = -3 - par;
+        c.nodes[(size_t)(code >> 1) * 16 + 12 + (code & 1)] = id * 64;                               // cluster root under a top-level node
     }
 
     int arrivals = 0;
     if (f & F_LEFT_LEAF) {
-        node[12] = ~(3 * s + (int)(ex[s] >> 32));
+        node[12] = ~(3 * s + (int)(c.ex[s] >> 32));
         F3 lo, hi; leaf_box(verts, tris, idx, s, split, eps, lo, hi);
         store_child_box(nodef, 0, lo, hi);
         arrivals++;
     }
     if (f & F_RIGHT_LEAF) {
-        node[13] = ~(3 * split + (int)(ex[split] >> 32));
+        node[13] = ~(3 * split + (int)(c.ex[split] >> 32));
         F3 lo, hi; leaf_box(verts, tris, idx, split, e, eps, lo, hi);
         store_child_box(nodef, 1, lo, hi);
         arrivals++;
@@ -393,28 +453,330 @@ __global__ void __launch_bounds__(256) emit_kernel(int n, const int* __restrict_
     if (arrivals == 0) return;
     if (arrivals == 1) {
         __threadfence();
-        if (atomicAdd(counters + g, 1) == 0) return;          // the inner child has not arrived yet
+        if (atomicAdd(c.gapCounters + g, 1) == 0) return;          // the inner child has not arrived yet
     }
+    climb(c, id, par);
+}
 
-    // bottom-up refit: this node is complete; carry its box to the parent until we are first somewhere
-    int cur = g, curId = id;
+// HLBVH: clusters with <= leafSize triangles hang directly under a top-level node as leaves
+// (distribute, emitTreeKernel.cu:990-996): link, leaf box, then join the refit.
+__global__ void __launch_bounds__(256) cluster_leaf_emit_kernel(int numClusters, int leafSize, const int* __restrict__ clsStart,
+                                                                 const int* __restrict__ clsParent,
+                                                                 const float* __restrict__ verts, const int* __restrict__ tris, const int* __restrict__ idx,
+                                                                 float eps, ClimbCtx c)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= numClusters) return;
+    const int cs = clsStart[k], ce = clsStart[k + 1];
+    if (ce - cs > leafSize) return;
+    const int code = clsParent[k];
+    const int pid = code >> 1, side = code & 1;
+    c.nodes[(size_t)pid * 16 + 12 + side] = ~(3 * cs + (int)(c.ex[cs] >> 32));
+    F3 lo, hi; leaf_box(verts, tris, idx, cs, ce, eps, lo, hi);
+    store_child_box(reinterpret_cast<float*>(c.nodes + (size_t)pid * 16), side, lo, hi);
+    __threadfence();
+    if (atomicAdd(c.topCounters + pid, 1) == 0) return;
+    climb(c, pid, c.topParent[pid]);
+}
+
+__global__ void __launch_bounds__(256) cluster_leaf_flag_kernel(int numClusters, int leafSize, const int* __restrict__ clsStart, uint* __restrict__ pack32)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= numClusters) return;
+    if (clsStart[k + 1] - clsStart[k] <= leafSize) pack32[2 * clsStart[k] + 1] = 1u;
+}
+
+// ------------------------------------------------------------------------------------------------
+// HLBVH: clusters = maximal runs of equal (key >> d) (createClusters, radixSort.cu:74-120), their boxes, and the
+// top-level binned SAH over cluster boxes (initBins / fillBins / findSplit / distribute, emitTreeKernel.cu:699-1027)
+// executed level by level inside ONE cooperative kernel (grid.sync between phases, no host readbacks).
+// Deterministic: output slots come from scans in task order and the object-split fallback ranks clusters by index,
+// i.e. exactly the serial schedule the CPU restatement uses.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int f2i_ord(float f) { const int i = __float_as_int(f); return (i >= 0) ? i : i ^ 0x7FFFFFFF; }
+__device__ __forceinline__ float i2f_ord(int i) { return __int_as_float((i >= 0) ? i : i ^ 0x7FFFFFFF); }
+
+__global__ void __launch_bounds__(256) cluster_mark_kernel(const uint* __restrict__ K, int n, int d, uint* __restrict__ head)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    head[p] = (p == 0 || (K[p] >> d) != (K[p - 1] >> d)) ? 1u : 0u;
+}
+
+// clusterOf[p] (inclusive count - 1) is written in place of the exclusive scan; clsStart[k] = first position of cluster k
+__global__ void __launch_bounds__(256) cluster_start_kernel(int n, const uint* __restrict__ head, uint* __restrict__ exToClusterOf,
+                                                             int* __restrict__ clsStart, int numClusters)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const uint k = exToClusterOf[p] + head[p] - 1u;
+    exToClusterOf[p] = k;
+    if (head[p]) clsStart[k] = p;
+    if (p == 0) clsStart[numClusters] = n;
+}
+
+__global__ void __launch_bounds__(256) cluster_box_init_kernel(int numClusters, int* __restrict__ boxI)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= numClusters * 6) return;
+    boxI[i] = ((i % 6) < 3) ? f2i_ord(kF32Max) : f2i_ord(-kF32Max);
+}
+
+__global__ void __launch_bounds__(256) cluster_box_kernel(int n, const uint* __restrict__ clusterOf, const float* __restrict__ verts,
+                                                           const int* __restrict__ tris, const int* __restrict__ idx, int* __restrict__ boxI)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const int t = __ldg(idx + p);
+    const F3 a = ld3(verts, __ldg(tris + 3 * t)), b = ld3(verts, __ldg(tris + 3 * t + 1)), c = ld3(verts, __ldg(tris + 3 * t + 2));
+    const F3 lo = min3v(a, min3v(b, c)), hi = max3v(a, max3v(b, c));
+    int* bx = boxI + (size_t)clusterOf[p] * 6;
+    atomicMin(bx + 0, f2i_ord(lo.x)); atomicMin(bx + 1, f2i_ord(lo.y)); atomicMin(bx + 2, f2i_ord(lo.z));
+    atomicMax(bx + 3, f2i_ord(hi.x)); atomicMax(bx + 4, f2i_ord(hi.y)); atomicMax(bx + 5, f2i_ord(hi.z));
+}
+
+constexpr int kBins = 8;            // BIN_CNT (emitTreeKernel.cuh:9)
+constexpr int kTopThreads = 256;
+
+struct TopArgs {
+    int C, leafSize;
+    const int* clsStart; const int* clsBoxI;
+    int* clsTask[2];          // current / next task of each cluster (-1 = done)
+    int* clsBin;              // C * 3
+    int* clsParent;           // C : topNode*2 + side once the cluster terminates
+    float* tBox[2];           // task boxes, 6 floats per task (lo xyz, hi xyz)
+    int* tCnt[2]; int* tId[2];
+    int* rSplit; int* rAxis; int* rCntL; int* rCntR; int* rLocalOfs; int* rChild; float* rBoxes;   // per task, current level
+    int* binBoxI; int* binCnt;
+    int* blockSum;
+    int* topNodes; int* topParent;
+    int* scal;                // [0] numTasks, [1] written (top nodes so far)
+    float sceneLo[3], sceneHi[3];
+};
+
+__device__ __forceinline__ float area3_rn(float x, float y, float z)
+{
+    return __fmul_rn(__fadd_rn(__fadd_rn(__fmul_rn(x, y), __fmul_rn(y, z)), __fmul_rn(z, x)), 2.0f);
+}
+
+__device__ __forceinline__ int block_exclusive_int(int v, int* s_warp, int& total)
+{
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += y; }
+    if (lane == 31) s_warp[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+        int x = (lane < kTopThreads / 32) ? s_warp[lane] : 0;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+        if (lane < kTopThreads / 32) s_warp[lane] = x;
+    }
+    __syncthreads();
+    const int base = (w == 0) ? 0 : s_warp[w - 1];
+    total = s_warp[kTopThreads / 32 - 1];
+    __syncthreads();
+    return base + inc - v;
+}
+
+// terminate-or-descend decision of one cluster (distribute, emitTreeKernel.cu:955-1027)
+__device__ __forceinline__ int distribute_one(const TopArgs& a, int c, int task, bool goLeft, int cntL, int cntR, int topId)
+{
+    const int leafs = ((cntL <= 1) ? 2 : 0) | ((cntR <= 1) ? 1 : 0);
+    const int childId = a.rChild[task];
+    if (leafs == 0) return childId + (goLeft ? 0 : 1);
+    const bool single = goLeft ? (leafs & 2) : (leafs & 1);
+    if (!single) return childId;                         // the other side terminated: the only child task sits at childId
+    a.clsParent[c] = topId * 2 + (goLeft ? 0 : 1);       // this cluster hangs under the top node as a leaf or an LBVH subtree
+    return -1;
+}
+
+__global__ void __launch_bounds__(kTopThreads) hlbvh_top_kernel(TopArgs a)
+{
+    namespace cg = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
+    __shared__ int s_warp[kTopThreads / 32];
+    __shared__ int s_red[2];
+    const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int gsize = gridDim.x * blockDim.x;
+    int cur = 0;
+
+    if (gtid == 0) {
+        for (int k = 0; k < 3; k++) { a.tBox[0][k] = a.sceneLo[k]; a.tBox[0][3 + k] = a.sceneHi[k]; }
+        a.tCnt[0][0] = a.C; a.tId[0][0] = 0;
+        a.topParent[0] = -1;
+        a.scal[0] = 1; a.scal[1] = 1;
+    }
+    for (int c = gtid; c < a.C; c += gsize) a.clsTask[0][c] = 0;
+    grid.sync();
+
     for (;;) {
-        const int p = parent[cur];
-        if (p < 0) break;
-        const float* c = reinterpret_cast<const float*>(nodes + (size_t)curId * 16);
-        const float4 b0 = __ldcg(reinterpret_cast<const float4*>(c));
-        const float4 b1 = __ldcg(reinterpret_cast<const float4*>(c + 4));
-        const float4 bz = __ldcg(reinterpret_cast<const float4*>(c + 8));
-        F3 lo, hi;
-        lo.x = fminf(b0.x, b1.x); hi.x = fmaxf(b0.y, b1.y);
-        lo.y = fminf(b0.z, b1.z); hi.y = fmaxf(b0.w, b1.w);
-        lo.z = fminf(bz.x, bz.z); hi.z = fmaxf(bz.y, bz.w);
-        const int pg = p >> 1;
-        const int pid = node_id((uint)ex[pg], rootRank, pg == rootGap);
-        store_child_box(reinterpret_cast<float*>(nodes + (size_t)pid * 16), p & 1, lo, hi);
-        __threadfence();
-        if (atomicAdd(counters + pg, 1) == 0) break;
-        cur = pg; curId = pid;
+        const int T = *(volatile int*)&a.scal[0];
+        if (T == 0) break;
+        const int written = *(volatile int*)&a.scal[1];
+        const float* tBox = a.tBox[cur]; const int* tCnt = a.tCnt[cur]; const int* tId = a.tId[cur];
+        const int* clsTask = a.clsTask[cur]; int* clsNext = a.clsTask[cur ^ 1];
+
+        // ---- initBins
+        for (int i = gtid; i < T * 3 * kBins; i += gsize) {
+            int* b = a.binBoxI + (size_t)i * 6;
+            b[0] = b[1] = b[2] = f2i_ord(kF32Max); b[3] = b[4] = b[5] = f2i_ord(-kF32Max);
+            a.binCnt[i] = 0;
+        }
+        grid.sync();
+
+        // ---- fillBins
+        for (int c = gtid; c < a.C; c += gsize) {
+            const int t = clsTask[c];
+            if (t < 0) continue;
+            const int* cb = a.clsBoxI + (size_t)c * 6;
+            float lo[3], hi[3];
+            for (int k = 0; k < 3; k++) { lo[k] = i2f_ord(cb[k]); hi[k] = i2f_ord(cb[3 + k]); }
+            for (int k = 0; k < 3; k++) {
+                const float mid = __fadd_rn(lo[k], __fdiv_rn(__fsub_rn(hi[k], lo[k]), 2.0f));
+                const float tl = tBox[t * 6 + k], th = tBox[t * 6 + 3 + k];
+                const float step = __fdiv_rn(__fsub_rn(th, tl), 8.0f);
+                const int bid = quantise(mid, tl, step, kBins);
+                a.clsBin[c * 3 + k] = bid;
+                int* b = a.binBoxI + ((size_t)(t * 3 + k) * kBins + bid) * 6;
+                atomicMin(b + 0, cb[0]); atomicMin(b + 1, cb[1]); atomicMin(b + 2, cb[2]);
+                atomicMax(b + 3, cb[3]); atomicMax(b + 4, cb[4]); atomicMax(b + 5, cb[5]);
+                atomicAdd(a.binCnt + (t * 3 + k) * kBins + bid, 1);
+            }
+        }
+        grid.sync();
+
+        // ---- findSplit, phase a: per task decision + block-local offsets of the child tasks
+        const int perBlock = (T + gridDim.x - 1) / gridDim.x;
+        const int t0 = min(T, (int)blockIdx.x * perBlock), t1 = min(T, t0 + perBlock);
+        int carry = 0;
+        for (int base = t0; base < t1; base += kTopThreads) {
+            const int t = base + threadIdx.x;
+            int nodesNew = 0;
+            if (t < t1) {
+                const int* bb = a.binBoxI + (size_t)t * 3 * kBins * 6;
+                const int* bc = a.binCnt + t * 3 * kBins;
+                float best = kF32Max;
+                int split = -1, axis = 0, cntL = 0, cntR = 0;
+                float bx[12];                              // mnL, mxL, mnR, mxR
+                for (int ax = 0; ax < 3; ax++) {
+                    float mn[kBins - 1][3], mx[kBins - 1][3]; int cnt[kBins - 1];
+                    float rl[3] = {kF32Max, kF32Max, kF32Max}, rh[3] = {-kF32Max, -kF32Max, -kF32Max};
+                    int cc = 0;
+                    for (int b = kBins - 1; b > 0; b--) {
+                        const int* q = bb + (size_t)(ax * kBins + b) * 6;
+                        for (int k = 0; k < 3; k++) { rl[k] = fminf(rl[k], i2f_ord(q[k])); rh[k] = fmaxf(rh[k], i2f_ord(q[3 + k])); mn[b - 1][k] = rl[k]; mx[b - 1][k] = rh[k]; }
+                        cc += bc[ax * kBins + b]; cnt[b - 1] = cc;
+                    }
+                    float ll[3] = {kF32Max, kF32Max, kF32Max}, lh[3] = {-kF32Max, -kF32Max, -kF32Max};
+                    cc = 0;
+                    for (int b = 0; b < kBins - 1; b++) {
+                        const int* q = bb + (size_t)(ax * kBins + b) * 6;
+                        for (int k = 0; k < 3; k++) { ll[k] = fminf(ll[k], i2f_ord(q[k])); lh[k] = fmaxf(lh[k], i2f_ord(q[3 + k])); }
+                        cc += bc[ax * kBins + b];
+                        const float aL = area3_rn(__fsub_rn(lh[0], ll[0]), __fsub_rn(lh[1], ll[1]), __fsub_rn(lh[2], ll[2]));
+                        const float aR = area3_rn(__fsub_rn(mx[b][0], mn[b][0]), __fsub_rn(mx[b][1], mn[b][1]), __fsub_rn(mx[b][2], mn[b][2]));
+                        const float s = __fadd_rn(__fmul_rn((float)cc, aL), __fmul_rn((float)cnt[b], aR));
+                        if (s < best) {
+                            best = s; split = b; axis = ax; cntL = cc; cntR = cnt[b];
+                            for (int k = 0; k < 3; k++) { bx[k] = ll[k]; bx[3 + k] = lh[k]; bx[6 + k] = mn[b][k]; bx[9 + k] = mx[b][k]; }
+                        }
+                    }
+                }
+                if (split == -1) {
+                    // no plane separates the clusters: halve them by index (object split).  The reference leaves the
+                    // right box half-assigned here (emitTreeKernel.cu:844-845); both children get the occupied bin's box.
+                    for (int i = 0; i < kBins; i++)
+                        if (bc[i] != 0) {
+                            for (int k = 0; k < 3; k++) { bx[k] = bx[6 + k] = i2f_ord(bb[(size_t)i * 6 + k]); bx[3 + k] = bx[9 + k] = i2f_ord(bb[(size_t)i * 6 + 3 + k]); }
+                            break;
+                        }
+                    cntR = tCnt[t] / 2; cntL = tCnt[t] - cntR;
+                    split = -cntL; axis = 0;
+                }
+                nodesNew = (cntL > 1) + (cntR > 1);
+                a.rSplit[t] = split; a.rAxis[t] = axis; a.rCntL[t] = cntL; a.rCntR[t] = cntR;
+                for (int k = 0; k < 12; k++) a.rBoxes[(size_t)t * 12 + k] = bx[k];
+            }
+            int total;
+            const int ex = block_exclusive_int(nodesNew, s_warp, total);
+            if (t < t1) a.rLocalOfs[t] = carry + ex;
+            carry += total;
+        }
+        if (threadIdx.x == 0) a.blockSum[blockIdx.x] = carry;
+        grid.sync();
+
+        // ---- findSplit, phase b: global offsets, child tasks, node links
+        {
+            int mine = 0, all = 0;
+            for (int b = threadIdx.x; b < (int)gridDim.x; b += kTopThreads) { const int v = a.blockSum[b]; all += v; if (b < (int)blockIdx.x) mine += v; }
+            int tot;
+            block_exclusive_int(mine, s_warp, tot);
+            if (threadIdx.x == 0) s_red[0] = tot;
+            __syncthreads();
+            block_exclusive_int(all, s_warp, tot);
+            if (threadIdx.x == 0) s_red[1] = tot;
+            __syncthreads();
+        }
+        const int blockBase = s_red[0], created = s_red[1];
+        float* oBox = a.tBox[cur ^ 1]; int* oCnt = a.tCnt[cur ^ 1]; int* oId = a.tId[cur ^ 1];
+        for (int t = t0 + threadIdx.x; t < t1; t += kTopThreads) {
+            const int ofs = blockBase + a.rLocalOfs[t];
+            const int idN = written + ofs;
+            const int cntL = a.rCntL[t], cntR = a.rCntR[t];
+            const float* bx = a.rBoxes + (size_t)t * 12;
+            int val = 0, l = 0, r = 0;
+            if (cntL > 1) {
+                l = idN * 64;
+                for (int k = 0; k < 6; k++) oBox[(size_t)ofs * 6 + k] = bx[k];
+                oCnt[ofs] = cntL; oId[ofs] = idN;
+                a.topParent[idN] = top_parent_code(tId[t], 0);
+                val = 1;
+            }
+            if (cntR > 1) {
+                r = (idN + val) * 64;
+                for (int k = 0; k < 6; k++) oBox[(size_t)(ofs + val) * 6 + k] = bx[6 + k];
+                oCnt[ofs + val] = cntR; oId[ofs + val] = idN + val;
+                a.topParent[idN + val] = top_parent_code(tId[t], 1);
+            }
+            a.rChild[t] = ofs;
+            int* w = a.topNodes + (size_t)tId[t] * 16;
+            w[12] = l; w[13] = r; w[14] = a.rAxis[t]; w[15] = 0;
+        }
+        grid.sync();
+        if (gtid == 0) { a.scal[0] = created; a.scal[1] = written + created; }      // read again only after the next grid.sync
+
+        // ---- distribute: plane splits per cluster; object-split fallback per task with clusters ranked by index
+        for (int c = gtid; c < a.C; c += gsize) {
+            const int t = clsTask[c];
+            if (t < 0) { clsNext[c] = -1; continue; }
+            const int split = a.rSplit[t];
+            if (split < 0) continue;                       // handled below
+            const bool goLeft = a.clsBin[c * 3 + a.rAxis[t]] <= split;
+            clsNext[c] = distribute_one(a, c, t, goLeft, a.rCntL[t], a.rCntR[t], tId[t]);
+        }
+        {
+            const int lane = threadIdx.x & 31;
+            const int warp = gtid >> 5, nwarps = gsize >> 5;
+            for (int t = warp; t < T; t += nwarps) {
+                if (a.rSplit[t] >= 0) continue;
+                const int cntL = a.rCntL[t], cntR = a.rCntR[t], topId = tId[t];
+                int seen = 0;
+                for (int base = 0; base < a.C; base += 32) {
+                    const int c = base + lane;
+                    const bool m = (c < a.C) && (clsTask[c] == t);
+                    const unsigned mask = __ballot_sync(0xffffffffu, m);
+                    if (m) {
+                        const int rank = seen + __popc(mask & ((1u << lane) - 1u));      // arrival order == cluster index order
+                        clsNext[c] = distribute_one(a, c, t, rank <= cntL - 1, cntL, cntR, topId);
+                    }
+                    seen += __popc(mask);
+                }
+            }
+        }
+        grid.sync();
+        cur ^= 1;
     }
 }
 
@@ -489,6 +851,9 @@ __global__ void single_triangle_kernel(const float* __restrict__ verts, const in
 
 struct Scratch {
     DevBuf keysB, idxB, hist, blockSums, nodeS, nodeE, parent, flags, pack, ex, counters, scalars;
+    // HLBVH
+    DevBuf clsHead, clusterOf, clsStart, clsBox, clsTask0, clsTask1, clsBin, clsParent;
+    DevBuf tBox0, tBox1, tCnt0, tCnt1, tId0, tId1, rInts, rBoxes, binBox, binCnt, blockSum, topNodes, topParent, topCounters;
 };
 Scratch g_scratch;
 
@@ -498,16 +863,17 @@ cudaError_t build_bvh_device(const float* dVerts, int numVerts, const int* dTris
                              const BuildParams& p, BuildOutput& out, cudaStream_t stream,
                              int numSMs, int* outLaunches, std::string* err)
 {
-    (void)numVerts; (void)numSMs;
+    (void)numVerts;
     int launches = 0;
     cudaError_t e;
 #define NT_TRY(call) do { e = (call); if (e != cudaSuccess) { *outLaunches = launches; return e; } } while (0)
 
-    if (p.builder != 0 && !(p.hlbvhBits == 10)) {
-        if (err) *err = "HLBVH top level (hlbvhBits != 10) is not implemented in this build; use NT_BUILDER_LBVH";
-        return cudaErrorNotSupported;
+    bool hl = (p.builder != 0) && (p.hlbvhBits != 10);            // HLBVHBuilder.cpp:44-47
+    if (hl && (p.hlbvhBits < 1 || p.hlbvhBits > 9)) {
+        if (err) *err = "HLBVH: hlbvhBits must be in [1, 9] (10 selects plain LBVH)";
+        return cudaErrorInvalidValue;
     }
-    if ((long long)n * 3 + n >= 0x7fffffffLL / 1) {
+    if ((long long)n * 4 >= 0x7fffffffLL) {
         if (err) *err = "scene too large for 32-bit Woop offsets";
         return cudaErrorInvalidValue;
     }
@@ -558,28 +924,105 @@ cudaError_t build_bvh_device(const float* dVerts, int numVerts, const int* dTris
         // four passes: the sorted data is back in keysA / idxA
     }
 
+    NT_TRY(sc.scalars.reserve(64));
+    NT_TRY(cudaMemsetAsync(sc.scalars.p, 0, 64, stream));
+    int* rootGap = sc.scalars.as<int>();                 // int [0]
+    u64* totals = sc.scalars.as<u64>() + 1;              // bytes 8..15: (leaves << 32 | inner gap nodes)
+    int* topScal = sc.scalars.as<int>() + 4;             // ints [4] numTasks, [5] top-level nodes written
+    uint* clusterCount = sc.scalars.as<uint>() + 6;      // int [6]
+
+    // ---- HLBVH: clusters + top-level SAH (one cooperative kernel)
+    int hb = 30, C = 0;
+    if (hl) {
+        const int d = 3 * p.hlbvhBits;                    // low bits dropped: clusters are cells of the 3m-bit grid
+        NT_TRY(sc.clsHead.reserve((size_t)n * 4)); NT_TRY(sc.clusterOf.reserve((size_t)n * 4));
+        cluster_mark_kernel<<<(n + 255) / 256, 256, 0, stream>>>(keysA, n, d, sc.clsHead.as<uint>());
+        launches++;
+        NT_TRY(exclusive_scan<uint>(sc.clsHead.as<uint>(), sc.clusterOf.as<uint>(), n, sc.blockSums.as<uint>(), clusterCount, stream, &launches));
+        uint hc = 0;
+        NT_TRY(cudaMemcpyAsync(&hc, clusterCount, 4, cudaMemcpyDeviceToHost, stream));     // readback 1 of 2: cluster count sizes the top-level buffers
+        NT_TRY(cudaStreamSynchronize(stream));
+        C = (int)hc;
+        if (C < 2) hl = false;       // the whole scene sits in one grid cell: nothing for the SAH stage to do, plain LBVH
+    }
+    if (hl) {
+        hb = 3 * p.hlbvhBits;
+        const size_t maxTasks = (size_t)C / 2 + 2;
+        NT_TRY(sc.clsStart.reserve(((size_t)C + 1) * 4)); NT_TRY(sc.clsBox.reserve((size_t)C * 24));
+        NT_TRY(sc.clsTask0.reserve((size_t)C * 4)); NT_TRY(sc.clsTask1.reserve((size_t)C * 4));
+        NT_TRY(sc.clsBin.reserve((size_t)C * 12)); NT_TRY(sc.clsParent.reserve((size_t)C * 4));
+        NT_TRY(sc.tBox0.reserve(maxTasks * 24)); NT_TRY(sc.tBox1.reserve(maxTasks * 24));
+        NT_TRY(sc.tCnt0.reserve(maxTasks * 4)); NT_TRY(sc.tCnt1.reserve(maxTasks * 4));
+        NT_TRY(sc.tId0.reserve(maxTasks * 4)); NT_TRY(sc.tId1.reserve(maxTasks * 4));
+        NT_TRY(sc.rInts.reserve(maxTasks * 6 * 4)); NT_TRY(sc.rBoxes.reserve(maxTasks * 48));
+        NT_TRY(sc.binBox.reserve(maxTasks * 3 * kBins * 24)); NT_TRY(sc.binCnt.reserve(maxTasks * 3 * kBins * 4));
+        NT_TRY(sc.topNodes.reserve((size_t)C * 64)); NT_TRY(sc.topParent.reserve((size_t)C * 4)); NT_TRY(sc.topCounters.reserve((size_t)C * 4));
+        NT_TRY(cudaMemsetAsync(sc.topNodes.p, 0, (size_t)C * 64, stream));
+        NT_TRY(cudaMemsetAsync(sc.topCounters.p, 0, (size_t)C * 4, stream));
+        NT_TRY(cudaMemsetAsync(sc.clsParent.p, 0, (size_t)C * 4, stream));
+
+        cluster_start_kernel<<<(n + 255) / 256, 256, 0, stream>>>(n, sc.clsHead.as<uint>(), sc.clusterOf.as<uint>(), sc.clsStart.as<int>(), C);
+        cluster_box_init_kernel<<<(C * 6 + 255) / 256, 256, 0, stream>>>(C, sc.clsBox.as<int>());
+        cluster_box_kernel<<<(n + 255) / 256, 256, 0, stream>>>(n, sc.clusterOf.as<uint>(), dVerts, dTris, idxA, sc.clsBox.as<int>());
+        launches += 3;
+        NT_TRY(cudaGetLastError());
+
+        static int topBlocksPerSM = 0;
+        if (!topBlocksPerSM) {
+            NT_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&topBlocksPerSM, hlbvh_top_kernel, kTopThreads, 0));
+            if (topBlocksPerSM < 1) topBlocksPerSM = 1;
+            if (topBlocksPerSM > 4) topBlocksPerSM = 4;
+        }
+        const int grid = numSMs * topBlocksPerSM;
+        NT_TRY(sc.blockSum.reserve((size_t)grid * 4));
+        TopArgs ta;
+        ta.C = C; ta.leafSize = p.leafSize;
+        ta.clsStart = sc.clsStart.as<int>(); ta.clsBoxI = sc.clsBox.as<int>();
+        ta.clsTask[0] = sc.clsTask0.as<int>(); ta.clsTask[1] = sc.clsTask1.as<int>();
+        ta.clsBin = sc.clsBin.as<int>(); ta.clsParent = sc.clsParent.as<int>();
+        ta.tBox[0] = sc.tBox0.as<float>(); ta.tBox[1] = sc.tBox1.as<float>();
+        ta.tCnt[0] = sc.tCnt0.as<int>(); ta.tCnt[1] = sc.tCnt1.as<int>();
+        ta.tId[0] = sc.tId0.as<int>(); ta.tId[1] = sc.tId1.as<int>();
+        int* ri = sc.rInts.as<int>();
+        ta.rSplit = ri; ta.rAxis = ri + maxTasks; ta.rCntL = ri + 2 * maxTasks; ta.rCntR = ri + 3 * maxTasks;
+        ta.rLocalOfs = ri + 4 * maxTasks; ta.rChild = ri + 5 * maxTasks;
+        ta.rBoxes = sc.rBoxes.as<float>();
+        ta.binBoxI = sc.binBox.as<int>(); ta.binCnt = sc.binCnt.as<int>();
+        ta.blockSum = sc.blockSum.as<int>();
+        ta.topNodes = sc.topNodes.as<int>(); ta.topParent = sc.topParent.as<int>();
+        ta.scal = topScal;
+        for (int k = 0; k < 3; k++) { ta.sceneLo[k] = p.lo[k]; ta.sceneHi[k] = p.hi[k]; }
+        void* kargs[] = {&ta};
+        NT_TRY(cudaLaunchCooperativeKernel((const void*)hlbvh_top_kernel, dim3(grid), dim3(kTopThreads), kargs, 0, stream));
+        launches++;
+    }
+
     // ---- topology, forced leaves, numbering
     const int gaps = n - 1;
     NT_TRY(sc.nodeS.reserve((size_t)n * 4)); NT_TRY(sc.nodeE.reserve((size_t)n * 4)); NT_TRY(sc.parent.reserve((size_t)n * 4));
     NT_TRY(sc.flags.reserve((size_t)n * 4)); NT_TRY(sc.pack.reserve((size_t)n * 8)); NT_TRY(sc.ex.reserve((size_t)n * 8));
-    NT_TRY(sc.counters.reserve((size_t)n * 4)); NT_TRY(sc.scalars.reserve(64));
+    NT_TRY(sc.counters.reserve((size_t)n * 4));
     NT_TRY(cudaMemsetAsync(sc.pack.p, 0, (size_t)n * 8, stream));
     NT_TRY(cudaMemsetAsync(sc.counters.p, 0, (size_t)n * 4, stream));
-    NT_TRY(cudaMemsetAsync(sc.scalars.p, 0, 64, stream));
-    int* rootGap = sc.scalars.as<int>();                 // [0]
-    u64* totals = sc.scalars.as<u64>() + 1;              // bytes 8..15: (leaves << 32 | inner nodes)
-    topology_kernel<<<(gaps + 255) / 256, 256, 0, stream>>>(keysA, n, p.leafSize, sc.nodeS.as<int>(), sc.nodeE.as<int>(), sc.parent.as<int>(),
-                                                             sc.flags.as<uint>(), rootGap);
-    finalize_kernel<<<(gaps + 255) / 256, 256, 0, stream>>>(n, sc.nodeS.as<int>(), sc.parent.as<int>(), sc.flags.as<uint>(), sc.pack.as<uint>());
+    topology_kernel<<<(gaps + 255) / 256, 256, 0, stream>>>(keysA, n, p.leafSize, hb, hl ? sc.clusterOf.as<uint>() : nullptr,
+                                                             hl ? sc.clsParent.as<int>() : nullptr,
+                                                             sc.nodeS.as<int>(), sc.nodeE.as<int>(), sc.parent.as<int>(), sc.flags.as<uint>(), rootGap);
+    finalize_kernel<<<(gaps + 255) / 256, 256, 0, stream>>>(n, hb, sc.nodeS.as<int>(), sc.parent.as<int>(), sc.flags.as<uint>(), sc.pack.as<uint>());
     launches += 2;
+    if (hl) {
+        cluster_leaf_flag_kernel<<<(C + 255) / 256, 256, 0, stream>>>(C, p.leafSize, sc.clsStart.as<int>(), sc.pack.as<uint>());
+        launches++;
+    }
     NT_TRY(cudaGetLastError());
     NT_TRY(exclusive_scan<u64>(sc.pack.as<u64>(), sc.ex.as<u64>(), n, sc.blockSums.as<u64>(), totals, stream, &launches));
 
-    // the only host readback of the build: inner-node and leaf counts size the output buffers
-    u64 tot = 0;
-    NT_TRY(cudaMemcpyAsync(&tot, totals, 8, cudaMemcpyDeviceToHost, stream));
+    // the (last) host readback of the build: node and leaf counts size the output buffers
+    int hs[8];
+    NT_TRY(cudaMemcpyAsync(hs, sc.scalars.p, 32, cudaMemcpyDeviceToHost, stream));
     NT_TRY(cudaStreamSynchronize(stream));
-    const size_t numInner = (size_t)(tot & 0xffffffffull), numLeaves = (size_t)(tot >> 32);
+    u64 tot; memcpy(&tot, &hs[2], 8);
+    const size_t numTop = hl ? (size_t)hs[5] : 0;
+    const size_t numInner = (size_t)(tot & 0xffffffffull) + numTop, numLeaves = (size_t)(tot >> 32);
     if (numInner == 0 || numLeaves == 0) { if (err) *err = "internal error: empty tree"; return cudaErrorUnknown; }
     if (numInner * 64 >= 0x76543210ull) { if (err) *err = "node buffer exceeds the 32-bit byte-offset range of BVHLayout_Compact"; return cudaErrorInvalidValue; }
     out.nodeBytes = numInner * 64;
@@ -589,12 +1032,23 @@ cudaError_t build_bvh_device(const float* dVerts, int numVerts, const int* dTris
     NT_TRY(out.woop->reserve(out.woopBytes));
     NT_TRY(out.triIndex->reserve(out.idxBytes));
 
-    emit_kernel<<<(gaps + 255) / 256, 256, 0, stream>>>(n, sc.nodeS.as<int>(), sc.nodeE.as<int>(), sc.parent.as<int>(), sc.flags.as<uint>(),
-                                                         sc.ex.as<u64>(), rootGap, dVerts, dTris, idxA, p.epsilon,
-                                                         out.nodes->as<int>(), sc.counters.as<int>());
+    ClimbCtx cc;
+    cc.nodes = out.nodes->as<int>(); cc.parent = sc.parent.as<int>(); cc.ex = sc.ex.as<u64>(); cc.gapCounters = sc.counters.as<int>();
+    cc.topParent = hl ? sc.topParent.as<int>() : nullptr; cc.topCounters = hl ? sc.topCounters.as<int>() : nullptr;
+    cc.nb.numTop = (int)numTop; cc.nb.rootGap = 0; cc.nb.rootRank = 0;
+    if (hl) NT_TRY(cudaMemcpyAsync(out.nodes->p, sc.topNodes.p, numTop * 64, cudaMemcpyDeviceToDevice, stream));
+
+    emit_kernel<<<(gaps + 255) / 256, 256, 0, stream>>>(n, sc.nodeS.as<int>(), sc.nodeE.as<int>(), sc.flags.as<uint>(), rootGap,
+                                                         dVerts, dTris, idxA, p.epsilon, cc);
+    launches++;
+    if (hl) {
+        cluster_leaf_emit_kernel<<<(C + 255) / 256, 256, 0, stream>>>(C, p.leafSize, sc.clsStart.as<int>(), sc.clsParent.as<int>(),
+                                                                       dVerts, dTris, idxA, p.epsilon, cc);
+        launches++;
+    }
     leaf_emit_kernel<<<(n + 255) / 256, 256, 0, stream>>>(n, sc.ex.as<u64>(), sc.pack.as<uint>(), dVerts, dTris, idxA,
                                                            out.woop->as<float4>(), out.triIndex->as<int>());
-    launches += 2;
+    launches++;
     NT_TRY(cudaGetLastError());
     *outLaunches = launches;
     return cudaSuccess;

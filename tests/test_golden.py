@@ -88,7 +88,11 @@ def test_gpu_reproduces_golden(gpu_host, orc, name):
         assert sha(c.woop) == e["woop_sha"]
         assert np.array_equal(c.boxes, orc.canonical(*_ref_lbvh(orc, verts, tris, lo, hi, leaf)).boxes)
         assert abs(orc.compact_sah(nodes, woop)["sah"] - e["sah"]) <= 0.005 * e["sah"]
-    # trace the reference-built SplitBVH with the CUDA kernel on the golden rays
+    capi.bvh_build(capi.BUILDER_HLBVH, np.ascontiguousarray(verts), np.ascontiguousarray(tris), lo, hi, 4, 8, 0.001)
+    nodes, woop, idx, _ = capi.bvh_download()
+    e = g["hlbvh_bits4_leaf8"]
+    assert len(nodes) // 16 == e["num_nodes"] and abs(orc.compact_sah(nodes, woop)["sah"] - e["sah"]) <= 0.005 * e["sah"]
+    # trace the reference-built SAH BVH with the CUDA kernel on the golden rays
     cam = fitted_camera(verts)
     rays = gpu_host.RayBuffer()
     gpu_host.RayGen().primary(rays, cam.position, camera.nscreen_to_world(cam, 128, 96), 128, 96, cam.far)
