@@ -45,6 +45,14 @@ def env_int(name, default):
         return default
 
 
+def host_threads():
+    """All host cores this process may use (torchrun exports OMP_NUM_THREADS=1; the CPU legs pass the count explicitly)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -133,7 +141,8 @@ def run_b200(args):
     build_s = []
     if rank == 0:
         for _ in range(1 + 5):
-            build_s.append(capi.bvh_build(capi.BUILDER_LBVH, scene.vtxPos, scene.triVtxIndex, scene.bboxMin, scene.bboxMax, 10, LEAF_SIZE, EPSILON))
+            build_s.append(capi.bvh_build(capi.BUILDER_HLBVH, scene.vtxPos, scene.triVtxIndex, scene.bboxMin, scene.bboxMax,
+                                          4 if args.builder == "hlbvh" else 10, LEAF_SIZE, EPSILON))
     bcast_ms = 0.0
     if world > 1:
         from ntrace_b200 import multigpu
@@ -260,7 +269,7 @@ def run_b200(args):
             "ms_per_step": sec / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": "conference stand-in room(283000, seed=2): primary + AO(32spp, r=5, any-hit) + diffuse(32spp, closest-hit), "
-                                   "1024x768, <=1Mi rays/batch, GPU LBVH leaf 8",
+                                   "1024x768, <=1Mi rays/batch, GPU %s leaf 8" % ("HLBVH(bits 4)" if args.builder == "hlbvh" else "LBVH"),
                        "rays_traced_per_step_per_gpu": int(sum(traced.values())), "rays_counted_per_step_per_gpu": int(counted_step),
                        "batches_per_step": n_launch_step, "kernel": "b200_persistent_speculative_while_while",
                        "l2": "inputs exceed L2: %.0f MB of rays per step stream from HBM; the %.0f MB BVH is reused within a frame by design"
@@ -294,7 +303,7 @@ def cpu_baseline_leg(verts, tris, cam, args, gpu_bvh=None, sample_batches=None):
     BVH::trace) on a bounded sample, (b) counts nodes/triangles per ray on the GPU-built BVH for the roofline."""
     import oracle
     from ntrace_b200 import camera
-    threads = oracle.max_threads()
+    threads = host_threads()
     t0 = time.time()
     cpu = oracle.CpuBVH(verts, tris, oracle.BUILDER_SPLIT, 1, 1, 1.0e-5)
     build_s = time.time() - t0
@@ -333,7 +342,7 @@ def run_reference(args):
     import oracle
     from ntrace_b200 import camera
     verts, tris, cam = make_workload()
-    threads = oracle.max_threads()
+    threads = host_threads()
     cpu = oracle.CpuBVH(verts, tris, oracle.BUILDER_SPLIT, 1, 1, 1.0e-5)
     rays, _, _ = oracle.raygen_primary(cam.position, camera.nscreen_to_world(cam, W, H), W, H, cam.far, 0)
     res = cpu.trace(rays, True, nthreads=threads)
@@ -375,6 +384,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--spp", type=int, default=32)
+    ap.add_argument("--builder", default="hlbvh", choices=["hlbvh", "lbvh"],
+                    help="GPU builder: hlbvh = Renderer default HLBVHParams{true, 4, 8, 0.001} (Renderer.cpp:201-209); lbvh = hlbvhBits 10")
     ap.add_argument("--profile", action="store_true", help="dev: only the device-timed region (for runs under ncu); prints no JSON")
     args = ap.parse_args()
     if args.impl == "reference":

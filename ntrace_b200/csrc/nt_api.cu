@@ -48,6 +48,10 @@ struct Context {
     cudaStream_t stream = nullptr;
     cudaEvent_t evA = nullptr, evB = nullptr;
     cudaEvent_t userEv[8] = {};
+    // host-buffer pipeline: copy-in / copy-out streams and per-chunk events
+    static constexpr int kMaxChunks = 16;
+    cudaStream_t sIn = nullptr, sOut = nullptr;
+    cudaEvent_t evIn[kMaxChunks] = {}, evKa[kMaxChunks] = {}, evKb[kMaxChunks] = {};
     bool deferred = false;
     int64_t launches = 0;
 
@@ -187,8 +191,15 @@ int nt_init(int device_ordinal)
     NT_CUDA(cudaEventCreate(&g.evA));
     NT_CUDA(cudaEventCreate(&g.evB));
     for (int i = 0; i < 8; i++) NT_CUDA(cudaEventCreate(&g.userEv[i]));
-    NT_CUDA(g.counters.reserve(64));
-    NT_CUDA(cudaMemsetAsync(g.counters.p, 0, 64, g.stream));
+    NT_CUDA(cudaStreamCreateWithFlags(&g.sIn, cudaStreamNonBlocking));
+    NT_CUDA(cudaStreamCreateWithFlags(&g.sOut, cudaStreamNonBlocking));
+    for (int i = 0; i < Context::kMaxChunks; i++) {
+        NT_CUDA(cudaEventCreateWithFlags(&g.evIn[i], cudaEventDisableTiming));
+        NT_CUDA(cudaEventCreate(&g.evKa[i]));
+        NT_CUDA(cudaEventCreate(&g.evKb[i]));
+    }
+    NT_CUDA(g.counters.reserve(256));
+    NT_CUDA(cudaMemsetAsync(g.counters.p, 0, 256, g.stream));
     NT_CUDA(cudaStreamSynchronize(g.stream));
     g.launches = 0;
     g.inited = true;
@@ -206,6 +217,8 @@ void nt_shutdown(void)
     for (DevBuf* b : bufs) b->release();
     cudaEventDestroy(g.evA); cudaEventDestroy(g.evB);
     for (int i = 0; i < 8; i++) cudaEventDestroy(g.userEv[i]);
+    for (int i = 0; i < Context::kMaxChunks; i++) { cudaEventDestroy(g.evIn[i]); cudaEventDestroy(g.evKa[i]); cudaEventDestroy(g.evKb[i]); }
+    cudaStreamDestroy(g.sIn); cudaStreamDestroy(g.sOut);
     cudaStreamDestroy(g.stream);
     g = Context();
 }
@@ -405,20 +418,58 @@ int nt_trace_batch(const float* rays, int32_t* results, int numRays, int needClo
     if (!g.haveBVH) { set_error("CudaBVHTracer: No BVH!"); return 1; }                          // :98-99
     if (g.bvhLayout != g.kernelLayout) { set_error("CudaBVHTracer: Incorrect BVH layout!"); return 1; }  // :100-101
 
-    const void* dRays; void* dRes; void* hostRes;
-    if (stage_in(rays, (size_t)numRays * 32, g.stRays, &dRays)) return 1;
-    if (stage_out(results, (size_t)numRays * 16, g.stResults, &dRes, &hostRes)) return 1;
+    const bool raysOnHost = !is_device_ptr(rays), resOnHost = !is_device_ptr(results);
 
     TraceLaunch a;
-    a.kernel = g.kernel; a.layout = g.kernelLayout; a.numRays = numRays; a.anyHit = needClosestHit ? 0 : 1;
-    a.rays = (const float4*)dRays; a.results = (int4*)dRes;
+    a.kernel = g.kernel; a.layout = g.kernelLayout; a.anyHit = needClosestHit ? 0 : 1;
     a.nodes = g.nodes.as<float4>(); a.woop = g.woop.as<float4>(); a.triIndices = g.triIndex.as<int>();
-    a.warpCounter = g.counters.as<int>(); a.numSMs = g.numSMs; a.stream = g.stream;
+    a.numSMs = g.numSMs; a.stream = g.stream;
+    int launches = 0;
 
+    if (raysOnHost || resOnHost) {
+        // Host buffers (the reference's Buffer would migrate them): stage through device buffers in chunks so that the
+        // H2D copy of chunk i+1, the kernel on chunk i and the D2H copy of chunk i-1 overlap on three streams.
+        const float4* dRays = (const float4*)rays; int4* dRes = (int4*)results;
+        if (raysOnHost) { NT_CUDA(g.stRays.reserve((size_t)numRays * 32)); dRays = g.stRays.as<float4>(); }
+        if (resOnHost) { NT_CUDA(g.stResults.reserve((size_t)numRays * 16)); dRes = g.stResults.as<int4>(); }
+        int chunk = (numRays + 7) / 8;
+        if (chunk < 65536) chunk = 65536;
+        chunk = (chunk + 127) & ~127;
+        const int numChunks = (numRays + chunk - 1) / chunk;          // <= 8 <= kMaxChunks
+        for (int i = 0; i < numChunks; i++) {
+            const int lo = i * chunk, cnt = (numRays - lo < chunk) ? numRays - lo : chunk;
+            if (raysOnHost) {
+                NT_CUDA(cudaMemcpyAsync((void*)(dRays + (size_t)lo * 2), rays + (size_t)lo * 8, (size_t)cnt * 32, cudaMemcpyHostToDevice, g.sIn));
+                NT_CUDA(cudaEventRecord(g.evIn[i], g.sIn));
+                NT_CUDA(cudaStreamWaitEvent(g.stream, g.evIn[i], 0));
+            }
+            a.numRays = cnt; a.rays = dRays + (size_t)lo * 2; a.results = dRes + lo;
+            a.warpCounter = g.counters.as<int>() + 8 + i;
+            NT_CUDA(cudaMemsetAsync(a.warpCounter, 0, sizeof(int), g.stream));
+            NT_CUDA(cudaEventRecord(g.evKa[i], g.stream));
+            int l = 0;
+            NT_CUDA(launch_trace(a, &l));
+            launches += l;
+            NT_CUDA(cudaEventRecord(g.evKb[i], g.stream));
+            if (resOnHost) {
+                NT_CUDA(cudaStreamWaitEvent(g.sOut, g.evKb[i], 0));
+                NT_CUDA(cudaMemcpyAsync(results + (size_t)lo * 4, dRes + lo, (size_t)cnt * 16, cudaMemcpyDeviceToHost, g.sOut));
+            }
+        }
+        g.launches += launches;
+        NT_CUDA(cudaStreamSynchronize(g.stream));
+        NT_CUDA(cudaStreamSynchronize(g.sOut));
+        float total = 0.0f;
+        for (int i = 0; i < numChunks; i++) { float ms = 0.0f; NT_CUDA(cudaEventElapsedTime(&ms, g.evKa[i], g.evKb[i])); total += ms; }
+        if (outSeconds) *outSeconds = total * 1.0e-3f;             // kernel time only, as the reference reports it
+        return 0;
+    }
+
+    a.numRays = numRays; a.rays = (const float4*)rays; a.results = (int4*)results;
+    a.warpCounter = g.counters.as<int>();
     // the counter reset is issued before the first event so the timed interval is the kernel only
     NT_CUDA(cudaMemsetAsync(a.warpCounter, 0, sizeof(int), g.stream));
-    int launches = 0;
-    if (g.deferred && !hostRes && dRays == (const void*)rays) {
+    if (g.deferred) {
         NT_CUDA(launch_trace(a, &launches));
         g.launches += launches;
         return 0;
@@ -427,7 +478,6 @@ int nt_trace_batch(const float* rays, int32_t* results, int numRays, int needClo
     NT_CUDA(launch_trace(a, &launches));
     NT_CUDA(cudaEventRecord(g.evB, g.stream));
     g.launches += launches;
-    if (copy_back(hostRes, dRes, (size_t)numRays * 16)) return 1;
     NT_CUDA(cudaStreamSynchronize(g.stream));
     float ms = 0.0f;
     NT_CUDA(cudaEventElapsedTime(&ms, g.evA, g.evB));

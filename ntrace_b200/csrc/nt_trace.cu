@@ -53,9 +53,9 @@ __device__ __forceinline__ const float4* node_ptr(const float4* nodes, int addr)
     return reinterpret_cast<const float4*>(reinterpret_cast<const char*>(nodes) + addr);
 }
 
-template <int LAYOUT, int BLOCK, int SMEM_N, bool PERSISTENT>
+template <int LAYOUT, int BLOCK, int SMEM_N, bool PERSISTENT, int TRI_MODE>
 __global__ void __launch_bounds__(BLOCK)
-trace_kernel(int numRays, int anyHit,
+trace_kernel(int numRays, int anyHit, int fetchThreshold,
              const float4* __restrict__ rays, int4* __restrict__ results,
              const float4* __restrict__ nodes, const float4* __restrict__ woop,
              const int* __restrict__ triIndices, int* __restrict__ warpCounter)
@@ -170,24 +170,31 @@ trace_kernel(int numRays, int anyHit,
 
             // Postponed leaves: Woop test against each triangle until the terminator.
             while (leafAddr < 0) {
-                for (int triAddr = ~leafAddr;; triAddr += 3) {
-                    const float4 v00 = __ldg(woop + triAddr);
+                // Woop test in exactly the operation order of Intersect::RayTriangleWoop (Util.cpp:99-127), every
+                // product and sum rounded separately (no FMA contraction) and an IEEE reciprocal, so that each
+                // accept/reject decision is bit-identical to the host reference's.
+                // TRI_MODE 0: rows 1 and 2 fetched only when needed (the reference's early-outs, least L1 traffic);
+                // TRI_MODE 1: the three rows of a triangle are requested together (one exposed latency instead of three);
+                // TRI_MODE 2: as 1, plus row 0 of the next triangle is requested before the current one is tested.
+                int triAddr = ~leafAddr;
+                float4 v00 = __ldg(woop + triAddr);
+                for (;;) {
+                    float4 v11, v22, nxt;
+                    if (TRI_MODE >= 1) { v11 = __ldg(woop + triAddr + 1); v22 = __ldg(woop + triAddr + 2); }
                     if (__float_as_int(v00.x) == (int)0x80000000) break;
+                    if (TRI_MODE == 2) nxt = __ldg(woop + triAddr + 3);
 
-                    // Woop test in exactly the operation order of Intersect::RayTriangleWoop (Util.cpp:99-127),
-                    // every product and sum rounded separately (no FMA contraction) and an IEEE reciprocal, so
-                    // that each accept/reject decision is bit-identical to the host reference's.
                     const float Oz = __fsub_rn(__fsub_rn(__fsub_rn(v00.w, __fmul_rn(origx, v00.x)), __fmul_rn(origy, v00.y)), __fmul_rn(origz, v00.z));
                     const float dd = __fadd_rn(__fadd_rn(__fmul_rn(dirx, v00.x), __fmul_rn(diry, v00.y)), __fmul_rn(dirz, v00.z));
                     const float t = __fmul_rn(Oz, __frcp_rn(dd));
 
                     if (t > tmin && t < hitT) {
-                        const float4 v11 = __ldg(woop + triAddr + 1);
+                        if (TRI_MODE == 0) v11 = __ldg(woop + triAddr + 1);
                         const float Ou = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(v11.x, origx), __fmul_rn(v11.y, origy)), __fmul_rn(v11.z, origz)), v11.w);
                         const float Du = __fadd_rn(__fadd_rn(__fmul_rn(v11.x, dirx), __fmul_rn(v11.y, diry)), __fmul_rn(v11.z, dirz));
                         const float u = __fadd_rn(Ou, __fmul_rn(t, Du));
                         if (u >= 0.0f) {
-                            const float4 v22 = __ldg(woop + triAddr + 2);
+                            if (TRI_MODE == 0) v22 = __ldg(woop + triAddr + 2);
                             const float Ov = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(v22.x, origx), __fmul_rn(v22.y, origy)), __fmul_rn(v22.z, origz)), v22.w);
                             const float Dv = __fadd_rn(__fadd_rn(__fmul_rn(v22.x, dirx), __fmul_rn(v22.y, diry)), __fmul_rn(v22.z, dirz));
                             const float v = __fadd_rn(Ov, __fmul_rn(t, Dv));
@@ -198,6 +205,8 @@ trace_kernel(int numRays, int anyHit,
                             }
                         }
                     }
+                    triAddr += 3;
+                    v00 = (TRI_MODE == 2) ? nxt : __ldg(woop + triAddr);
                 }
                 // Another leaf was postponed => process it as well.
                 leafAddr = nodeAddr;
@@ -205,7 +214,7 @@ trace_kernel(int numRays, int anyHit,
             }
 
             // Too few lanes left busy => leave and refill the idle ones (kepler...cu:310-311).
-            if (PERSISTENT && __popc(__activemask()) < kDynamicFetchThreshold) break;
+            if (PERSISTENT && __popc(__activemask()) < fetchThreshold) break;
         }
 
         // ---------------- result ----------------
@@ -226,22 +235,24 @@ constexpr int kBlock = 128;
 // Tuning knobs (defaults chosen from the ncu captures in profiles/; the NT_TRACE_* environment variables exist
 // for experiments only): entries of the traversal stack kept in shared memory, and the shared-memory carveout
 // that decides how many CTAs fit next to the L1.
-struct Tuning { int smemStack; int carveout; };
+struct Tuning { int smemStack; int carveout; int triMode; int fetchThreshold; };
 Tuning tuning()
 {
     static Tuning t = [] {
-        Tuning r{8, 20};
+        Tuning r{8, 20, 0, kDynamicFetchThreshold};
         if (const char* e = getenv("NT_TRACE_SMEM")) r.smemStack = atoi(e);
         if (const char* e = getenv("NT_TRACE_CARVEOUT")) r.carveout = atoi(e);
+        if (const char* e = getenv("NT_TRACE_TRI")) r.triMode = atoi(e);
+        if (const char* e = getenv("NT_TRACE_FETCH")) r.fetchThreshold = atoi(e);
         return r;
     }();
     return t;
 }
 
-template <int LAYOUT, int SMEM_N, bool PERSISTENT>
+template <int LAYOUT, int SMEM_N, bool PERSISTENT, int TRI_MODE>
 cudaError_t launch_variant(const TraceLaunch& a, int* launches)
 {
-    auto kern = trace_kernel<LAYOUT, kBlock, SMEM_N, PERSISTENT>;
+    auto kern = trace_kernel<LAYOUT, kBlock, SMEM_N, PERSISTENT, TRI_MODE>;
     static int blocksPerSM = 0;
     if (!blocksPerSM) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, tuning().carveout);
@@ -252,19 +263,28 @@ cudaError_t launch_variant(const TraceLaunch& a, int* launches)
     }
     int grid = (a.numRays + kBlock - 1) / kBlock;
     if (PERSISTENT && grid > a.numSMs * blocksPerSM) grid = a.numSMs * blocksPerSM;   // one resident wave
-    kern<<<grid, kBlock, 0, a.stream>>>(a.numRays, a.anyHit, a.rays, a.results, a.nodes, a.woop, a.triIndices, a.warpCounter);
+    kern<<<grid, kBlock, 0, a.stream>>>(a.numRays, a.anyHit, tuning().fetchThreshold, a.rays, a.results, a.nodes, a.woop, a.triIndices, a.warpCounter);
     if (launches) *launches = 1;
     return cudaGetLastError();
+}
+
+template <int LAYOUT, bool PERSISTENT, int TRI_MODE>
+cudaError_t launch_tri(const TraceLaunch& a, int* launches)
+{
+    switch (tuning().smemStack) {
+    case 4:  return launch_variant<LAYOUT, 4, PERSISTENT, TRI_MODE>(a, launches);
+    case 16: return launch_variant<LAYOUT, 16, PERSISTENT, TRI_MODE>(a, launches);
+    default: return launch_variant<LAYOUT, 8, PERSISTENT, TRI_MODE>(a, launches);
+    }
 }
 
 template <int LAYOUT, bool PERSISTENT>
 cudaError_t launch_one(const TraceLaunch& a, int* launches)
 {
-    switch (tuning().smemStack) {
-    case 4:  return launch_variant<LAYOUT, 4, PERSISTENT>(a, launches);
-    case 16: return launch_variant<LAYOUT, 16, PERSISTENT>(a, launches);
-    case 24: return launch_variant<LAYOUT, 24, PERSISTENT>(a, launches);
-    default: return launch_variant<LAYOUT, 8, PERSISTENT>(a, launches);
+    switch (tuning().triMode) {
+    case 1:  return launch_tri<LAYOUT, PERSISTENT, 1>(a, launches);
+    case 2:  return launch_tri<LAYOUT, PERSISTENT, 2>(a, launches);
+    default: return launch_tri<LAYOUT, PERSISTENT, 0>(a, launches);
     }
 }
 

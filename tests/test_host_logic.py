@@ -105,3 +105,48 @@ def test_scene_generators_are_exact_and_deterministic():
     lo, hi = scenes.bbox(v)
     c = camera.named_camera(cam)
     assert (c.position > lo).all() and (c.position < hi).all()      # the reference camera sits inside the stand-in room
+
+
+def test_environment_reads_the_reference_config_grammar(tmp_path):
+    from ntrace_b200.environment import Environment, EnvironmentError_
+    text = """
+App {
+benchmark false
+frameWidth 1024   # comment
+}
+Benchmark { scene data/Armadillo/armadillo.obj
+camera GBSvz1V04qy/Ju69/21iChCz/idyKy10A0Kfx1pzUoy/DuY2/0aNqY10sZpuu/5/5f/0/
+kernel fermi_speculative_while_while
+warmupRepeats 1 }
+Renderer {
+# BVH construction currently supported = [SplitBVH, SAHBVH, OcclusionBVH, HLBVH, PersistentBVH]
+builder PersistentKDTree
+rayType primary
+samples 8
+sortRays true
+}
+SubdivisionRayCaster { numWarpsPerBlock 4
+    Nested { depthK1 1.2 } }
+"""
+    p = tmp_path / "config.conf"
+    p.write_text(text)
+    env = Environment()
+    env.Parse([str(p), "-DRenderer.builder=HLBVH", "-DRenderer.rayType=primary;AO", "-renderer_samples=32"])
+    assert env.GetBool("App.benchmark") is False and env.GetInt("App.frameWidth") == 1024 and env.GetInt("App.frameHeight") == 768
+    assert env.GetString("Renderer.builder") == "HLBVH" and env.GetInt("Renderer.samples") == 32
+    assert env.GetString("Benchmark.kernel") == "fermi_speculative_while_while"
+    assert env.GetString("SubdivisionRayCaster.Nested.depthK1") == "1.2"        # unknown sections are kept
+    assert env.GetFloat("SBVH.alpha") == 1.0e-5 and env.GetBool("Renderer.sortRays") is True
+    from ntrace_b200 import camera
+    assert abs(camera.decode_signature(env.GetString("Benchmark.camera")).fov - 73.7) < 0.1
+    with pytest.raises(EnvironmentError_):
+        env.Parse(["-DApp.frameWidth=wide"])
+    with pytest.raises(EnvironmentError_):
+        Environment().ParseEnvString("App { benchmark true")
+    with pytest.raises(EnvironmentError_):
+        Environment().ParseEnvString("}")
+    # the reference's shipped config.conf parses unchanged when present (not on the GPU box)
+    import os
+    if os.path.exists("/root/reference/config.conf"):
+        e2 = Environment(); e2.ReadEnvFile("/root/reference/config.conf")
+        assert e2.GetString("Renderer.dataStructure") == "KDTree" and e2.GetInt("Benchmark.measureRepeats") == 5
