@@ -116,6 +116,11 @@ int nt_raygen_ao(float* outRays, int32_t* outIDToSlot, int32_t* outSlotToID,
                  const float* inRays, const int32_t* inResults, const float* triNormals,
                  int firstInputSlot, int numInputRays, int numSamples,
                  float maxDist, uint32_t randomSeed);
+/* RayBuffer::mortonSort (src/rt/ray/RayBuffer.cpp:103-163): reorder the batch in place by the Morton key of
+ * (origin, direction) and rebuild the id<->slot maps (outSlotToID[new] = inSlotToID[old], outIDToSlot[id] = new).
+ * The reference sorts 192-bit keys on the CPU; here the top 64 significant key bits are radix-sorted on the GPU, ties
+ * keep their original order. */
+int nt_ray_sort(float* rays, int32_t* idToSlot, int32_t* slotToID, int numRays);
 /* countHitsKernel (RendererKernels.cu:174-224, Renderer.cpp:693-705): results with id >= 0. */
 int nt_count_hits(const int32_t* results, int numRays, int* outHits);
 /* Scene::triNormal (src/rt/Scene.cpp:112): normalize(cross(v1 - v0, v2 - v0)) per triangle. */

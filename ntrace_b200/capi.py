@@ -28,7 +28,7 @@ EXPORTS = [
     "nt_set_kernel", "nt_desired_layout", "nt_kernel_config",
     "nt_bvh_upload", "nt_bvh_alloc", "nt_bvh_build", "nt_bvh_sizes", "nt_bvh_download",
     "nt_bvh_device_ptrs", "nt_bvh_build_debug",
-    "nt_trace_batch", "nt_raygen_primary", "nt_raygen_ao", "nt_count_hits", "nt_tri_normals",
+    "nt_trace_batch", "nt_raygen_primary", "nt_raygen_ao", "nt_ray_sort", "nt_count_hits", "nt_tri_normals",
 ]
 
 
@@ -206,6 +206,12 @@ def raygen_ao(out_rays, out_id_to_slot, out_slot_to_id, in_rays, in_results, tri
     _check(lib().nt_raygen_ao(ptr(out_rays, np.float32, count * samples * 32), ptr(out_id_to_slot, np.int32), ptr(out_slot_to_id, np.int32),
                               ptr(in_rays, np.float32), ptr(in_results, np.int32), ptr(tri_normals, np.float32),
                               C.c_int(first), C.c_int(count), C.c_int(samples), C.c_float(max_dist), C.c_uint32(seed)))
+
+
+def ray_sort(rays, id_to_slot, slot_to_id, num_rays: int):
+    """RayBuffer::mortonSort, in place."""
+    _check(lib().nt_ray_sort(ptr(rays, np.float32, num_rays * 32), ptr(id_to_slot, np.int32, num_rays * 4), ptr(slot_to_id, np.int32, num_rays * 4),
+                             C.c_int(num_rays)))
 
 
 def count_hits(results, num_rays: int) -> int:

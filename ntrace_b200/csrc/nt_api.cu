@@ -548,6 +548,34 @@ int nt_raygen_ao(float* outRays, int32_t* outIDToSlot, int32_t* outSlotToID, con
     return 0;
 }
 
+int nt_ray_sort(float* rays, int32_t* idToSlot, int32_t* slotToID, int numRays)
+{
+    std::lock_guard<std::mutex> lock(g_mutex);
+    if (require_init()) return 1;
+    if (numRays <= 1) return 0;
+    if (!rays || !idToSlot || !slotToID) { set_error("ntrace_b200: null ray buffer"); return 1; }
+    const bool dev = is_device_ptr(rays);
+    if (dev != is_device_ptr(idToSlot) || dev != is_device_ptr(slotToID)) { set_error("ntrace_b200: ray buffer and id maps must live on the same side"); return 1; }
+    float4* dRays = (float4*)rays; int* dI2S = idToSlot; int* dS2I = slotToID;
+    if (!dev) {
+        NT_CUDA(g.stRays.reserve((size_t)numRays * 32)); NT_CUDA(g.stA.reserve((size_t)numRays * 4)); NT_CUDA(g.stB.reserve((size_t)numRays * 4));
+        dRays = g.stRays.as<float4>(); dI2S = g.stA.as<int>(); dS2I = g.stB.as<int>();
+        NT_CUDA(cudaMemcpyAsync(dRays, rays, (size_t)numRays * 32, cudaMemcpyHostToDevice, g.stream));
+        NT_CUDA(cudaMemcpyAsync(dS2I, slotToID, (size_t)numRays * 4, cudaMemcpyHostToDevice, g.stream));
+    }
+    int launches = 0;
+    cudaError_t e = ray_sort_device(dRays, dI2S, dS2I, numRays, g.stream, g.numSMs, &launches);
+    g.launches += launches;
+    NT_CUDA(e);
+    if (!dev) {
+        NT_CUDA(cudaMemcpyAsync(rays, dRays, (size_t)numRays * 32, cudaMemcpyDeviceToHost, g.stream));
+        NT_CUDA(cudaMemcpyAsync(idToSlot, dI2S, (size_t)numRays * 4, cudaMemcpyDeviceToHost, g.stream));
+        NT_CUDA(cudaMemcpyAsync(slotToID, dS2I, (size_t)numRays * 4, cudaMemcpyDeviceToHost, g.stream));
+    }
+    NT_CUDA(cudaStreamSynchronize(g.stream));
+    return 0;
+}
+
 int nt_count_hits(const int32_t* results, int numRays, int* outHits)
 {
     std::lock_guard<std::mutex> lock(g_mutex);

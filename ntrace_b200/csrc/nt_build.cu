@@ -24,15 +24,13 @@
 //     node (atomicAdd + __threadfence), writing child boxes straight into the parent's node words.
 // One host readback (node / leaf counts, to size the output buffers) instead of one per level.
 #include "nt_common.cuh"
+#include "nt_sort.cuh"
 #include <cooperative_groups.h>
 #include <cstring>
 
 namespace nt {
 
 namespace {
-
-typedef unsigned int uint;
-typedef unsigned long long u64;
 
 constexpr float kF32Max = 3.402823466e+38f;
 
@@ -74,158 +72,6 @@ __global__ void __launch_bounds__(256) morton_kernel(const float* __restrict__ v
     const uint qx = (uint)quantise(mx, lox, sx, 1024), qy = (uint)quantise(my, loy, sy, 1024), qz = (uint)quantise(mz, loz, sz, 1024);
     keys[t] = spread10(qx) | (spread10(qy) << 1) | (spread10(qz) << 2);
     idx[t] = t;
-}
-
-// ------------------------------------------------------------------------------------------------
-// Exclusive scan (reduce / scan block sums / apply), T = uint or u64.  Hand-written, no CUB/thrust.
-// ------------------------------------------------------------------------------------------------
-constexpr int kScanThreads = 256;
-constexpr int kScanItems = 8;
-constexpr int kScanTile = kScanThreads * kScanItems;
-
-template <class T>
-__device__ __forceinline__ T block_exclusive(T v, T* s_warp, T& total)
-{
-    // exclusive scan of one value per thread across a 256-thread block
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    T inc = v;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { T y = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += y; }
-    if (lane == 31) s_warp[w] = inc;
-    __syncthreads();
-    if (w == 0) {
-        T x = (lane < kScanThreads / 32) ? s_warp[lane] : T(0);
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { T y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
-        if (lane < kScanThreads / 32) s_warp[lane] = x;          // inclusive over warps
-    }
-    __syncthreads();
-    const T warpBase = (w == 0) ? T(0) : s_warp[w - 1];
-    total = s_warp[kScanThreads / 32 - 1];
-    __syncthreads();
-    return warpBase + inc - v;
-}
-
-template <class T>
-__global__ void __launch_bounds__(kScanThreads) scan_reduce_kernel(const T* __restrict__ in, long long n, T* __restrict__ blockSums)
-{
-    __shared__ T s_warp[kScanThreads / 32];
-    const long long base = (long long)blockIdx.x * kScanTile + (long long)threadIdx.x * kScanItems;
-    T sum = 0;
-#pragma unroll
-    for (int i = 0; i < kScanItems; i++) if (base + i < n) sum += in[base + i];
-    T total;
-    block_exclusive<T>(sum, s_warp, total);
-    if (threadIdx.x == 0) blockSums[blockIdx.x] = total;
-}
-
-template <class T>
-__global__ void __launch_bounds__(kScanThreads) scan_sums_kernel(T* __restrict__ blockSums, int numBlocks, T* __restrict__ grandTotal)
-{
-    __shared__ T s_warp[kScanThreads / 32];
-    T carry = 0;
-    for (int base = 0; base < numBlocks; base += kScanThreads) {
-        const int i = base + threadIdx.x;
-        const T v = (i < numBlocks) ? blockSums[i] : T(0);
-        T total;
-        const T ex = block_exclusive<T>(v, s_warp, total);
-        if (i < numBlocks) blockSums[i] = carry + ex;
-        carry += total;
-    }
-    if (threadIdx.x == 0 && grandTotal) *grandTotal = carry;
-}
-
-template <class T>
-__global__ void __launch_bounds__(kScanThreads) scan_apply_kernel(const T* __restrict__ in, T* __restrict__ out, long long n, const T* __restrict__ blockSums)
-{
-    __shared__ T s_warp[kScanThreads / 32];
-    const long long base = (long long)blockIdx.x * kScanTile + (long long)threadIdx.x * kScanItems;
-    T v[kScanItems];
-    T sum = 0;
-#pragma unroll
-    for (int i = 0; i < kScanItems; i++) { v[i] = (base + i < n) ? in[base + i] : T(0); sum += v[i]; }
-    T total;
-    T run = block_exclusive<T>(sum, s_warp, total) + blockSums[blockIdx.x];
-#pragma unroll
-    for (int i = 0; i < kScanItems; i++) { if (base + i < n) out[base + i] = run; run += v[i]; }
-}
-
-template <class T>
-cudaError_t exclusive_scan(const T* in, T* out, long long n, T* blockSums /* >= ceil(n/tile) */, T* grandTotal, cudaStream_t s, int* launches)
-{
-    const int nb = (int)((n + kScanTile - 1) / kScanTile);
-    scan_reduce_kernel<T><<<nb, kScanThreads, 0, s>>>(in, n, blockSums);
-    scan_sums_kernel<T><<<1, kScanThreads, 0, s>>>(blockSums, nb, grandTotal);
-    scan_apply_kernel<T><<<nb, kScanThreads, 0, s>>>(in, out, n, blockSums);
-    *launches += 3;
-    return cudaGetLastError();
-}
-
-// ------------------------------------------------------------------------------------------------
-// Stable LSD radix sort of (key, index) pairs, 8-bit digits.
-// ------------------------------------------------------------------------------------------------
-constexpr int kSortThreads = 256;
-constexpr int kSortItems = 8;                       // rounds of 32 consecutive keys per warp
-constexpr int kSortTile = kSortThreads * kSortItems;
-
-__global__ void __launch_bounds__(kSortThreads) radix_hist_kernel(const uint* __restrict__ keys, int n, int shift, uint* __restrict__ hist, int numBlocks)
-{
-    __shared__ uint s_hist[256];
-    s_hist[threadIdx.x] = 0;
-    __syncthreads();
-    const int base = blockIdx.x * kSortTile;
-#pragma unroll
-    for (int r = 0; r < kSortItems; r++) {
-        const int i = base + r * kSortThreads + threadIdx.x;
-        if (i < n) atomicAdd(&s_hist[(keys[i] >> shift) & 255u], 1u);
-    }
-    __syncthreads();
-    hist[threadIdx.x * numBlocks + blockIdx.x] = s_hist[threadIdx.x];     // digit-major: one scan gives global offsets
-}
-
-__global__ void __launch_bounds__(kSortThreads) radix_scatter_kernel(const uint* __restrict__ keysIn, const int* __restrict__ idxIn,
-                                                                     uint* __restrict__ keysOut, int* __restrict__ idxOut,
-                                                                     int n, int shift, const uint* __restrict__ histScan, int numBlocks)
-{
-    __shared__ uint s_cnt[kSortThreads / 32][256];
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    for (int i = threadIdx.x; i < (kSortThreads / 32) * 256; i += kSortThreads) (&s_cnt[0][0])[i] = 0;
-    __syncthreads();
-
-    const int segBase = blockIdx.x * kSortTile + w * (kSortItems * 32);
-    uint key[kSortItems];
-    uint rank[kSortItems];
-#pragma unroll
-    for (int r = 0; r < kSortItems; r++) {
-        const int i = segBase + r * 32 + lane;
-        const bool valid = i < n;
-        key[r] = valid ? keysIn[i] : 0xffffffffu;
-        const uint digit = valid ? ((key[r] >> shift) & 255u) : 256u;
-        const uint peers = __match_any_sync(0xffffffffu, digit);
-        uint pre = 0;
-        if (valid) pre = s_cnt[w][digit];
-        __syncwarp();
-        if (valid && lane == (31 - __clz(peers))) s_cnt[w][digit] = pre + __popc(peers);
-        __syncwarp();
-        rank[r] = pre + __popc(peers & ((1u << lane) - 1u));
-    }
-    __syncthreads();
-    {
-        // digit = threadIdx.x: exclusive prefix over the warps of this tile + global base of (digit, tile)
-        uint run = histScan[threadIdx.x * numBlocks + blockIdx.x];
-#pragma unroll
-        for (int ww = 0; ww < kSortThreads / 32; ww++) { const uint c = s_cnt[ww][threadIdx.x]; s_cnt[ww][threadIdx.x] = run; run += c; }
-    }
-    __syncthreads();
-#pragma unroll
-    for (int r = 0; r < kSortItems; r++) {
-        const int i = segBase + r * 32 + lane;
-        if (i < n) {
-            const uint pos = s_cnt[w][(key[r] >> shift) & 255u] + rank[r];
-            keysOut[pos] = key[r];
-            idxOut[pos] = idxIn[i];
-        }
-    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -525,14 +371,36 @@ __global__ void __launch_bounds__(256) cluster_box_init_kernel(int numClusters, 
 __global__ void __launch_bounds__(256) cluster_box_kernel(int n, const uint* __restrict__ clusterOf, const float* __restrict__ verts,
                                                            const int* __restrict__ tris, const int* __restrict__ idx, int* __restrict__ boxI)
 {
+    // Sorted positions of one cluster are contiguous, so the lanes of a warp form a few contiguous segments: reduce each
+    // segment with shuffles and let only its first lane touch memory (ordered-int atomics: the result is order independent).
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= n) return;
-    const int t = __ldg(idx + p);
-    const F3 a = ld3(verts, __ldg(tris + 3 * t)), b = ld3(verts, __ldg(tris + 3 * t + 1)), c = ld3(verts, __ldg(tris + 3 * t + 2));
-    const F3 lo = min3v(a, min3v(b, c)), hi = max3v(a, max3v(b, c));
-    int* bx = boxI + (size_t)clusterOf[p] * 6;
-    atomicMin(bx + 0, f2i_ord(lo.x)); atomicMin(bx + 1, f2i_ord(lo.y)); atomicMin(bx + 2, f2i_ord(lo.z));
-    atomicMax(bx + 3, f2i_ord(hi.x)); atomicMax(bx + 4, f2i_ord(hi.y)); atomicMax(bx + 5, f2i_ord(hi.z));
+    const int lane = threadIdx.x & 31;
+    const bool valid = p < n;
+    uint cid = 0xffffffffu;
+    float lo[3] = {kF32Max, kF32Max, kF32Max}, hi[3] = {-kF32Max, -kF32Max, -kF32Max};
+    if (valid) {
+        cid = clusterOf[p];
+        const int t = __ldg(idx + p);
+        const F3 a = ld3(verts, __ldg(tris + 3 * t)), b = ld3(verts, __ldg(tris + 3 * t + 1)), c = ld3(verts, __ldg(tris + 3 * t + 2));
+        const F3 l = min3v(a, min3v(b, c)), h = max3v(a, max3v(b, c));
+        lo[0] = l.x; lo[1] = l.y; lo[2] = l.z; hi[0] = h.x; hi[1] = h.y; hi[2] = h.z;
+    }
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint oc = __shfl_down_sync(0xffffffffu, cid, o);
+        const bool take = (lane + o < 32) && (oc == cid);
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            const float ol = __shfl_down_sync(0xffffffffu, lo[k], o), oh = __shfl_down_sync(0xffffffffu, hi[k], o);
+            if (take) { lo[k] = fminf(lo[k], ol); hi[k] = fmaxf(hi[k], oh); }
+        }
+    }
+    const uint pc = __shfl_up_sync(0xffffffffu, cid, 1);
+    if (valid && (lane == 0 || pc != cid)) {
+        int* bx = boxI + (size_t)cid * 6;
+        atomicMin(bx + 0, f2i_ord(lo[0])); atomicMin(bx + 1, f2i_ord(lo[1])); atomicMin(bx + 2, f2i_ord(lo[2]));
+        atomicMax(bx + 3, f2i_ord(hi[0])); atomicMax(bx + 4, f2i_ord(hi[1])); atomicMax(bx + 5, f2i_ord(hi[2]));
+    }
 }
 
 constexpr int kBins = 8;            // BIN_CNT (emitTreeKernel.cuh:9)
@@ -609,6 +477,11 @@ __global__ void __launch_bounds__(kTopThreads) hlbvh_top_kernel(TopArgs a)
         a.scal[0] = 1; a.scal[1] = 1;
     }
     for (int c = gtid; c < a.C; c += gsize) a.clsTask[0][c] = 0;
+    for (int i = gtid; i < 3 * kBins; i += gsize) {                       // initBins for the root task
+        int* b = a.binBoxI + (size_t)i * 6;
+        b[0] = b[1] = b[2] = f2i_ord(kF32Max); b[3] = b[4] = b[5] = f2i_ord(-kF32Max);
+        a.binCnt[i] = 0;
+    }
     grid.sync();
 
     for (;;) {
@@ -618,13 +491,7 @@ __global__ void __launch_bounds__(kTopThreads) hlbvh_top_kernel(TopArgs a)
         const float* tBox = a.tBox[cur]; const int* tCnt = a.tCnt[cur]; const int* tId = a.tId[cur];
         const int* clsTask = a.clsTask[cur]; int* clsNext = a.clsTask[cur ^ 1];
 
-        // ---- initBins
-        for (int i = gtid; i < T * 3 * kBins; i += gsize) {
-            int* b = a.binBoxI + (size_t)i * 6;
-            b[0] = b[1] = b[2] = f2i_ord(kF32Max); b[3] = b[4] = b[5] = f2i_ord(-kF32Max);
-            a.binCnt[i] = 0;
-        }
-        grid.sync();
+        // (bins of this level's tasks were cleared during the previous level's distribute phase / the prologue)
 
         // ---- fillBins
         for (int c = gtid; c < a.C; c += gsize) {
@@ -775,6 +642,13 @@ __global__ void __launch_bounds__(kTopThreads) hlbvh_top_kernel(TopArgs a)
                 }
             }
         }
+        // ---- initBins for the next level's tasks (their bins are not read by anything in this phase: the bins consulted
+        // by distribute are per-task results copied into rSplit/rAxis/rCnt*, and clsBin holds the per-cluster bin ids)
+        for (int i = gtid; i < created * 3 * kBins; i += gsize) {
+            int* b = a.binBoxI + (size_t)i * 6;
+            b[0] = b[1] = b[2] = f2i_ord(kF32Max); b[3] = b[4] = b[5] = f2i_ord(-kF32Max);
+            a.binCnt[i] = 0;
+        }
         grid.sync();
         cur ^= 1;
     }
@@ -900,29 +774,12 @@ cudaError_t build_bvh_device(const float* dVerts, int numVerts, const int* dTris
         return cudaSuccess;
     }
 
-    // ---- stable LSD radix sort, 4 x 8-bit digits over the 30-bit codes
-    {
-        const int nb = (n + kSortTile - 1) / kSortTile;
-        NT_TRY(sc.keysB.reserve((size_t)n * 4));
-        NT_TRY(sc.idxB.reserve((size_t)n * 4));
-        NT_TRY(sc.hist.reserve((size_t)nb * 256 * 4));
-        const long long histLen = (long long)nb * 256;
-        NT_TRY(sc.blockSums.reserve(((size_t)(histLen + kScanTile - 1) / kScanTile + (size_t)(n + kScanTile - 1) / kScanTile + 16) * 8));
-        uint* kin = keysA; int* iin = idxA;
-        uint* kout = sc.keysB.as<uint>(); int* iout = sc.idxB.as<int>();
-        for (int pass = 0; pass < 4; pass++) {
-            const int shift = pass * 8;
-            radix_hist_kernel<<<nb, kSortThreads, 0, stream>>>(kin, n, shift, sc.hist.as<uint>(), nb);
-            launches++;
-            NT_TRY(exclusive_scan<uint>(sc.hist.as<uint>(), sc.hist.as<uint>(), histLen, sc.blockSums.as<uint>(), nullptr, stream, &launches));
-            radix_scatter_kernel<<<nb, kSortThreads, 0, stream>>>(kin, iin, kout, iout, n, shift, sc.hist.as<uint>(), nb);
-            launches++;
-            NT_TRY(cudaGetLastError());
-            uint* tk = kin; kin = kout; kout = tk;
-            int* ti = iin; iin = iout; iout = ti;
-        }
-        // four passes: the sorted data is back in keysA / idxA
-    }
+    // ---- stable LSD radix sort, 4 x 8-bit digits over the 30-bit codes (four passes: sorted data ends in keysA / idxA)
+    NT_TRY(sc.keysB.reserve((size_t)n * 4));
+    NT_TRY(sc.idxB.reserve((size_t)n * 4));
+    NT_TRY(sc.hist.reserve(radix_hist_bytes(n)));
+    NT_TRY(sc.blockSums.reserve(scan_block_sums_bytes((long long)radix_hist_bytes(n) / 4) + scan_block_sums_bytes(n)));
+    NT_TRY(radix_sort_pairs<uint>(keysA, idxA, sc.keysB.as<uint>(), sc.idxB.as<int>(), n, 4, sc.hist.as<uint>(), sc.blockSums.as<uint>(), stream, &launches));
 
     NT_TRY(sc.scalars.reserve(64));
     NT_TRY(cudaMemsetAsync(sc.scalars.p, 0, 64, stream));
@@ -971,7 +828,7 @@ cudaError_t build_bvh_device(const float* dVerts, int numVerts, const int* dTris
         if (!topBlocksPerSM) {
             NT_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&topBlocksPerSM, hlbvh_top_kernel, kTopThreads, 0));
             if (topBlocksPerSM < 1) topBlocksPerSM = 1;
-            if (topBlocksPerSM > 4) topBlocksPerSM = 4;
+            if (topBlocksPerSM > 1) topBlocksPerSM = 1;       // fewer CTAs = cheaper grid.sync; the phases are latency bound
         }
         const int grid = numSMs * topBlocksPerSM;
         NT_TRY(sc.blockSum.reserve((size_t)grid * 4));

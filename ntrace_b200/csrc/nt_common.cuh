@@ -65,6 +65,9 @@ cudaError_t launch_raygen_ao(const AOArgs& a, cudaStream_t s);
 cudaError_t launch_count_hits(const int4* results, int numRays, int* dCounter, cudaStream_t s);
 cudaError_t launch_tri_normals(const float* verts, const int* tris, int numTris, float* out, cudaStream_t s);
 
+// ---- ray Morton sort (nt_raysort.cu): in place on device buffers
+cudaError_t ray_sort_device(float4* rays, int* idToSlot, int* slotToID, int numRays, cudaStream_t stream, int numSMs, int* outLaunches);
+
 // ---- GPU LBVH / HLBVH builder (nt_build.cu) ---------------------------------------------------
 struct DevBuf {
     void* p = nullptr; size_t cap = 0;

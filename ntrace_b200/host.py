@@ -80,7 +80,7 @@ class RayBuffer:
     def resize(self, n: int):
         if n < 0:
             raise NtError("RayBuffer: negative size")
-        if n > self._cap:
+        if n > self._cap or self._rays is None:
             t, dev = torch(), device()
             cap = max(n, 1)
             old = (self._rays, self._results, self._id2slot, self._slot2id)
@@ -112,6 +112,12 @@ class RayBuffer:
 
     def getSlotToIDBuffer(self):
         return self._slot2id[: self._size]
+
+    def mortonSort(self):
+        """RayBuffer::mortonSort (RayBuffer.cpp:103-163): reorder rays by Morton key, keep the id<->slot maps consistent."""
+        if self._size > 1:
+            _sync()
+            capi.ray_sort(self.getRayBuffer(), self.getIDToSlotBuffer(), self.getSlotToIDBuffer(), self._size)
 
     def setRays(self, rays_np):
         """Upload host rays (N x 8 float32); ids become the identity."""
@@ -408,6 +414,9 @@ class Renderer:
             self.m_batchRays = self.m_secondaryRays
         else:
             raise NtError(f"unsupported ray type {rt}")
+        # Renderer.cpp:561-562: the reference's condition is a tautology, so primary batches are sorted too
+        if self.m_params.sortSecondary:
+            self.m_batchRays.mortonSort()
         return True
 
     def traceBatch(self) -> float:

@@ -275,6 +275,15 @@ def raygen_ao(in_rays, in_results, normals, first, count, samples, max_dist, see
     return out, a, b
 
 
+def ray_morton_order(rays, truncated=False):
+    """RayBuffer::mortonSort order: order[new] = old slot (+ the 64-bit truncated keys, old-slot indexed)."""
+    rays = _f32(rays).reshape(-1, 8)
+    order = np.zeros(len(rays), dtype=np.int32)
+    k64 = np.zeros(len(rays), dtype=np.uint64)
+    lib().orc_ray_morton_order(_p(rays), C.c_int(len(rays)), C.c_int(1 if truncated else 0), _p(order), _p(k64))
+    return order, k64
+
+
 def count_hits(results) -> int:
     results = _i32(results).reshape(-1, 4)
     return int(lib().orc_count_hits(_p(results), C.c_int(len(results))))

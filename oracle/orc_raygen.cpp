@@ -170,3 +170,67 @@ void tri_normals(const Scene& sc, V3* out)
 }
 
 } // namespace orc
+
+// ---- RayBuffer::mortonSort restated (RayBuffer.cpp:88-163, RayBufferKernels.cu:62-196) ---------------------------
+namespace orc {
+
+static inline uint32_t f2u_sat(float f)
+{
+    if (!(f > 0.0f)) return 0u;                    // NaN and negatives -> 0 (device conversion semantics)
+    if (f >= 4294967296.0f) return 0xFFFFFFFFu;
+    return (uint32_t)f;
+}
+
+void ray_morton_keys(const Ray* rays, int n, uint32_t* keys6 /* n*6 */, float aabb[6])
+{
+    V3 lo(F32_MAX, F32_MAX, F32_MAX), hi(-F32_MAX, -F32_MAX, -F32_MAX);
+    for (int i = 0; i < n; i++) {                  // findAABBKernel: origins and end points
+        V3 o = rays[i].o;
+        lo = vmin(lo, o); hi = vmax(hi, o);
+        V3 e = o + rays[i].d * rays[i].tmax;
+        lo = vmin(lo, e); hi = vmax(hi, e);
+    }
+    aabb[0] = lo.x; aabb[1] = lo.y; aabb[2] = lo.z; aabb[3] = hi.x; aabb[4] = hi.y; aabb[5] = hi.z;
+    for (int i = 0; i < n; i++) {                  // genMortonKeysKernel
+        V3 a = (rays[i].o - lo) / (hi - lo);
+        V3 nd = normalize(rays[i].d);
+        V3 b = V3((nd.x + 1.0f) * 0.5f, (nd.y + 1.0f) * 0.5f, (nd.z + 1.0f) * 0.5f);
+        uint32_t comp[6] = {f2u_sat(a.x * 256.0f * 65536.0f), f2u_sat(a.y * 256.0f * 65536.0f), f2u_sat(a.z * 256.0f * 65536.0f),
+                            f2u_sat(b.x * 32.0f * 65536.0f), f2u_sat(b.y * 32.0f * 65536.0f), f2u_sat(b.z * 32.0f * 65536.0f)};
+        uint32_t* h = keys6 + (size_t)i * 6;
+        for (int k = 0; k < 6; k++) h[k] = 0;
+        for (int k = 0; k < 6; k++)               // collectBits
+            for (int bit = 0; bit < 32; bit++) {
+                int pos = k + bit * 6;
+                h[pos >> 5] |= ((comp[k] >> bit) & 1u) << (pos & 31);
+            }
+    }
+}
+
+// order[new] = old slot.  truncated == 0: full 192-bit comparator of compareMortonKey (hash[5] most significant), ties by
+// old slot (the reference's quicksort leaves ties unspecified); truncated != 0: only key bits [83,147) compared.
+void ray_morton_order(const Ray* rays, int n, int truncated, int32_t* order, uint64_t* key64Out)
+{
+    std::vector<uint32_t> keys((size_t)n * 6);
+    float aabb[6];
+    ray_morton_keys(rays, n, keys.data(), aabb);
+    std::vector<uint64_t> k64(n);
+    for (int i = 0; i < n; i++) {
+        const uint32_t* h = &keys[(size_t)i * 6];
+        uint64_t v = 0;
+        for (int pos = 83; pos < 147; pos++) v |= (uint64_t)((h[pos >> 5] >> (pos & 31)) & 1u) << (pos - 83);
+        k64[i] = v;
+    }
+    for (int i = 0; i < n; i++) order[i] = i;
+    if (truncated)
+        std::stable_sort(order, order + n, [&](int a, int b) { return k64[a] < k64[b]; });
+    else
+        std::stable_sort(order, order + n, [&](int a, int b) {
+            const uint32_t* x = &keys[(size_t)a * 6]; const uint32_t* y = &keys[(size_t)b * 6];
+            for (int w = 5; w >= 0; w--) if (x[w] != y[w]) return x[w] < y[w];
+            return false;
+        });
+    if (key64Out) for (int i = 0; i < n; i++) key64Out[i] = k64[i];
+}
+
+} // namespace orc

@@ -14,3 +14,8 @@ int  count_hits(const RayResult* results, int n);                               
 void tri_normals(const Scene& sc, V3* out);                                                    // Scene.cpp:112
 
 } // namespace orc
+
+namespace orc {
+void ray_morton_keys(const Ray* rays, int n, uint32_t* keys6, float aabb[6]);                     // RayBufferKernels.cu:62-163
+void ray_morton_order(const Ray* rays, int n, int truncated, int32_t* order, uint64_t* key64Out);  // RayBuffer.cpp:88-149
+}
