@@ -405,6 +405,7 @@ __global__ void __launch_bounds__(256) cluster_box_kernel(int n, const uint* __r
 
 constexpr int kBins = 8;            // BIN_CNT (emitTreeKernel.cuh:9)
 constexpr int kTopThreads = 256;
+constexpr int kSmemTasks = 32;      // levels with at most this many tasks bin through shared memory first
 
 struct TopArgs {
     int C, leafSize;
@@ -466,6 +467,8 @@ __global__ void __launch_bounds__(kTopThreads) hlbvh_top_kernel(TopArgs a)
     cg::grid_group grid = cg::this_grid();
     __shared__ int s_warp[kTopThreads / 32];
     __shared__ int s_red[2];
+    __shared__ int s_binBox[kSmemTasks * 3 * kBins * 6];
+    __shared__ int s_binCnt[kSmemTasks * 3 * kBins];
     const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
     const int gsize = gridDim.x * blockDim.x;
     int cur = 0;
@@ -493,7 +496,17 @@ __global__ void __launch_bounds__(kTopThreads) hlbvh_top_kernel(TopArgs a)
 
         // (bins of this level's tasks were cleared during the previous level's distribute phase / the prologue)
 
-        // ---- fillBins
+        // ---- fillBins.  While a level has few tasks every cluster hammers the same handful of bins, so the block first
+        // accumulates into a shared-memory copy and flushes one atomic per non-empty bin; deeper levels go straight to L2.
+        const bool binsInSmem = (T <= kSmemTasks);
+        if (binsInSmem) {
+            for (int i = threadIdx.x; i < T * 3 * kBins; i += kTopThreads) {
+                int* b = s_binBox + i * 6;
+                b[0] = b[1] = b[2] = f2i_ord(kF32Max); b[3] = b[4] = b[5] = f2i_ord(-kF32Max);
+                s_binCnt[i] = 0;
+            }
+            __syncthreads();
+        }
         for (int c = gtid; c < a.C; c += gsize) {
             const int t = clsTask[c];
             if (t < 0) continue;
@@ -506,10 +519,23 @@ __global__ void __launch_bounds__(kTopThreads) hlbvh_top_kernel(TopArgs a)
                 const float step = __fdiv_rn(__fsub_rn(th, tl), 8.0f);
                 const int bid = quantise(mid, tl, step, kBins);
                 a.clsBin[c * 3 + k] = bid;
-                int* b = a.binBoxI + ((size_t)(t * 3 + k) * kBins + bid) * 6;
+                const int slot = (t * 3 + k) * kBins + bid;
+                int* b = binsInSmem ? (s_binBox + slot * 6) : (a.binBoxI + (size_t)slot * 6);
                 atomicMin(b + 0, cb[0]); atomicMin(b + 1, cb[1]); atomicMin(b + 2, cb[2]);
                 atomicMax(b + 3, cb[3]); atomicMax(b + 4, cb[4]); atomicMax(b + 5, cb[5]);
-                atomicAdd(a.binCnt + (t * 3 + k) * kBins + bid, 1);
+                atomicAdd(binsInSmem ? (s_binCnt + slot) : (a.binCnt + slot), 1);
+            }
+        }
+        if (binsInSmem) {
+            __syncthreads();
+            for (int i = threadIdx.x; i < T * 3 * kBins; i += kTopThreads) {
+                const int cnt = s_binCnt[i];
+                if (cnt == 0) continue;
+                const int* sb = s_binBox + i * 6;
+                int* b = a.binBoxI + (size_t)i * 6;
+                atomicMin(b + 0, sb[0]); atomicMin(b + 1, sb[1]); atomicMin(b + 2, sb[2]);
+                atomicMax(b + 3, sb[3]); atomicMax(b + 4, sb[4]); atomicMax(b + 5, sb[5]);
+                atomicAdd(a.binCnt + i, cnt);
             }
         }
         grid.sync();
