@@ -88,6 +88,11 @@ int nt_bvh_build(int builder, const float* vtxPos, int numVerts,
                  const float bboxLo[3], const float bboxHi[3],
                  int hlbvhBits, int leafSize, float epsilon,
                  float* outGpuSeconds);
+/* Leaf formation of the GPU builder (NEW).  mode 0 (default) = the reference's rule: a child
+ * range with <= leafSize triangles is a leaf (this is the mode every parity check runs in).  mode 1 = SAH-guided
+ * collapse: the tree is emitted down to single triangles and subtrees are folded back into leaves of at most
+ * maxLeafSize triangles (0 = leafSize) wherever that does not increase the SAH cost (Platform costs Cn = Ct = 1). */
+int nt_bvh_set_collapse(int mode, int maxLeafSize);
 /* sizes[3] = bytes of (nodes, woop, triIndex); layout of the resident BVH in *outLayout. */
 int nt_bvh_sizes(size_t sizes[3], int* outLayout);
 /* CudaBVH::serialize source buffers (CudaBVH.cpp:105-125): copy the device BVH out (host or device dst). */

@@ -26,7 +26,7 @@ EXPORTS = [
     "nt_init", "nt_shutdown", "nt_last_error", "nt_launch_count",
     "nt_event_record", "nt_event_elapsed", "nt_set_deferred", "nt_synchronize",
     "nt_set_kernel", "nt_desired_layout", "nt_kernel_config",
-    "nt_bvh_upload", "nt_bvh_alloc", "nt_bvh_build", "nt_bvh_sizes", "nt_bvh_download",
+    "nt_bvh_upload", "nt_bvh_alloc", "nt_bvh_build", "nt_bvh_set_collapse", "nt_bvh_sizes", "nt_bvh_download",
     "nt_bvh_device_ptrs", "nt_bvh_build_debug",
     "nt_trace_batch", "nt_raygen_primary", "nt_raygen_ao", "nt_ray_sort", "nt_count_hits", "nt_tri_normals",
 ]
@@ -154,6 +154,10 @@ def bvh_build(builder: int, verts, tris, bbox_lo, bbox_hi, hlbvh_bits=4, leaf_si
     _check(lib().nt_bvh_build(C.c_int(builder), ptr(verts, np.float32), C.c_int(nv), ptr(tris, np.int32), C.c_int(nt), lo, hi,
                               C.c_int(hlbvh_bits), C.c_int(leaf_size), C.c_float(epsilon), C.byref(sec)))
     return float(sec.value)
+
+
+def bvh_set_collapse(mode: int, max_leaf: int = 0):
+    _check(lib().nt_bvh_set_collapse(C.c_int(mode), C.c_int(max_leaf)))
 
 
 def bvh_sizes():

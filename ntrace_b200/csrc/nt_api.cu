@@ -65,6 +65,7 @@ struct Context {
     bool haveBVH = false;
     DevBuf sortedKeys, sortedIdx;
     int builtTris = 0;
+    int collapseMode = 0, collapseMaxLeaf = 0;
 
     // staging
     DevBuf stRays, stResults, stA, stB, stC, stD, stE;
@@ -339,6 +340,7 @@ int nt_bvh_build(int builder, const float* vtxPos, int numVerts, const int32_t* 
     if (stage_in(triVtxIndex, (size_t)numTris * 12, g.sceneTris, &dT)) return 1;
     BuildParams p;
     p.builder = builder; p.hlbvhBits = hlbvhBits; p.leafSize = leafSize; p.epsilon = epsilon;
+    p.collapse = g.collapseMode; p.collapseMaxLeaf = g.collapseMaxLeaf;
     for (int i = 0; i < 3; i++) { p.lo[i] = bboxLo[i]; p.hi[i] = bboxHi[i]; }
     BuildOutput out;
     out.nodes = &g.nodes; out.woop = &g.woop; out.triIndex = &g.triIndex;
@@ -363,6 +365,15 @@ int nt_bvh_build(int builder, const float* vtxPos, int numVerts, const int32_t* 
     g.bvhLayout = Layout_Compact;           // HLBVHBuilder output is Compact only (HLBVHBuilder.cpp:33)
     g.haveBVH = true;
     g.builtTris = numTris;
+    return 0;
+}
+
+int nt_bvh_set_collapse(int mode, int maxLeafSize)
+{
+    std::lock_guard<std::mutex> lock(g_mutex);
+    if (mode != 0 && mode != 1) { set_error("ntrace_b200: collapse mode must be 0 (reference leaf rule) or 1 (SAH)"); return 1; }
+    if (maxLeafSize < 0) { set_error("ntrace_b200: negative maxLeafSize"); return 1; }
+    g.collapseMode = mode; g.collapseMaxLeaf = maxLeafSize;
     return 0;
 }
 

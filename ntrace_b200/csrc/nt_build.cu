@@ -111,6 +111,7 @@ __device__ __forceinline__ int gallop_right(int from, int n, Pred pred)
 __global__ void __launch_bounds__(256) topology_kernel(const uint* __restrict__ K, int n, int leafSize, int hb,
                                                         const uint* __restrict__ clusterOf,   // exclusive scan of cluster heads (HLBVH) or null
                                                         const int* __restrict__ clsParent,    // per cluster: topNode*2+side (HLBVH) or null
+                                                        const int* __restrict__ clsStart, int clusterLeaf,   // HLBVH: clusters with <= clusterLeaf triangles are leaves
                                                         int* __restrict__ nodeS, int* __restrict__ nodeE, int* __restrict__ parent,
                                                         uint* __restrict__ flags, int* __restrict__ rootGap)
 {
@@ -153,7 +154,12 @@ __global__ void __launch_bounds__(256) topology_kernel(const uint* __restrict__ 
     }
     const int split = g + 1;
     uint f = 0;
-    if ((e - s) > leafSize || (root && !clsParent)) {
+    bool keep = (e - s) > leafSize || (root && !clsParent);
+    if (keep && clsParent) {                                   // HLBVH: nothing is emitted inside a leaf cluster
+        const uint k = clusterOf[s];
+        if (clsStart[k + 1] - clsStart[k] <= clusterLeaf) keep = false;
+    }
+    if (keep) {
         f = F_KEPT;
         if (split - s <= leafSize) f |= F_LEFT_LEAF;
         if (e - split <= leafSize) f |= F_RIGHT_LEAF;
@@ -170,7 +176,7 @@ __global__ void __launch_bounds__(256) topology_kernel(const uint* __restrict__ 
 // forced leaves hb-1 levels below the cluster root (emitTreeKernel.cu:289-292 `oldLevel == 0`), then scan inputs:
 // pack[i].lo = gap i is an inner node, pack[i].hi = a leaf starts at sorted position i
 __global__ void __launch_bounds__(256) finalize_kernel(int n, int hb, const int* __restrict__ nodeS, const int* __restrict__ parent,
-                                                        uint* __restrict__ flags, uint* __restrict__ pack32)
+                                                        uint* __restrict__ flags, uint* __restrict__ pack32 /* null: flags only */)
 {
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= n - 1) return;
@@ -180,8 +186,21 @@ __global__ void __launch_bounds__(256) finalize_kernel(int n, int hb, const int*
         for (int p = parent[g]; p >= 0; p = parent[p >> 1]) depth++;
         if (depth >= hb) f &= ~(F_KEPT | F_LEFT_LEAF | F_RIGHT_LEAF);
         else if (depth == hb - 1) f |= F_LEFT_LEAF | F_RIGHT_LEAF;
+        f &= ~F_NEED_DEPTH;
         flags[g] = f;
     }
+    if (pack32 && (f & F_KEPT)) {
+        pack32[2 * g] = 1u;
+        if (f & F_LEFT_LEAF) pack32[2 * nodeS[g] + 1] = 1u;
+        if (f & F_RIGHT_LEAF) pack32[2 * (g + 1) + 1] = 1u;
+    }
+}
+
+__global__ void __launch_bounds__(256) pack_kernel(int n, const int* __restrict__ nodeS, const uint* __restrict__ flags, uint* __restrict__ pack32)
+{
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n - 1) return;
+    const uint f = flags[g];
     if (f & F_KEPT) {
         pack32[2 * g] = 1u;
         if (f & F_LEFT_LEAF) pack32[2 * nodeS[g] + 1] = 1u;
@@ -680,6 +699,89 @@ __global__ void __launch_bounds__(kTopThreads) hlbvh_top_kernel(TopArgs a)
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// SAH-guided collapse (optional; not part of the reference, never used for the parity rows).
+// The emitter is run with leaf size 1, then subtrees are folded back into leaves bottom-up wherever a leaf is not
+// more expensive than the subtree under the reference's cost model (Platform: Cn = Ct = 1, BVHNode.cpp:79-94):
+//   C(leaf) = A * Ct * n ,  C(inner) = A * 2 Cn + C(left) + C(right) ,  collapse iff n <= maxLeaf and C(leaf) <= C(inner).
+// One arrival counter per node, as in the refit; the decision is taken by whoever completes the node.
+// ------------------------------------------------------------------------------------------------
+enum : uint { F_COLLAPSED = 16u };
+
+struct CollapseCtx {
+    const int* nodeS; const int* nodeE; const int* parent; uint* flags;
+    float* childBox;      // 12 floats per gap node: child 0 lo/hi, child 1 lo/hi
+    float* childCost;     // 2 floats per gap node
+    int* counters; int maxLeaf;
+};
+
+__device__ __forceinline__ float box_area(const float* lo, const float* hi)
+{
+    const float dx = hi[0] - lo[0], dy = hi[1] - lo[1], dz = hi[2] - lo[2];
+    return 2.0f * (dx * dy + dy * dz + dz * dx);
+}
+
+__global__ void __launch_bounds__(256) collapse_analyse_kernel(int n, CollapseCtx c, const float* __restrict__ verts,
+                                                                const int* __restrict__ tris, const int* __restrict__ idx, float eps)
+{
+    const int g0 = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g0 >= n - 1) return;
+    const uint f0 = c.flags[g0];
+    if (!(f0 & F_KEPT)) return;
+    int arrivals = 0;
+    for (int side = 0; side < 2; side++) {
+        if (!(f0 & (side ? F_RIGHT_LEAF : F_LEFT_LEAF))) continue;
+        const int a = side ? g0 + 1 : c.nodeS[g0], b = side ? c.nodeE[g0] : g0 + 1;
+        F3 lo, hi; leaf_box(verts, tris, idx, a, b, eps, lo, hi);
+        float* cb = c.childBox + (size_t)g0 * 12 + side * 6;
+        cb[0] = lo.x; cb[1] = lo.y; cb[2] = lo.z; cb[3] = hi.x; cb[4] = hi.y; cb[5] = hi.z;
+        c.childCost[(size_t)g0 * 2 + side] = box_area(cb, cb + 3) * (float)(b - a);
+        arrivals++;
+    }
+    if (arrivals == 0) return;
+    if (arrivals == 1) { __threadfence(); if (atomicAdd(c.counters + g0, 1) == 0) return; }
+    int g = g0;
+    for (;;) {
+        const float* cb = c.childBox + (size_t)g * 12;
+        float lo[3], hi[3];
+        for (int k = 0; k < 3; k++) { lo[k] = fminf(__ldcg(cb + k), __ldcg(cb + 6 + k)); hi[k] = fmaxf(__ldcg(cb + 3 + k), __ldcg(cb + 9 + k)); }
+        const float area = box_area(lo, hi);
+        const int count = c.nodeE[g] - c.nodeS[g];
+        float cost = 2.0f * area + __ldcg(c.childCost + (size_t)g * 2) + __ldcg(c.childCost + (size_t)g * 2 + 1);
+        const int p = c.parent[g];
+        if (p >= 0 && count <= c.maxLeaf && area * (float)count <= cost) {      // roots of clusters / of the tree never fold
+            cost = area * (float)count;
+            c.flags[g] |= F_COLLAPSED;
+        }
+        if (p < 0) return;
+        const int pg = p >> 1, side = p & 1;
+        float* pb = c.childBox + (size_t)pg * 12 + side * 6;
+        for (int k = 0; k < 3; k++) { pb[k] = lo[k]; pb[3 + k] = hi[k]; }
+        c.childCost[(size_t)pg * 2 + side] = cost;
+        __threadfence();
+        if (atomicAdd(c.counters + pg, 1) == 0) return;
+        g = pg;
+    }
+}
+
+// top-down resolution: a node below a folded ancestor disappears; a folded node becomes a leaf child of its parent
+__global__ void __launch_bounds__(256) collapse_resolve_kernel(int n, const int* __restrict__ parent, const uint* __restrict__ flagsIn,
+                                                                uint* __restrict__ flagsOut)
+{
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n - 1) return;
+    const uint f = flagsIn[g];
+    if (!(f & F_KEPT)) return;
+    bool below = false;
+    for (int p = parent[g]; p >= 0; p = parent[p >> 1]) if (flagsIn[p >> 1] & F_COLLAPSED) { below = true; break; }
+    if (below) { atomicAnd(flagsOut + g, ~(F_KEPT | F_LEFT_LEAF | F_RIGHT_LEAF)); return; }
+    if (f & F_COLLAPSED) {
+        atomicAnd(flagsOut + g, ~(F_KEPT | F_LEFT_LEAF | F_RIGHT_LEAF));
+        const int p = parent[g];
+        atomicOr(flagsOut + (p >> 1), (p & 1) ? F_RIGHT_LEAF : F_LEFT_LEAF);
+    }
+}
+
 // Woop rows of one triangle, 3x3 adjugate form of the reference (calcWoop, emitTreeKernel.cu:574-635),
 // evaluated without FMA contraction so the rows are reproducible bit for bit.
 __device__ __forceinline__ void calc_woop(F3 v0, F3 v1, F3 v2, float4& o0, float4& o1, float4& o2)
@@ -751,6 +853,7 @@ __global__ void single_triangle_kernel(const float* __restrict__ verts, const in
 
 struct Scratch {
     DevBuf keysB, idxB, hist, blockSums, nodeS, nodeE, parent, flags, pack, ex, counters, scalars;
+    DevBuf childBox, childCost, flags2;      // SAH collapse
     // HLBVH
     DevBuf clsHead, clusterOf, clsStart, clsBox, clsTask0, clsTask1, clsBin, clsParent;
     DevBuf tBox0, tBox1, tCnt0, tCnt1, tId0, tId1, rInts, rBoxes, binBox, binCnt, blockSum, topNodes, topParent, topCounters;
@@ -887,11 +990,27 @@ cudaError_t build_bvh_device(const float* dVerts, int numVerts, const int* dTris
     NT_TRY(sc.counters.reserve((size_t)n * 4));
     NT_TRY(cudaMemsetAsync(sc.pack.p, 0, (size_t)n * 8, stream));
     NT_TRY(cudaMemsetAsync(sc.counters.p, 0, (size_t)n * 4, stream));
-    topology_kernel<<<(gaps + 255) / 256, 256, 0, stream>>>(keysA, n, p.leafSize, hb, hl ? sc.clusterOf.as<uint>() : nullptr,
-                                                             hl ? sc.clsParent.as<int>() : nullptr,
+    const bool collapse = (p.collapse != 0);
+    const int emitLeaf = collapse ? 1 : p.leafSize;          // SAH collapse starts from single-triangle leaves
+    topology_kernel<<<(gaps + 255) / 256, 256, 0, stream>>>(keysA, n, emitLeaf, hb, hl ? sc.clusterOf.as<uint>() : nullptr,
+                                                             hl ? sc.clsParent.as<int>() : nullptr, hl ? sc.clsStart.as<int>() : nullptr, p.leafSize,
                                                              sc.nodeS.as<int>(), sc.nodeE.as<int>(), sc.parent.as<int>(), sc.flags.as<uint>(), rootGap);
-    finalize_kernel<<<(gaps + 255) / 256, 256, 0, stream>>>(n, hb, sc.nodeS.as<int>(), sc.parent.as<int>(), sc.flags.as<uint>(), sc.pack.as<uint>());
+    finalize_kernel<<<(gaps + 255) / 256, 256, 0, stream>>>(n, hb, sc.nodeS.as<int>(), sc.parent.as<int>(), sc.flags.as<uint>(),
+                                                             collapse ? nullptr : sc.pack.as<uint>());
     launches += 2;
+    if (collapse) {
+        NT_TRY(sc.childBox.reserve((size_t)n * 48)); NT_TRY(sc.childCost.reserve((size_t)n * 8)); NT_TRY(sc.flags2.reserve((size_t)n * 4));
+        CollapseCtx cx;
+        cx.nodeS = sc.nodeS.as<int>(); cx.nodeE = sc.nodeE.as<int>(); cx.parent = sc.parent.as<int>(); cx.flags = sc.flags.as<uint>();
+        cx.childBox = sc.childBox.as<float>(); cx.childCost = sc.childCost.as<float>(); cx.counters = sc.counters.as<int>();
+        cx.maxLeaf = (p.collapseMaxLeaf > 0) ? p.collapseMaxLeaf : p.leafSize;
+        collapse_analyse_kernel<<<(gaps + 255) / 256, 256, 0, stream>>>(n, cx, dVerts, dTris, idxA, p.epsilon);
+        NT_TRY(cudaMemcpyAsync(sc.flags2.p, sc.flags.p, (size_t)gaps * 4, cudaMemcpyDeviceToDevice, stream));
+        collapse_resolve_kernel<<<(gaps + 255) / 256, 256, 0, stream>>>(n, sc.parent.as<int>(), sc.flags2.as<uint>(), sc.flags.as<uint>());
+        pack_kernel<<<(gaps + 255) / 256, 256, 0, stream>>>(n, sc.nodeS.as<int>(), sc.flags.as<uint>(), sc.pack.as<uint>());
+        NT_TRY(cudaMemsetAsync(sc.counters.p, 0, (size_t)n * 4, stream));      // the refit in emit_kernel counts arrivals again
+        launches += 3;
+    }
     if (hl) {
         cluster_leaf_flag_kernel<<<(C + 255) / 256, 256, 0, stream>>>(C, p.leafSize, sc.clsStart.as<int>(), sc.pack.as<uint>());
         launches++;

@@ -80,6 +80,8 @@ struct BuildParams {
     int builder;              // 0 = LBVH, 1 = HLBVH
     int hlbvhBits, leafSize; float epsilon;
     float lo[3], hi[3];
+    int collapse = 0;         // 0 = reference leaf rule (count <= leafSize), 1 = SAH-guided collapse
+    int collapseMaxLeaf = 0;  // largest leaf the collapse may create (0 = leafSize)
 };
 struct BuildOutput {          // device buffers owned by the context
     DevBuf* nodes; DevBuf* woop; DevBuf* triIndex;
