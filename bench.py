@@ -139,10 +139,11 @@ def run_b200(args):
 
     # ---- BVH: GPU LBVH build on rank 0 (timed), NCCL broadcast of the three buffers to the replicas
     build_s = []
+    capi.bvh_set_collapse(args.collapse, LEAF_SIZE)
     if rank == 0:
         for _ in range(1 + 5):
             build_s.append(capi.bvh_build(capi.BUILDER_HLBVH, scene.vtxPos, scene.triVtxIndex, scene.bboxMin, scene.bboxMax,
-                                          4 if args.builder == "hlbvh" else 10, LEAF_SIZE, EPSILON))
+                                          args.hlbvh_bits if args.builder == "hlbvh" else 10, LEAF_SIZE, EPSILON))
     bcast_ms = 0.0
     if world > 1:
         from ntrace_b200 import multigpu
@@ -269,7 +270,7 @@ def run_b200(args):
             "ms_per_step": sec / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": "conference stand-in room(283000, seed=2): primary + AO(32spp, r=5, any-hit) + diffuse(32spp, closest-hit), "
-                                   "1024x768, <=1Mi rays/batch, GPU %s leaf 8" % ("HLBVH(bits 4)" if args.builder == "hlbvh" else "LBVH"),
+                                   "1024x768, <=1Mi rays/batch, GPU %s leaf 8%s" % ("HLBVH(hlbvhBits %d)" % args.hlbvh_bits if args.builder == "hlbvh" else "LBVH", ", SAH-guided collapse" if args.collapse else ""),
                        "rays_traced_per_step_per_gpu": int(sum(traced.values())), "rays_counted_per_step_per_gpu": int(counted_step),
                        "batches_per_step": n_launch_step, "kernel": "b200_persistent_speculative_while_while",
                        "l2": "inputs exceed L2: %.0f MB of rays per step stream from HBM; the %.0f MB BVH is reused within a frame by design"
@@ -386,6 +387,10 @@ def main():
     ap.add_argument("--spp", type=int, default=32)
     ap.add_argument("--builder", default="hlbvh", choices=["hlbvh", "lbvh"],
                     help="GPU builder: hlbvh = Renderer default HLBVHParams{true, 4, 8, 0.001} (Renderer.cpp:201-209); lbvh = hlbvhBits 10")
+    ap.add_argument("--hlbvh-bits", type=int, default=2,
+                    help="HLBVHParams.hlbvhBits for --builder hlbvh (reference Renderer default 4; 2 = finer SAH top level: better tree, +1 ms build)")
+    ap.add_argument("--collapse", type=int, default=1, choices=[0, 1],
+                    help="leaf formation of the GPU builder: 1 = SAH-guided collapse (north_star pipeline, maxLeaf 8), 0 = the reference's count rule")
     ap.add_argument("--profile", action="store_true", help="dev: only the device-timed region (for runs under ncu); prints no JSON")
     args = ap.parse_args()
     if args.impl == "reference":

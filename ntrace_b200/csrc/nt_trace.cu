@@ -60,8 +60,8 @@ trace_kernel(int numRays, int anyHit, int fetchThreshold,
              const float4* __restrict__ nodes, const float4* __restrict__ woop,
              const int* __restrict__ triIndices, int* __restrict__ warpCounter)
 {
-    static_assert(SMEM_N >= 1 && SMEM_N <= kStackSize, "stack split");
-    __shared__ int s_stack[SMEM_N * BLOCK];
+    static_assert(SMEM_N >= 0 && SMEM_N <= kStackSize, "stack split");
+    __shared__ int s_stack[(SMEM_N > 0 ? SMEM_N : 1) * BLOCK];
     int l_stack[(kStackSize > SMEM_N) ? (kStackSize - SMEM_N) : 1];
 
     const int tid = threadIdx.x;
@@ -114,7 +114,7 @@ trace_kernel(int numRays, int anyHit, int fetchThreshold,
                 idirz = 1.0f / (fabsf(d.z) > ooeps ? d.z : copysignf(ooeps, d.z));
                 oodx = origx * idirx; oody = origy * idiry; oodz = origz * idirz;
                 sp = 0;
-                sbase[0] = kEntrypointSentinel;
+                if (SMEM_N > 0) sbase[0] = kEntrypointSentinel; else l_stack[0] = kEntrypointSentinel;
                 leafAddr = 0;
                 nodeAddr = 0;
                 hitIndex = -1;
@@ -272,6 +272,7 @@ template <int LAYOUT, bool PERSISTENT, int TRI_MODE>
 cudaError_t launch_tri(const TraceLaunch& a, int* launches)
 {
     switch (tuning().smemStack) {
+    case 0:  return launch_variant<LAYOUT, 0, PERSISTENT, TRI_MODE>(a, launches);
     case 4:  return launch_variant<LAYOUT, 4, PERSISTENT, TRI_MODE>(a, launches);
     case 16: return launch_variant<LAYOUT, 16, PERSISTENT, TRI_MODE>(a, launches);
     default: return launch_variant<LAYOUT, 8, PERSISTENT, TRI_MODE>(a, launches);
