@@ -8,6 +8,7 @@
 #include "../../include/ntrace_b200.h"
 #include "nt_common.cuh"
 
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <vector>
@@ -84,6 +85,19 @@ bool is_device_ptr(const void* p)
     cudaError_t e = cudaPointerGetAttributes(&at, p);
     if (e != cudaSuccess) { cudaGetLastError(); return false; }
     return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+}
+
+// address the device can dereference for a caller buffer: device/managed memory as is, pinned host memory through its
+// UVA mapping; nullptr for pageable host memory
+template <class T> T* mapped_device_ptr(T* p)
+{
+    if (!p) return nullptr;
+    cudaPointerAttributes at;
+    cudaError_t e = cudaPointerGetAttributes(&at, (const void*)p);
+    if (e != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    if (at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged) return p;
+    if (at.type == cudaMemoryTypeHost && at.devicePointer) return (T*)at.devicePointer;
+    return nullptr;
 }
 
 // device view of a caller buffer that the call only reads
@@ -429,7 +443,12 @@ int nt_trace_batch(const float* rays, int32_t* results, int numRays, int needClo
     if (!g.haveBVH) { set_error("CudaBVHTracer: No BVH!"); return 1; }                          // :98-99
     if (g.bvhLayout != g.kernelLayout) { set_error("CudaBVHTracer: Incorrect BVH layout!"); return 1; }  // :100-101
 
-    const bool raysOnHost = !is_device_ptr(rays), resOnHost = !is_device_ptr(results);
+    // Pinned (page-locked, UVA-mapped) host buffers are traversed in place: the kernel reads rays and writes results
+    // over PCIe (zero copy), which overlaps both transfers with the traversal inside ONE launch.  Pageable host memory
+    // cannot be touched by the device and goes through the staged, chunked copy pipeline below.
+    const void* raysDev = mapped_device_ptr(rays);
+    void* resDev = mapped_device_ptr(results);
+    const bool raysOnHost = (raysDev == nullptr), resOnHost = (resDev == nullptr);
 
     TraceLaunch a;
     a.kernel = g.kernel; a.layout = g.kernelLayout; a.anyHit = needClosestHit ? 0 : 1;
@@ -440,13 +459,14 @@ int nt_trace_batch(const float* rays, int32_t* results, int numRays, int needClo
     if (raysOnHost || resOnHost) {
         // Host buffers (the reference's Buffer would migrate them): stage through device buffers in chunks so that the
         // H2D copy of chunk i+1, the kernel on chunk i and the D2H copy of chunk i-1 overlap on three streams.
-        const float4* dRays = (const float4*)rays; int4* dRes = (int4*)results;
+        const float4* dRays = (const float4*)raysDev; int4* dRes = (int4*)resDev;
         if (raysOnHost) { NT_CUDA(g.stRays.reserve((size_t)numRays * 32)); dRays = g.stRays.as<float4>(); }
         if (resOnHost) { NT_CUDA(g.stResults.reserve((size_t)numRays * 16)); dRes = g.stResults.as<int4>(); }
-        int chunk = (numRays + 7) / 8;
-        if (chunk < 65536) chunk = 65536;
+        static const int wantChunks = [] { const char* e = getenv("NT_E2E_CHUNKS"); int v = e ? atoi(e) : 2; return v < 1 ? 1 : (v > Context::kMaxChunks ? Context::kMaxChunks : v); }();
+        int chunk = (numRays + wantChunks - 1) / wantChunks;
+        if (chunk < 32768) chunk = 32768;
         chunk = (chunk + 127) & ~127;
-        const int numChunks = (numRays + chunk - 1) / chunk;          // <= 8 <= kMaxChunks
+        const int numChunks = (numRays + chunk - 1) / chunk;          // <= wantChunks <= kMaxChunks
         for (int i = 0; i < numChunks; i++) {
             const int lo = i * chunk, cnt = (numRays - lo < chunk) ? numRays - lo : chunk;
             if (raysOnHost) {
@@ -476,11 +496,11 @@ int nt_trace_batch(const float* rays, int32_t* results, int numRays, int needClo
         return 0;
     }
 
-    a.numRays = numRays; a.rays = (const float4*)rays; a.results = (int4*)results;
+    a.numRays = numRays; a.rays = (const float4*)raysDev; a.results = (int4*)resDev;
     a.warpCounter = g.counters.as<int>();
     // the counter reset is issued before the first event so the timed interval is the kernel only
     NT_CUDA(cudaMemsetAsync(a.warpCounter, 0, sizeof(int), g.stream));
-    if (g.deferred) {
+    if (g.deferred && is_device_ptr(rays) && is_device_ptr(results)) {
         NT_CUDA(launch_trace(a, &launches));
         g.launches += launches;
         return 0;

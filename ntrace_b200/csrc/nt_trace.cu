@@ -53,7 +53,7 @@ __device__ __forceinline__ const float4* node_ptr(const float4* nodes, int addr)
     return reinterpret_cast<const float4*>(reinterpret_cast<const char*>(nodes) + addr);
 }
 
-template <int LAYOUT, int BLOCK, int SMEM_N, bool PERSISTENT, int TRI_MODE>
+template <int LAYOUT, int BLOCK, int SMEM_N, bool PERSISTENT, int TRI_MODE, bool PREFETCH = false>
 __global__ void __launch_bounds__(BLOCK)
 trace_kernel(int numRays, int anyHit, int fetchThreshold,
              const float4* __restrict__ rays, int4* __restrict__ results,
@@ -155,6 +155,11 @@ trace_kernel(int numRays, int anyHit, int fetchThreshold,
                     if (trav0 && trav1) {
                         if (c1min < c0min) { const int t = nodeAddr; nodeAddr = c1idx; c1idx = t; }
                         NT_PUSH(c1idx);
+                        if (PREFETCH && c1idx >= 0) {
+                            // the far child will be fetched after the near subtree: start pulling its node into L1 now
+                            const float4* far = node_ptr<LAYOUT>(nodes, c1idx);
+                            asm volatile("prefetch.global.L1 [%0];" :: "l"(far));
+                        }
                     }
                 }
 
@@ -249,10 +254,10 @@ Tuning tuning()
     return t;
 }
 
-template <int LAYOUT, int SMEM_N, bool PERSISTENT, int TRI_MODE>
+template <int LAYOUT, int SMEM_N, bool PERSISTENT, int TRI_MODE, bool PREFETCH = false>
 cudaError_t launch_variant(const TraceLaunch& a, int* launches)
 {
-    auto kern = trace_kernel<LAYOUT, kBlock, SMEM_N, PERSISTENT, TRI_MODE>;
+    auto kern = trace_kernel<LAYOUT, kBlock, SMEM_N, PERSISTENT, TRI_MODE, PREFETCH>;
     static int blocksPerSM = 0;
     if (!blocksPerSM) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, tuning().carveout);
@@ -283,6 +288,7 @@ template <int LAYOUT, bool PERSISTENT>
 cudaError_t launch_one(const TraceLaunch& a, int* launches)
 {
     switch (tuning().triMode) {
+    case 3:  return launch_variant<LAYOUT, 8, PERSISTENT, 0, true>(a, launches);
     case 1:  return launch_tri<LAYOUT, PERSISTENT, 1>(a, launches);
     case 2:  return launch_tri<LAYOUT, PERSISTENT, 2>(a, launches);
     default: return launch_tri<LAYOUT, PERSISTENT, 0>(a, launches);
