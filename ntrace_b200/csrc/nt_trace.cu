@@ -35,6 +35,18 @@ constexpr int kDynamicFetchThreshold = 20;     // reference: kepler_dynamic_fetc
 __device__ __forceinline__ float fmin3(float a, float b, float c) { float r; asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c)); return r; }
 __device__ __forceinline__ float fmax3(float a, float b, float c) { float r; asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c)); return r; }
 
+// 256-bit global loads (new on sm_100: LDG.E.256): one request per 32-byte ray / half node instead of two
+__device__ __forceinline__ void ld256_nc(const float4* p, float4& a, float4& b)
+{
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(p));
+}
+__device__ __forceinline__ void ld256_cs(const float4* p, float4& a, float4& b)
+{
+    asm volatile("ld.global.cs.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(p));
+}
+
 // span begin = max(min(a0,a1), min(b0,b1), min(c0,c1), d); span end = min(max.., d)
 __device__ __forceinline__ float span_begin(float a0, float a1, float b0, float b1, float c0, float c1, float d)
 {
@@ -53,7 +65,7 @@ __device__ __forceinline__ const float4* node_ptr(const float4* nodes, int addr)
     return reinterpret_cast<const float4*>(reinterpret_cast<const char*>(nodes) + addr);
 }
 
-template <int LAYOUT, int BLOCK, int SMEM_N, bool PERSISTENT, int TRI_MODE, bool PREFETCH = false>
+template <int LAYOUT, int BLOCK, int SMEM_N, bool PERSISTENT, int TRI_MODE, bool PREFETCH = false, bool WIDE = false>
 __global__ void __launch_bounds__(BLOCK)
 trace_kernel(int numRays, int anyHit, int fetchThreshold,
              const float4* __restrict__ rays, int4* __restrict__ results,
@@ -104,8 +116,9 @@ trace_kernel(int numRays, int anyHit, int fetchThreshold,
         if (need) {
             if (rayidx >= numRays) { alive = false; rayidx = -1; }
             else {
-                const float4 o = __ldcs(rays + rayidx * 2 + 0);
-                const float4 d = __ldcs(rays + rayidx * 2 + 1);
+                float4 o, d;
+                if (WIDE) ld256_cs(rays + rayidx * 2, o, d);        // 32-byte aligned ray buffer (checked by the launcher)
+                else { o = __ldcs(rays + rayidx * 2 + 0); d = __ldcs(rays + rayidx * 2 + 1); }
                 origx = o.x; origy = o.y; origz = o.z; tmin = o.w;
                 dirx = d.x; diry = d.y; dirz = d.z; hitT = d.w;
                 const float ooeps = exp2f(-80.0f);                      // fermi...cu:94-98
@@ -128,10 +141,13 @@ trace_kernel(int numRays, int anyHit, int fetchThreshold,
             // Inner nodes, until every lane still in this loop holds a postponed leaf.
             while ((unsigned)nodeAddr < (unsigned)kEntrypointSentinel) {
                 const float4* ptr = node_ptr<LAYOUT>(nodes, nodeAddr);
-                const float4 n0xy = __ldg(ptr + 0);   // (c0.lo.x, c0.hi.x, c0.lo.y, c0.hi.y)
-                const float4 n1xy = __ldg(ptr + 1);   // (c1.lo.x, c1.hi.x, c1.lo.y, c1.hi.y)
-                const float4 nz   = __ldg(ptr + 2);   // (c0.lo.z, c0.hi.z, c1.lo.z, c1.hi.z)
-                const float4 cn   = __ldg(ptr + 3);   // (c0, c1, splitInfo, 0) as ints
+                float4 n0xy, n1xy, nz, cn;
+                if (WIDE) {
+                    ld256_nc(ptr, n0xy, n1xy);        // (c0.lo.x, c0.hi.x, c0.lo.y, c0.hi.y), (c1.lo.x, c1.hi.x, c1.lo.y, c1.hi.y)
+                    ld256_nc(ptr + 2, nz, cn);        // (c0.lo.z, c0.hi.z, c1.lo.z, c1.hi.z), (c0, c1, splitInfo, 0) as ints
+                } else {
+                    n0xy = __ldg(ptr + 0); n1xy = __ldg(ptr + 1); nz = __ldg(ptr + 2); cn = __ldg(ptr + 3);
+                }
                 int c0idx = __float_as_int(cn.x), c1idx = __float_as_int(cn.y);
 
                 const float c0lox = n0xy.x * idirx - oodx, c0hix = n0xy.y * idirx - oodx;
@@ -244,7 +260,7 @@ struct Tuning { int smemStack; int carveout; int triMode; int fetchThreshold; };
 Tuning tuning()
 {
     static Tuning t = [] {
-        Tuning r{8, 20, 0, kDynamicFetchThreshold};
+        Tuning r{8, 20, 4, kDynamicFetchThreshold};      // triMode 4 = reference early-outs + 256-bit ray/node loads
         if (const char* e = getenv("NT_TRACE_SMEM")) r.smemStack = atoi(e);
         if (const char* e = getenv("NT_TRACE_CARVEOUT")) r.carveout = atoi(e);
         if (const char* e = getenv("NT_TRACE_TRI")) r.triMode = atoi(e);
@@ -254,10 +270,10 @@ Tuning tuning()
     return t;
 }
 
-template <int LAYOUT, int SMEM_N, bool PERSISTENT, int TRI_MODE, bool PREFETCH = false>
+template <int LAYOUT, int SMEM_N, bool PERSISTENT, int TRI_MODE, bool PREFETCH = false, bool WIDE = false>
 cudaError_t launch_variant(const TraceLaunch& a, int* launches)
 {
-    auto kern = trace_kernel<LAYOUT, kBlock, SMEM_N, PERSISTENT, TRI_MODE, PREFETCH>;
+    auto kern = trace_kernel<LAYOUT, kBlock, SMEM_N, PERSISTENT, TRI_MODE, PREFETCH, WIDE>;
     static int blocksPerSM = 0;
     if (!blocksPerSM) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, tuning().carveout);
@@ -289,6 +305,9 @@ cudaError_t launch_one(const TraceLaunch& a, int* launches)
 {
     switch (tuning().triMode) {
     case 3:  return launch_variant<LAYOUT, 8, PERSISTENT, 0, true>(a, launches);
+    case 4:  if ((reinterpret_cast<size_t>(a.rays) & 31) == 0 && (reinterpret_cast<size_t>(a.nodes) & 63) == 0)
+                 return launch_variant<LAYOUT, 8, PERSISTENT, 0, false, true>(a, launches);
+             return launch_tri<LAYOUT, PERSISTENT, 0>(a, launches);
     case 1:  return launch_tri<LAYOUT, PERSISTENT, 1>(a, launches);
     case 2:  return launch_tri<LAYOUT, PERSISTENT, 2>(a, launches);
     default: return launch_tri<LAYOUT, PERSISTENT, 0>(a, launches);
