@@ -33,8 +33,8 @@ MAX_BATCH = 1 << 20                   # Renderer.cpp:45
 AO_RADIUS = 5.0                       # config.conf:38
 LEAF_SIZE, EPSILON = 8, 0.001         # Renderer.cpp:201-209
 # dram__bytes_read.sum + dram__bytes_write.sum per trace launch, from the ncu --set full captures of one primary, one AO
-# and one diffuse batch weighted by the 1 + 24 + 24 launches of a step (profiles/r1_summary.md)
-NCU_TRAFFIC_BYTES_PER_LAUNCH = 42.3e6
+# and one diffuse batch weighted by the 1 + 24 + 24 launches of a step (profiles/r1_summary.md, round-1b captures: 35.1 / 37.0 / 53.9 MB)
+NCU_TRAFFIC_BYTES_PER_LAUNCH = 45.2e6
 METRIC = "Mrays/s (primary+AO+diffuse, counted rays / trace time, Conference stand-in 283K tris, 1024x768)"
 
 

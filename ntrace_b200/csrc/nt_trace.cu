@@ -29,7 +29,7 @@ namespace nt {
 
 namespace {
 
-constexpr int kStackSize = 64;                 // reference: STACK_SIZE 64 (fermi...cu:41)
+constexpr int kStackSize = 96;                 // reference: STACK_SIZE 64 (fermi...cu:41); SAH/Split trees go 64 deep, keep headroom
 constexpr int kDynamicFetchThreshold = 20;     // reference: kepler_dynamic_fetch.cu:43
 
 __device__ __forceinline__ float fmin3(float a, float b, float c) { float r; asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c)); return r; }

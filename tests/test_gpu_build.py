@@ -266,3 +266,31 @@ def test_randomised_small_inputs_match_restatement(gpu_host, orc):
             _assert_same_tree(orc, (nodes, woop, idx), ref)
         except AssertionError as e:
             raise AssertionError(f"trial {trial}: n={n} leaf={leaf} hlbvh={hl} bits={bits} pad={pad}: {e}") from None
+
+
+def test_trace_through_a_30_level_chain(gpu_host, orc):
+    """Deepest LBVH shape (one split per Morton bit, then a forced leaf): the traversal stack spills past its 8
+    shared-memory entries into the local array; results must still match the CPU trace of the same buffers."""
+    cells = [_demorton(0)] + [_demorton(1 << j) for j in range(30)]
+    v, t, lo, hi = _cells_scene(cells, [60] + [3] * 30)
+    nodes, woop, idx, keys, order, _ = _gpu_build(gpu_host, v, t, lo, hi, 1)
+    assert orc.compact_sah(nodes, woop)["max_depth"] >= 30
+    rng = np.random.default_rng(3)
+    n = 4096
+    rays = np.zeros((n, 8), np.float32)
+    pick = t[rng.integers(0, len(t), n)]
+    targets = (v[pick[:, 0]] + v[pick[:, 1]] + v[pick[:, 2]]) / np.float32(3.0) + rng.normal(0, 0.002, (n, 3)).astype(np.float32)
+    origins = np.array([1500.0, 1400.0, 1300.0], np.float32) + rng.normal(0, 50, (n, 3)).astype(np.float32)
+    d = targets - origins
+    rays[:, 0:3] = origins; rays[:, 4:7] = d / np.linalg.norm(d, axis=1, keepdims=True); rays[:, 7] = 1e5
+    tracer = gpu_host.CudaBVHTracer()
+    tracer.setBVH(gpu_host.CudaBVH(nodes, woop, idx))
+    for kernel in ("b200_persistent_speculative_while_while", "b200_speculative_while_while"):
+        tracer.setKernel(kernel)
+        rb = gpu_host.RayBuffer(); rb.setRays(rays)
+        tracer.traceBatch(rb)
+        got = rb.results_host()
+        ref = orc.compact_trace(nodes, woop, idx, rays, True)
+        assert np.array_equal(got[:, 0], ref[:, 0]) and np.array_equal(got[:, 1], ref[:, 1])
+        assert (ref[:, 0] >= 0).mean() > 0.3
+    tracer.setKernel("b200_persistent_speculative_while_while")
