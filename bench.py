@@ -8,7 +8,7 @@ LBVH.  Rays counted as the reference counts them (Renderer::getTotalNumRays: w*h
 secondary type); Mrays/s = counted rays / device time.
 
     python bench.py --gpus N --steps K --warmup W            # B200 arm (this repo's CUDA path)
-    python bench.py --impl reference ...                      # the reference's CPU path (oracle port), host cores
+    python bench.py --impl reference ...                      # the reference's CPU path (oracle/_ref, else the port), host cores
 
 Prints ONE JSON line on rank 0.  See DESIGN.md "Measurement" for every field.
 """
@@ -336,17 +336,32 @@ def cpu_baseline_leg(verts, tris, cam, args, gpu_bvh=None, sample_batches=None):
 
 
 def run_reference(args):
-    """--impl reference: the reference's own CPU implementation of the path (oracle port; the reference host is
-    Win32-only and cannot be built here), all host threads, same metric/config; rank 0 only."""
+    """--impl reference: the reference's own CPU implementation of the path, all host threads, same metric/config; rank 0
+    only.  When oracle/_ref/libref.so exists (the reference's SplitBVHBuilder + CudaBVH::trace — the tracer its CPURenderer
+    calls, CPURenderer.cpp:108-124 — compiled unmodified, oracle/Makefile) that is what runs (kind "reference"); otherwise
+    the restated port (kind "port").  Rays come from the restated ray generator in both cases (input data, untimed)."""
     if env_int("RANK", 0) != 0:
         return
     import oracle
+    from oracle import ref
     from ntrace_b200 import camera
     verts, tris, cam = make_workload()
     threads = host_threads()
-    cpu = oracle.CpuBVH(verts, tris, oracle.BUILDER_SPLIT, 1, 1, 1.0e-5)
+    use_ref = ref.available() and os.environ.get("NT_BENCH_REFERENCE_PORT", "0") != "1"
+    if use_ref:
+        cpu = ref.RefBVH(verts, tris, split=True, min_leaf=1, max_leaf=1, split_alpha=1.0e-5)     # Renderer.cpp:88-89 leaf prefs
+
+        def trace(r, closest):
+            return cpu.compact_trace(r, closest, nthreads=threads)
+        what = "the reference's own SplitBVHBuilder + CudaBVH::trace (compiled unmodified: oracle/_ref), one CudaBVH per thread, rays split evenly"
+    else:
+        cpu = oracle.CpuBVH(verts, tris, oracle.BUILDER_SPLIT, 1, 1, 1.0e-5)
+
+        def trace(r, closest):
+            return cpu.trace(r, closest, nthreads=threads)
+        what = "restated SplitBVH + BVH::trace, OpenMP"
     rays, _, _ = oracle.raygen_primary(cam.position, camera.nscreen_to_world(cam, W, H), W, H, cam.far, 0)
-    res = cpu.trace(rays, True, nthreads=threads)
+    res = trace(rays, True)
     hits = oracle.count_hits(res)
     normals = oracle.tri_normals(verts, tris)
     n_in = MAX_BATCH // args.spp                     # one secondary batch of each type per step (bounded sample)
@@ -356,9 +371,9 @@ def run_reference(args):
     counted = W * H + 2 * hit_in * args.spp
 
     def step():
-        cpu.trace(rays, True, nthreads=threads)
-        cpu.trace(ao, False, nthreads=threads)
-        cpu.trace(df, True, nthreads=threads)
+        trace(rays, True)
+        trace(ao, False)
+        trace(df, True)
 
     for _ in range(args.warmup):
         step()
@@ -367,12 +382,12 @@ def run_reference(args):
         step()
     sec = time.time() - t0
     value = counted * args.steps / sec * 1e-6
-    sample = f"per step: {len(rays)} primary + {len(ao)} AO + {len(df)} diffuse rays (one <=1Mi batch of each secondary type), restated SplitBVH + BVH::trace, OpenMP {threads} threads"
+    sample = f"per step: {len(rays)} primary + {len(ao)} AO + {len(df)} diffuse rays (one <=1Mi batch of each secondary type), {what}, {threads} threads"
     out = {"impl": "reference", "metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": sec / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
            "config": {"workload": "conference stand-in room(283000, seed=2): primary + AO(32spp, r=5) + diffuse(32spp), 1024x768; CPU arm traces a bounded sample per step",
                       "primary_hits": int(hits)},
-           "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": threads, "kind": "port", "sample": sample},
+           "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": threads, "kind": "reference" if use_ref else "port", "sample": sample},
            "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
     print(json.dumps(out), flush=True)

@@ -6,9 +6,12 @@ ctypes loader for ``oracle/liborc.so``, the CPU restatement of NTrace's tracing 
 Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` /
 ``--impl reference`` legs may import this package.  Nothing under ``ntrace_b200/`` does.
 
-Parity status: UNPINNED by the reference's own tests (it ships none with golden values and
-its Win32-only host cannot be built here); the restatement is cross-validated against brute
-force and between its two tracers in ``tests/test_oracle_*.py``.
+Parity status: the reference ships no tests with golden values, so the CPU part of this
+restatement (builders, SAH metric, createCompact/Woop, both tracers, Intersect primitives, pixel
+table) is PINNED bit-for-bit against the reference's own sources compiled unmodified
+(``oracle/ref.py``, ``oracle/_ref/libref.so``; ``tests/test_reference_pin.py``).  The restated
+HLBVH builder and ray generators mirror device code that cannot run here: parity UNPINNED for
+those, cross-validated in ``tests/test_oracle_*.py``.
 """
 from __future__ import annotations
 

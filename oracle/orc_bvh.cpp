@@ -156,7 +156,7 @@ struct ObjSplit { float sah = F32_MAX; int dim = 0; int numLeft = 0; AABB lb, rb
 struct SpatSplit { float sah = F32_MAX; int dim = 0; float pos = 0.0f; };
 struct Bin { AABB b; int enter = 0, exit = 0; };
 
-static inline float min3f(float a, float b, float c) { return std::min(std::min(a, b), c); }
+static inline float min3f(float a, float b, float c) { return fw_min(fw_min(a, b), c); }
 
 // float -> int as the x86 cvttss2si the reference compiles to: out-of-range / NaN -> INT_MIN.
 static inline int trunc_i(float f) {
@@ -392,7 +392,7 @@ private:
                 spatial = findSpatialSplit(spec, nodeSAH);
         }
 
-        float minSAH = (m_kind == BUILDER_SPLIT) ? min3f(leafSAH, object.sah, spatial.sah) : std::min(leafSAH, object.sah);
+        float minSAH = (m_kind == BUILDER_SPLIT) ? min3f(leafSAH, object.sah, spatial.sah) : fw_min(leafSAH, object.sah);
         if (level != 0 && minSAH == leafSAH && spec.numRef <= m_p.maxLeaf)
             return newLeaf(spec);
 

@@ -1,5 +1,5 @@
-// ORACLE — TEST INFRASTRUCTURE ONLY (see orc_math.hpp header).  Parity unpinned by the
-// reference's own tests; cross-validated in tests/test_oracle_*.py.
+// ORACLE — TEST INFRASTRUCTURE ONLY (see orc_math.hpp header).  Parity PINNED against the
+// compiled reference (oracle/_ref, tests/test_reference_pin.py): bit-identical SAH, trees, Woop data and trace results.
 //
 // CPU pointer-tree BVH (array-backed), the reference's two CPU builders, its SAH metric and
 // its two CPU tracers, restated from:

@@ -1,4 +1,4 @@
-// ORACLE — TEST INFRASTRUCTURE ONLY (see orc_math.hpp header).  Parity unpinned.
+// ORACLE — TEST INFRASTRUCTURE ONLY (see orc_math.hpp header).  Parity status per module: see orc_math.hpp.
 // Plain-C entry points for the ctypes loader in oracle/__init__.py.
 #include "orc_bvh.hpp"
 #include "orc_lbvh.hpp"

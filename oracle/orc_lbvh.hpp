@@ -1,5 +1,7 @@
-// ORACLE — TEST INFRASTRUCTURE ONLY (see orc_math.hpp header).  Parity unpinned by the
-// reference's own tests; see tests/test_oracle_lbvh.py for the invariants used instead.
+// ORACLE — TEST INFRASTRUCTURE ONLY (see orc_math.hpp header).  Parity UNPINNED: the reference's
+// HLBVH builder is device code (emitTreeKernel.cu: shared memory, warp scans, atomics) and cannot run here, and it has
+// no tests of its own; see tests/test_oracle_lbvh.py for the invariants used instead.  The pieces it shares with the
+// pinned CPU path (SAH metric, Compact node encoding, flat tracer that consumes the result) are pinned (orc_math.hpp).
 //
 // CPU restatement of the reference GPU LBVH / HLBVH builder, executed with a *serial
 // schedule* (threads in queue order), which is one of the schedules the reference's

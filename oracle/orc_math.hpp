@@ -3,10 +3,14 @@
 // product path (ntrace_b200/, include/) may include, link or call this; only tests/,
 // __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs do.
 //
-// Parity status: UNPINNED by the reference's own tests (the reference ships no golden
-// vectors for this path) and the reference host cannot be compiled here
-// (Win32-only).  The restatement is cross-validated three ways instead (pointer-tree trace
-// vs flat Woop trace vs brute force) in tests/test_oracle_*.py.
+// Parity status: the reference ships no golden vectors for this path, so the
+// oracle is pinned against OUTPUTS OF THE REFERENCE ITSELF: oracle/_ref/libref.so is the reference's
+// own CPU sources (SAHBVHBuilder, SplitBVHBuilder, BVHNode SAH, BVH::trace, CudaBVH createCompact /
+// woopifyTri / trace, Intersect::*, PixelTable) compiled unmodified (oracle/Makefile `ref`), and
+// tests/test_reference_pin.py requires bit-identical results from this restatement, live and against
+// frozen fixtures (tests/golden/ref_*).  PINNED: orc_math, orc_bvh, pixel_table.  Still UNPINNED
+// (device-only code in the reference, not buildable here): orc_lbvh (HLBVH kernels) and the rest of
+// orc_raygen; those are cross-validated in tests/test_oracle_*.py instead.
 //
 // Compile with: -O2 -ffp-contract=off -fno-fast-math  (IEEE fp32, no FMA contraction).
 //
@@ -39,10 +43,14 @@ static inline V3 operator*(V3 a, float s) { return V3(a.x * s, a.y * s, a.z * s)
 static inline V3 operator*(float s, V3 a) { return a * s; }
 static inline V3 operator*(V3 a, V3 b) { return V3(a.x * b.x, a.y * b.y, a.z * b.z); }
 static inline V3 operator/(V3 a, V3 b) { return V3(a.x / b.x, a.y / b.y, a.z / b.z); }
-static inline V3 vmin(V3 a, V3 b) { return V3(std::min(a.x, b.x), std::min(a.y, b.y), std::min(a.z, b.z)); }
-static inline V3 vmax(V3 a, V3 b) { return V3(std::max(a.x, b.x), std::max(a.y, b.y), std::max(a.z, b.z)); }
-static inline float hmin(V3 a) { return std::min(std::min(a.x, a.y), a.z); }
-static inline float hmax(V3 a) { return std::max(std::max(a.x, a.y), a.z); }
+// Defs.hpp:212-213 — FW::min / FW::max on the host: on equal operands (incl. +0 vs -0) and on NaN they return b,
+// unlike std::min / std::max which return a.  Visible in the sign of zero of node boxes, so restated exactly.
+static inline float fw_min(float a, float b) { return (a < b) ? a : b; }
+static inline float fw_max(float a, float b) { return (a > b) ? a : b; }
+static inline V3 vmin(V3 a, V3 b) { return V3(fw_min(a.x, b.x), fw_min(a.y, b.y), fw_min(a.z, b.z)); }
+static inline V3 vmax(V3 a, V3 b) { return V3(fw_max(a.x, b.x), fw_max(a.y, b.y), fw_max(a.z, b.z)); }
+static inline float hmin(V3 a) { return fw_min(fw_min(a.x, a.y), a.z); }
+static inline float hmax(V3 a) { return fw_max(fw_max(a.x, a.y), a.z); }
 // Math.hpp:148 — r = v[0]; r += v[1]; r += v[2]
 static inline float hsum(V3 a) { float r = a.x; r += a.y; r += a.z; return r; }
 // Math.hpp:185 — r = 0; r += a[i]*b[i]
@@ -56,7 +64,7 @@ static inline float length(V3 a) { return std::sqrt(dot(a, a)); }
 static inline V3 normalize(V3 a) { return a * (1.0f * rcp(length(a))); }
 // Math.hpp:115
 static inline V3 lerp(V3 a, V3 b, float t) { return a * (1.0f - t) + b * t; }
-static inline float clampf(float v, float lo, float hi) { return std::min(std::max(v, lo), hi); }
+static inline float clampf(float v, float lo, float hi) { return fw_min(fw_max(v, lo), hi); }
 
 static inline uint32_t f2u(float f) { uint32_t u; std::memcpy(&u, &f, 4); return u; }
 static inline float u2f(uint32_t u) { float f; std::memcpy(&f, &u, 4); return f; }

@@ -1,4 +1,4 @@
-// ORACLE — TEST INFRASTRUCTURE ONLY (see orc_math.hpp header).  Parity unpinned.
+// ORACLE — TEST INFRASTRUCTURE ONLY (see orc_math.hpp header).  pixel_table PINNED against the compiled reference (oracle/_ref); ray generation parity unpinned (device code).
 //
 // Ray generation restated on the CPU from:
 //   src/rt/ray/PixelTable.cpp:57-141          index <-> pixel tables

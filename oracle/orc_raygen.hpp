@@ -1,4 +1,4 @@
-// ORACLE — TEST INFRASTRUCTURE ONLY (see orc_math.hpp header).  Parity unpinned.
+// ORACLE — TEST INFRASTRUCTURE ONLY (see orc_math.hpp header).  pixel_table PINNED against the compiled reference (oracle/_ref); ray generation parity unpinned (device code).
 #pragma once
 #include "orc_bvh.hpp"
 

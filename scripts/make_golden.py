@@ -3,7 +3,7 @@ ingestion rule) and known-answer values computed by the CPU oracle on them.
 
 Run in the build container (needs /root/reference): python scripts/make_golden.py
 The reference ships no golden vectors for this path, so these pin the *oracle* against drift and
-give the GPU tests fixed inputs; they do not pin the oracle against the reference ("parity unpinned").
+give the GPU tests fixed inputs; the pin against the reference itself is scripts/make_ref_golden.py + tests/test_reference_pin.py.
 """
 import hashlib
 import json
