@@ -64,49 +64,91 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock / throttle reasons DURING the timed region (B200_PROFILING.md recipe).  NVML is polled in-process from a
+    thread (the timed region sits in C calls that release the GIL), so even a 100 ms region gets tens of samples; an
+    `nvidia-smi -lms` child started at the same time is the fallback when NVML cannot be loaded."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    REASON_BITS = {"sw_power_cap": 0x4, "hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
 
-    def __init__(self, gpu_index):
-        self.gpu, self.proc, self.path = gpu_index, None, None
+    def __init__(self, gpu_index, uuid=None):
+        self.gpu, self.uuid, self.proc, self.path = gpu_index, uuid, None, None
+        self.thread, self.stop_flag, self.nvml_sm, self.nvml_reasons, self.nvml_max = None, False, [], 0, None
+
+    def _nvml_loop(self, nv, handle):
+        while not self.stop_flag:
+            try:
+                self.nvml_sm.append(float(nv.nvmlDeviceGetClockInfo(handle, nv.NVML_CLOCK_SM)))
+                try:
+                    self.nvml_reasons |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(handle))
+                except Exception:
+                    self.nvml_reasons |= int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(handle))
+            except Exception:
+                break
+            time.sleep(0.004)
 
     def start(self):
         try:
+            import threading
+            import pynvml as nv
+            nv.nvmlInit()
+            handle = None
+            if self.uuid:
+                for u in (self.uuid, self.uuid.encode()):
+                    try:
+                        handle = nv.nvmlDeviceGetHandleByUUID(u)
+                        break
+                    except Exception:
+                        handle = None
+            if handle is None:
+                handle = nv.nvmlDeviceGetHandleByIndex(self.gpu)
+            self.nvml_max = float(nv.nvmlDeviceGetMaxClockInfo(handle, nv.NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._nvml_loop, args=(nv, handle), daemon=True)
+            self.thread.start()
+        except Exception:
+            self.thread = None
+        try:
             fd, self.path = tempfile.mkstemp(suffix=".csv")
             os.close(fd)
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+            ident = self.uuid if self.uuid else str(self.gpu)
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={ident}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        if self.proc is None:
-            return out
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
+        self.stop_flag = True
+        if self.thread is not None:
+            self.thread.join(timeout=2)
         sm, mx, reasons = [], [], set()
-        try:
-            for line in open(self.path):
-                f = [x.strip() for x in line.split(",")]
-                if len(f) < 9:
-                    continue
-                try:
-                    sm.append(float(f[1])); mx.append(float(f[2]))
-                except ValueError:
-                    continue
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
-            os.unlink(self.path)
-        except Exception:
-            pass
-        if sm:
-            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(np.max(mx)), reasons=sorted(reasons), samples=len(sm))
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+            try:
+                for line in open(self.path):
+                    f = [x.strip() for x in line.split(",")]
+                    if len(f) < 9:
+                        continue
+                    try:
+                        sm.append(float(f[1])); mx.append(float(f[2]))
+                    except ValueError:
+                        continue
+                    for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                        if v.lower().startswith("active"):
+                            reasons.add(name)
+                os.unlink(self.path)
+            except Exception:
+                pass
+        if self.nvml_sm:
+            reasons |= {n for n, bit in self.REASON_BITS.items() if self.nvml_reasons & bit}
+            out.update(sm_mhz=float(np.median(self.nvml_sm)), sm_max_mhz=self.nvml_max if self.nvml_max else (float(np.max(mx)) if mx else None),
+                       reasons=sorted(reasons), samples=len(self.nvml_sm), source="nvml" + (f"+nvidia-smi({len(sm)})" if sm else ""))
+        elif sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(np.max(mx)), reasons=sorted(reasons), samples=len(sm), source="nvidia-smi")
         return out
 
 
@@ -115,6 +157,13 @@ def make_workload():
     from ntrace_b200 import camera, scenes
     verts, tris, cam_name = scenes.config_scene("conference")
     return verts, tris, camera.named_camera(cam_name)
+
+
+def gpu_uuid(torch, local):
+    try:
+        return "GPU-" + str(torch.cuda.get_device_properties(local).uuid)
+    except Exception:
+        return None
 
 
 def bytes_per_ray(cnt, hit_frac):
@@ -192,7 +241,7 @@ def run_b200(args):
     for _ in range(args.warmup):
         step()
     barrier()
-    sampler = ClockSampler(local)
+    sampler = ClockSampler(local, gpu_uuid(torch, local))
     sampler.start()
     l0 = capi.launch_count()
     capi.event_record(0)
@@ -217,6 +266,8 @@ def run_b200(args):
 
     # ---- e2e: the same step through the C ABI with HOST buffers (pinned), H2D of the rays and D2H of the
     # results inside the timed region, every step
+    from ntrace_b200 import multigpu
+    prev_affinity, numa_node = multigpu.bind_host_to_gpu(local)      # pinned buffers land on the GPU's NUMA node
     host_batches = []
     for name, rays, n, closest in batches:
         hb = torch.empty((n, 8), dtype=torch.float32, pin_memory=True)
@@ -235,6 +286,8 @@ def run_b200(args):
     capi.event_record(3)
     e2e_sec = capi.event_elapsed(2, 3)
     barrier()
+    if prev_affinity is not None:
+        os.sched_setaffinity(0, prev_affinity)                        # the CPU baseline leg uses every core again
 
     # ---- max over ranks
     if world > 1:
@@ -281,7 +334,7 @@ def run_b200(args):
                        "build_ms": float(np.mean(build_s[1:]) * 1e3), "build_mtris": len(tris) / float(np.mean(build_s[1:])) * 1e-6,
                        "bvh_broadcast_ms": bcast_ms, "primary_hits": int(hits)},
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": int(ray_bytes), "d2h_bytes_per_step": int(ray_bytes // 2),
-                    "steps": e2e_steps},
+                    "steps": e2e_steps, "host_numa_node": numa_node},
             "gpu_launches": launches_all,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH,

@@ -66,7 +66,9 @@ int nt_synchronize(void);
 /* ---- kernel selection: CudaBVHTracer::setKernel + queryConfig (CudaBVHTracer.cpp:52-84) --- */
 /* Names: "b200_persistent_speculative_while_while" (default), "b200_speculative_while_while",
  * and the reference's kernel file names as aliases: "fermi_speculative_while_while" (Compact),
- * "kepler_dynamic_fetch" (Compact2).  Unknown names fail. */
+ * "kepler_dynamic_fetch" (Compact2), "tesla_persistent_while_while" / "tesla_persistent_speculative_while_while" /
+ * "tesla_persistent_packet" (AOS_AOS, as those files ship); "b200_persistent_speculative_while_while_{aos_aos,aos_soa,
+ * soa_aos,soa_soa}" select the other basic layouts.  Unknown names fail. */
 int nt_set_kernel(const char* name);
 /* CudaBVHTracer::getDesiredBVHLayout -> BVHLayout of the selected kernel. */
 int nt_desired_layout(void);
@@ -74,7 +76,11 @@ int nt_desired_layout(void);
 int nt_kernel_config(int32_t out4[4]);
 
 /* ---- BVH: CudaAS / CudaBVH buffers (src/rt/cuda/CudaBVH.hpp:137-152) ----------------------- */
-/* setBVH(CudaAS*): copy the three CudaBVH buffers (node, triWoop, triIndex) to the device. */
+/* setBVH(CudaAS*): copy the three CudaBVH buffers (node, triWoop, triIndex) to the device.  layout = BVHLayout value
+ * (CudaTracerKernels.hpp:52-63): Compact (4) and Compact2 (5) are traversed as they are; the basic layouts AOS_AOS (0),
+ * AOS_SOA (1), SOA_AOS (2), SOA_SOA (3) of createNodeBasic / createTriWoopBasic / createTriIndexBasic (CudaBVH.cpp:453-575)
+ * are kept as given (nt_bvh_download returns them unchanged) and rewritten on the device into the Compact form the
+ * traversal kernel reads; the tree is validated on the way and a malformed one is refused. */
 int nt_bvh_upload(int layout, const void* nodes, size_t nodeBytes,
                   const void* woop, size_t woopBytes,
                   const int32_t* triIndex, size_t idxBytes);
@@ -93,6 +99,10 @@ int nt_bvh_build(int builder, const float* vtxPos, int numVerts,
  * collapse: the tree is emitted down to single triangles and subtrees are folded back into leaves of at most
  * maxLeafSize triangles (0 = leafSize) wherever that does not increase the SAH cost (Platform costs Cn = Ct = 1). */
 int nt_bvh_set_collapse(int mode, int maxLeafSize);
+/* Make the resident BVH BVHLayout_Compact (4) or BVHLayout_Compact2 (5) in place: AOS/SOA uploads are replaced by their
+ * Compact form (CudaBVH.cpp:579-664 semantics: implicit leaves, terminator-delimited Woop lists), Compact <-> Compact2
+ * rescales the inner-child offsets (createCompact's nodeOffsetSizeDiv, CudaBVH.cpp:86,614). */
+int nt_bvh_convert(int layout);
 /* sizes[3] = bytes of (nodes, woop, triIndex); layout of the resident BVH in *outLayout. */
 int nt_bvh_sizes(size_t sizes[3], int* outLayout);
 /* CudaBVH::serialize source buffers (CudaBVH.cpp:105-125): copy the device BVH out (host or device dst). */
@@ -121,6 +131,13 @@ int nt_raygen_ao(float* outRays, int32_t* outIDToSlot, int32_t* outSlotToID,
                  const float* inRays, const int32_t* inResults, const float* triNormals,
                  int firstInputSlot, int numInputRays, int numSamples,
                  float maxDist, uint32_t randomSeed);
+/* RayGen::shadow + rayGenShadowKernel (RayGen.cpp:114-147, RayGenKernels.cu:240-302): numSamples any-hit rays from each
+ * input hit point (backed off 1e-2 along the ray) towards a point in the cube of half-size lightRadius around lightPos;
+ * tmax = distance to that point, or -1 (degenerate) when the input ray missed.  Used by the reference's VPL mode. */
+int nt_raygen_shadow(float* outRays, int32_t* outIDToSlot, int32_t* outSlotToID,
+                     const float* inRays, const int32_t* inResults,
+                     int firstInputSlot, int numInputRays, int numSamples,
+                     const float lightPos[3], float lightRadius, uint32_t randomSeed);
 /* RayBuffer::mortonSort (src/rt/ray/RayBuffer.cpp:103-163): reorder the batch in place by the Morton key of
  * (origin, direction) and rebuild the id<->slot maps (outSlotToID[new] = inSlotToID[old], outIDToSlot[id] = new).
  * The reference sorts 192-bit keys on the CPU; here the top 64 significant key bits are radix-sorted on the GPU, ties

@@ -26,9 +26,9 @@ EXPORTS = [
     "nt_init", "nt_shutdown", "nt_last_error", "nt_launch_count",
     "nt_event_record", "nt_event_elapsed", "nt_set_deferred", "nt_synchronize",
     "nt_set_kernel", "nt_desired_layout", "nt_kernel_config",
-    "nt_bvh_upload", "nt_bvh_alloc", "nt_bvh_build", "nt_bvh_set_collapse", "nt_bvh_sizes", "nt_bvh_download",
+    "nt_bvh_upload", "nt_bvh_alloc", "nt_bvh_build", "nt_bvh_set_collapse", "nt_bvh_convert", "nt_bvh_sizes", "nt_bvh_download",
     "nt_bvh_device_ptrs", "nt_bvh_build_debug",
-    "nt_trace_batch", "nt_raygen_primary", "nt_raygen_ao", "nt_ray_sort", "nt_count_hits", "nt_tri_normals",
+    "nt_trace_batch", "nt_raygen_primary", "nt_raygen_ao", "nt_raygen_shadow", "nt_ray_sort", "nt_count_hits", "nt_tri_normals",
 ]
 
 
@@ -156,6 +156,11 @@ def bvh_build(builder: int, verts, tris, bbox_lo, bbox_hi, hlbvh_bits=4, leaf_si
     return float(sec.value)
 
 
+def bvh_convert(layout: int):
+    """Make the resident BVH Compact (4) / Compact2 (5) in place."""
+    _check(lib().nt_bvh_convert(C.c_int(layout)))
+
+
 def bvh_set_collapse(mode: int, max_leaf: int = 0):
     _check(lib().nt_bvh_set_collapse(C.c_int(mode), C.c_int(max_leaf)))
 
@@ -210,6 +215,14 @@ def raygen_ao(out_rays, out_id_to_slot, out_slot_to_id, in_rays, in_results, tri
     _check(lib().nt_raygen_ao(ptr(out_rays, np.float32, count * samples * 32), ptr(out_id_to_slot, np.int32), ptr(out_slot_to_id, np.int32),
                               ptr(in_rays, np.float32), ptr(in_results, np.int32), ptr(tri_normals, np.float32),
                               C.c_int(first), C.c_int(count), C.c_int(samples), C.c_float(max_dist), C.c_uint32(seed)))
+
+
+def raygen_shadow(out_rays, out_id_to_slot, out_slot_to_id, in_rays, in_results, first: int, count: int, samples: int,
+                  light_pos, light_radius: float, seed: int):
+    lp = (C.c_float * 3)(*[float(v) for v in light_pos])
+    _check(lib().nt_raygen_shadow(ptr(out_rays, np.float32, count * samples * 32), ptr(out_id_to_slot, np.int32), ptr(out_slot_to_id, np.int32),
+                                  ptr(in_rays, np.float32), ptr(in_results, np.int32), C.c_int(first), C.c_int(count), C.c_int(samples),
+                                  lp, C.c_float(light_radius), C.c_uint32(seed)))
 
 
 def ray_sort(rays, id_to_slot, slot_to_id, num_rays: int):

@@ -64,6 +64,11 @@ struct Context {
     size_t nodeBytes = 0, woopBytes = 0, idxBytes = 0;
     int bvhLayout = Layout_Max;
     bool haveBVH = false;
+    // a BVH uploaded in one of the basic layouts (AOS/SOA) is kept as given in src* (what download / device_ptrs /
+    // broadcast see) and rewritten on the device into nodes/woop/triIndex (Compact form) before the first trace
+    DevBuf srcNodes, srcWoop, srcIdx, layoutScratch;
+    size_t srcNodeBytes = 0, srcWoopBytes = 0, srcIdxBytes = 0;
+    bool basic = false, converted = false;
     DevBuf sortedKeys, sortedIdx;
     int builtTris = 0;
     int collapseMode = 0, collapseMaxLeaf = 0;
@@ -124,6 +129,30 @@ int stage_out(void* dst, size_t bytes, DevBuf& st, void** out, void** hostDst)
 int copy_back(void* hostDst, const void* dev, size_t bytes)
 {
     if (hostDst && bytes) NT_CUDA(cudaMemcpyAsync(hostDst, dev, bytes, cudaMemcpyDeviceToHost, g.stream));
+    return 0;
+}
+
+bool is_basic_layout(int layout) { return layout >= Layout_AOS_AOS && layout <= Layout_SOA_SOA; }
+
+// (re)build the traversal form of a basic-layout BVH; caller holds the mutex
+int ensure_traversal_form()
+{
+    if (!g.basic || g.converted) return 0;
+    BuildOutput out;
+    out.nodes = &g.nodes; out.woop = &g.woop; out.triIndex = &g.triIndex;
+    out.sortedKeys = out.sortedIdx = nullptr;
+    out.nodeBytes = out.woopBytes = out.idxBytes = 0;
+    int launches = 0;
+    std::string err;
+    cudaError_t e = convert_basic_layout(g.bvhLayout, g.srcNodes.p, g.srcNodeBytes, g.srcWoop.p, g.srcWoopBytes, g.srcIdx.as<int>(), g.srcIdxBytes,
+                                         Layout_Compact, out, g.layoutScratch, g.stream, &launches, &err);
+    g.launches += launches;
+    if (e != cudaSuccess) {
+        if (!err.empty()) { set_error("ntrace_b200: " + err); cudaGetLastError(); return 1; }
+        NT_CUDA(e);
+    }
+    g.nodeBytes = out.nodeBytes; g.woopBytes = out.woopBytes; g.idxBytes = out.idxBytes;
+    g.converted = true;
     return 0;
 }
 
@@ -292,6 +321,16 @@ int nt_set_kernel(const char* name)
         // reference kernel file names (src/rt/kernels/*.cu) accepted as aliases with their layouts
         {"fermi_speculative_while_while", Kernel_PlainSpeculative, Layout_Compact},
         {"kepler_dynamic_fetch", Kernel_PersistentSpeculative, Layout_Compact2},
+        // tesla_* ship with NODES/TRIANGLES_ARRAY_OF_STRUCTURES defined (tesla_persistent_while_while.cu:40-41): AOS_AOS.
+        // The BVH is rewritten to the Compact form on the device (nt_layout.cu) and traversed by the one B200 kernel.
+        {"tesla_persistent_while_while", Kernel_PersistentSpeculative, Layout_AOS_AOS},
+        {"tesla_persistent_speculative_while_while", Kernel_PersistentSpeculative, Layout_AOS_AOS},
+        {"tesla_persistent_packet", Kernel_PersistentSpeculative, Layout_AOS_AOS},
+        // the three variants those files select by commenting the defines out
+        {"b200_persistent_speculative_while_while_aos_aos", Kernel_PersistentSpeculative, Layout_AOS_AOS},
+        {"b200_persistent_speculative_while_while_aos_soa", Kernel_PersistentSpeculative, Layout_AOS_SOA},
+        {"b200_persistent_speculative_while_while_soa_aos", Kernel_PersistentSpeculative, Layout_SOA_AOS},
+        {"b200_persistent_speculative_while_while_soa_soa", Kernel_PersistentSpeculative, Layout_SOA_SOA},
     };
     for (const Entry& e : table)
         if (strcmp(e.name, name) == 0) { g.kernel = e.kernel; g.kernelLayout = e.layout; return 0; }
@@ -312,11 +351,27 @@ int nt_bvh_alloc(int layout, size_t nodeBytes, size_t woopBytes, size_t idxBytes
 {
     std::lock_guard<std::mutex> lock(g_mutex);
     if (require_init()) return 1;
-    if (layout != Layout_Compact && layout != Layout_Compact2) { set_error("ntrace_b200: only BVHLayout_Compact / Compact2 are supported"); return 1; }
+    if (is_basic_layout(layout)) {
+        if (nodeBytes < 64 || nodeBytes % 64 || woopBytes % 64 || idxBytes == 0 || idxBytes % 4 || woopBytes / 64 < idxBytes / 4) {
+            set_error("ntrace_b200: inconsistent CudaBVH buffer sizes (AOS/SOA layouts: nodes and Woop triangles in 64 B records, one S32 index per triangle)");
+            return 1;
+        }
+        NT_CUDA(g.srcNodes.reserve(nodeBytes));
+        NT_CUDA(g.srcWoop.reserve(woopBytes));
+        NT_CUDA(g.srcIdx.reserve(idxBytes));
+        g.srcNodeBytes = nodeBytes; g.srcWoopBytes = woopBytes; g.srcIdxBytes = idxBytes;
+        g.bvhLayout = layout;
+        g.basic = true; g.converted = false;
+        g.haveBVH = true;
+        g.builtTris = 0;
+        return 0;
+    }
+    if (layout != Layout_Compact && layout != Layout_Compact2) { set_error("ntrace_b200: BVHLayout_CPU (no Woop data) cannot be traced on the device"); return 1; }
     if (nodeBytes < 64 || nodeBytes % 64 || woopBytes % 16 || idxBytes * 4 != woopBytes) {
         set_error("ntrace_b200: inconsistent CudaBVH buffer sizes (nodes multiple of 64 B, woop of 16 B, one index per woop float4)");
         return 1;
     }
+    g.basic = false; g.converted = false;
     NT_CUDA(g.nodes.reserve(nodeBytes));
     NT_CUDA(g.woop.reserve(woopBytes));
     NT_CUDA(g.triIndex.reserve(idxBytes));
@@ -333,10 +388,11 @@ int nt_bvh_upload(int layout, const void* nodes, size_t nodeBytes, const void* w
     if (!nodes || !woop || !triIndex) { set_error("ntrace_b200: null BVH buffer"); return 1; }
     if (nt_bvh_alloc(layout, nodeBytes, woopBytes, idxBytes)) return 1;
     std::lock_guard<std::mutex> lock(g_mutex);
-    NT_CUDA(cudaMemcpyAsync(g.nodes.p, nodes, nodeBytes, cudaMemcpyDefault, g.stream));
-    NT_CUDA(cudaMemcpyAsync(g.woop.p, woop, woopBytes, cudaMemcpyDefault, g.stream));
-    NT_CUDA(cudaMemcpyAsync(g.triIndex.p, triIndex, idxBytes, cudaMemcpyDefault, g.stream));
+    NT_CUDA(cudaMemcpyAsync(g.basic ? g.srcNodes.p : g.nodes.p, nodes, nodeBytes, cudaMemcpyDefault, g.stream));
+    NT_CUDA(cudaMemcpyAsync(g.basic ? g.srcWoop.p : g.woop.p, woop, woopBytes, cudaMemcpyDefault, g.stream));
+    NT_CUDA(cudaMemcpyAsync(g.basic ? g.srcIdx.p : g.triIndex.p, triIndex, idxBytes, cudaMemcpyDefault, g.stream));
     NT_CUDA(cudaStreamSynchronize(g.stream));
+    if (g.basic && ensure_traversal_form()) { g.haveBVH = false; return 1; }     // validates the tree; a malformed upload is refused here
     return 0;
 }
 
@@ -361,6 +417,7 @@ int nt_bvh_build(int builder, const float* vtxPos, int numVerts, const int32_t* 
     out.sortedKeys = &g.sortedKeys; out.sortedIdx = &g.sortedIdx;
     out.nodeBytes = out.woopBytes = out.idxBytes = 0;
     g.haveBVH = false;
+    g.basic = false; g.converted = false;
     NT_CUDA(cudaEventRecord(g.evA, g.stream));
     int launches = 0;
     std::string err;
@@ -391,12 +448,33 @@ int nt_bvh_set_collapse(int mode, int maxLeafSize)
     return 0;
 }
 
+int nt_bvh_convert(int layout)
+{
+    std::lock_guard<std::mutex> lock(g_mutex);
+    if (require_init()) return 1;
+    if (!g.haveBVH) { set_error("CudaBVHTracer: No BVH!"); return 1; }
+    if (layout != Layout_Compact && layout != Layout_Compact2) { set_error("ntrace_b200: the resident BVH can only be converted to BVHLayout_Compact / Compact2"); return 1; }
+    if (g.basic) {
+        if (ensure_traversal_form()) return 1;                      // AOS/SOA -> Compact (nt_layout.cu)
+        g.basic = false; g.converted = false;
+        g.bvhLayout = Layout_Compact;
+    }
+    if (g.bvhLayout == layout) return 0;
+    const bool toCompact2 = (layout == Layout_Compact2);
+    NT_CUDA(rescale_compact_links(g.nodes.as<int4>(), g.nodeBytes / 64, toCompact2 ? 1 : 16, toCompact2 ? 16 : 1, g.stream));
+    g.launches += 1;
+    NT_CUDA(cudaStreamSynchronize(g.stream));
+    g.bvhLayout = layout;
+    return 0;
+}
+
 int nt_bvh_sizes(size_t sizes[3], int* outLayout)
 {
     std::lock_guard<std::mutex> lock(g_mutex);
     if (require_init()) return 1;
     if (!g.haveBVH) { set_error("CudaBVHTracer: No BVH!"); return 1; }
-    sizes[0] = g.nodeBytes; sizes[1] = g.woopBytes; sizes[2] = g.idxBytes;
+    if (g.basic) { sizes[0] = g.srcNodeBytes; sizes[1] = g.srcWoopBytes; sizes[2] = g.srcIdxBytes; }
+    else { sizes[0] = g.nodeBytes; sizes[1] = g.woopBytes; sizes[2] = g.idxBytes; }
     if (outLayout) *outLayout = g.bvhLayout;
     return 0;
 }
@@ -406,9 +484,15 @@ int nt_bvh_download(void* nodes, void* woop, int32_t* triIndex)
     std::lock_guard<std::mutex> lock(g_mutex);
     if (require_init()) return 1;
     if (!g.haveBVH) { set_error("CudaBVHTracer: No BVH!"); return 1; }
-    if (nodes) NT_CUDA(cudaMemcpyAsync(nodes, g.nodes.p, g.nodeBytes, cudaMemcpyDefault, g.stream));
-    if (woop) NT_CUDA(cudaMemcpyAsync(woop, g.woop.p, g.woopBytes, cudaMemcpyDefault, g.stream));
-    if (triIndex) NT_CUDA(cudaMemcpyAsync(triIndex, g.triIndex.p, g.idxBytes, cudaMemcpyDefault, g.stream));
+    if (g.basic) {
+        if (nodes) NT_CUDA(cudaMemcpyAsync(nodes, g.srcNodes.p, g.srcNodeBytes, cudaMemcpyDefault, g.stream));
+        if (woop) NT_CUDA(cudaMemcpyAsync(woop, g.srcWoop.p, g.srcWoopBytes, cudaMemcpyDefault, g.stream));
+        if (triIndex) NT_CUDA(cudaMemcpyAsync(triIndex, g.srcIdx.p, g.srcIdxBytes, cudaMemcpyDefault, g.stream));
+    } else {
+        if (nodes) NT_CUDA(cudaMemcpyAsync(nodes, g.nodes.p, g.nodeBytes, cudaMemcpyDefault, g.stream));
+        if (woop) NT_CUDA(cudaMemcpyAsync(woop, g.woop.p, g.woopBytes, cudaMemcpyDefault, g.stream));
+        if (triIndex) NT_CUDA(cudaMemcpyAsync(triIndex, g.triIndex.p, g.idxBytes, cudaMemcpyDefault, g.stream));
+    }
     NT_CUDA(cudaStreamSynchronize(g.stream));
     return 0;
 }
@@ -418,7 +502,8 @@ int nt_bvh_device_ptrs(void* ptrs[3])
     std::lock_guard<std::mutex> lock(g_mutex);
     if (require_init()) return 1;
     if (!g.haveBVH) { set_error("CudaBVHTracer: No BVH!"); return 1; }
-    ptrs[0] = g.nodes.p; ptrs[1] = g.woop.p; ptrs[2] = g.triIndex.p;
+    if (g.basic) { ptrs[0] = g.srcNodes.p; ptrs[1] = g.srcWoop.p; ptrs[2] = g.srcIdx.p; g.converted = false; }   // caller may write (broadcast)
+    else { ptrs[0] = g.nodes.p; ptrs[1] = g.woop.p; ptrs[2] = g.triIndex.p; }
     return 0;
 }
 
@@ -442,6 +527,7 @@ int nt_trace_batch(const float* rays, int32_t* results, int numRays, int needClo
     if (numRays < 0 || !rays || !results) { set_error("ntrace_b200: invalid ray batch"); return 1; }
     if (!g.haveBVH) { set_error("CudaBVHTracer: No BVH!"); return 1; }                          // :98-99
     if (g.bvhLayout != g.kernelLayout) { set_error("CudaBVHTracer: Incorrect BVH layout!"); return 1; }  // :100-101
+    if (ensure_traversal_form()) return 1;
 
     // Pinned (page-locked, UVA-mapped) host buffers are traversed in place: the kernel reads rays and writes results
     // over PCIe (zero copy), which overlaps both transfers with the traversal inside ONE launch.  Pageable host memory
@@ -451,7 +537,7 @@ int nt_trace_batch(const float* rays, int32_t* results, int numRays, int needClo
     const bool raysOnHost = (raysDev == nullptr), resOnHost = (resDev == nullptr);
 
     TraceLaunch a;
-    a.kernel = g.kernel; a.layout = g.kernelLayout; a.anyHit = needClosestHit ? 0 : 1;
+    a.kernel = g.kernel; a.layout = g.basic ? (int)Layout_Compact : g.kernelLayout; a.anyHit = needClosestHit ? 0 : 1;
     a.nodes = g.nodes.as<float4>(); a.woop = g.woop.as<float4>(); a.triIndices = g.triIndex.as<int>();
     a.numSMs = g.numSMs; a.stream = g.stream;
     int launches = 0;
@@ -573,6 +659,43 @@ int nt_raygen_ao(float* outRays, int32_t* outIDToSlot, int32_t* outSlotToID, con
     a.inRays = (const float4*)dInRays; a.inResults = (const int4*)dInRes; a.normals = (const float*)dNormals;
     a.firstInputSlot = first; a.numInputRays = numInputRays; a.numSamples = numSamples; a.maxDist = maxDist; a.seed = randomSeed;
     NT_CUDA(launch_raygen_ao(a, g.stream));
+    g.launches += 1;
+    if (copy_back(hOut, dOut, nOut * 32) || copy_back(hA, dA, nOut * 4) || copy_back(hB, dB, nOut * 4)) return 1;
+    NT_CUDA(cudaStreamSynchronize(g.stream));
+    return 0;
+}
+
+int nt_raygen_shadow(float* outRays, int32_t* outIDToSlot, int32_t* outSlotToID, const float* inRays, const int32_t* inResults,
+                     int firstInputSlot, int numInputRays, int numSamples, const float lightPos[3], float lightRadius, uint32_t randomSeed)
+{
+    std::lock_guard<std::mutex> lock(g_mutex);
+    if (require_init()) return 1;
+    if (numInputRays == 0) return 0;
+    if (numInputRays < 0 || numSamples <= 0 || firstInputSlot < 0 || !outRays || !inRays || !inResults || !lightPos) {
+        set_error("ntrace_b200: invalid shadow ray request");
+        return 1;
+    }
+    if (is_device_ptr(inRays) != is_device_ptr(inResults)) { set_error("ntrace_b200: inRays and inResults must live on the same side"); return 1; }
+    const size_t nOut = (size_t)numInputRays * numSamples;
+    if (nOut > 0x3fffffffull) { set_error("ntrace_b200: shadow batch too large"); return 1; }
+    const void *dInRays, *dInRes;
+    int first = firstInputSlot;
+    if (!is_device_ptr(inRays)) {
+        if (stage_in(inRays + (size_t)firstInputSlot * 8, (size_t)numInputRays * 32, g.stC, &dInRays)) return 1;
+        if (stage_in(inResults + (size_t)firstInputSlot * 4, (size_t)numInputRays * 16, g.stD, &dInRes)) return 1;
+        first = 0;
+    } else { dInRays = inRays; dInRes = inResults; }
+    void *dOut, *hOut, *dA, *hA, *dB, *hB;
+    if (stage_out(outRays, nOut * 32, g.stRays, &dOut, &hOut)) return 1;
+    if (stage_out(outIDToSlot, nOut * 4, g.stA, &dA, &hA)) return 1;
+    if (stage_out(outSlotToID, nOut * 4, g.stB, &dB, &hB)) return 1;
+    ShadowArgs a;
+    a.outRays = (float4*)dOut; a.outIDToSlot = (int*)dA; a.outSlotToID = (int*)dB;
+    a.inRays = (const float4*)dInRays; a.inResults = (const int4*)dInRes;
+    a.firstInputSlot = first; a.numInputRays = numInputRays; a.numSamples = numSamples;
+    for (int i = 0; i < 3; i++) a.lightPos[i] = lightPos[i];
+    a.lightRadius = lightRadius; a.seed = randomSeed;
+    NT_CUDA(launch_raygen_shadow(a, g.stream));
     g.launches += 1;
     if (copy_back(hOut, dOut, nOut * 32) || copy_back(hA, dA, nOut * 4) || copy_back(hB, dB, nOut * 4)) return 1;
     NT_CUDA(cudaStreamSynchronize(g.stream));

@@ -62,6 +62,12 @@ struct AOArgs {
     int firstInputSlot, numInputRays, numSamples; float maxDist; unsigned seed;
 };
 cudaError_t launch_raygen_ao(const AOArgs& a, cudaStream_t s);
+struct ShadowArgs {
+    float4* outRays; int* outIDToSlot; int* outSlotToID;
+    const float4* inRays; const int4* inResults;
+    int firstInputSlot, numInputRays, numSamples; float lightPos[3]; float lightRadius; unsigned seed;
+};
+cudaError_t launch_raygen_shadow(const ShadowArgs& a, cudaStream_t s);
 cudaError_t launch_count_hits(const int4* results, int numRays, int* dCounter, cudaStream_t s);
 cudaError_t launch_tri_normals(const float* verts, const int* tris, int numTris, float* out, cudaStream_t s);
 
@@ -92,5 +98,11 @@ struct BuildOutput {          // device buffers owned by the context
 cudaError_t build_bvh_device(const float* dVerts, int numVerts, const int* dTris, int numTris,
                              const BuildParams& p, BuildOutput& out, cudaStream_t stream,
                              int numSMs, int* outLaunches, std::string* err);
+
+// ---- basic CudaBVH layouts (nt_layout.cu): AOS/SOA buffers on the device -> Compact / Compact2 form in `out`
+cudaError_t rescale_compact_links(int4* dNodes, size_t numNodes, int mulNum, int mulDen, cudaStream_t stream);
+cudaError_t convert_basic_layout(int layout, const void* dNodes, size_t nodeBytes, const void* dWoop, size_t woopBytes,
+                                 const int* dTriIndex, size_t idxBytes, int targetLayout, BuildOutput& out, DevBuf& scratch,
+                                 cudaStream_t stream, int* outLaunches, std::string* err);
 
 } // namespace nt

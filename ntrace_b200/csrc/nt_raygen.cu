@@ -154,6 +154,59 @@ __global__ void __launch_bounds__(256) raygen_ao_kernel(AOArgs a)
     if (a.outSlotToID) a.outSlotToID[o] = o;
 }
 
+// rayGenShadowKernel (RayGenKernels.cu:240-302): numSamples rays from each hit point towards a spherical light,
+// sample i = Cranley-Patterson rotated (Sobol2D(i), Hammersley(i)) point in the light's bounding cube.
+__global__ void __launch_bounds__(256) raygen_shadow_kernel(ShadowArgs a)
+{
+    const int o = blockIdx.x * blockDim.x + threadIdx.x;
+    const int total = a.numInputRays * a.numSamples;
+    if (o >= total) return;
+    const int task = o / a.numSamples;
+    const int i = o - task * a.numSamples;
+    const int inSlot = task + a.firstInputSlot;
+
+    const float4 ro = __ldg(a.inRays + inSlot * 2 + 0);
+    const float4 rd = __ldg(a.inRays + inSlot * 2 + 1);
+    const int4 res = __ldg(a.inResults + inSlot);
+    const int tri = res.x;
+    const float back = fmaxf(__fsub_rn(__int_as_float(res.y), 1.0e-2f), 0.0f);
+    const F3 origin = mk(__fadd_rn(ro.x, __fmul_rn(rd.x, back)), __fadd_rn(ro.y, __fmul_rn(rd.y, back)), __fadd_rn(ro.z, __fmul_rn(rd.z, back)));
+
+    unsigned ha = a.seed + (unsigned)task, hb = 0x9e3779b9u, hc = 0x9e3779b9u;
+    jenkins_mix(ha, hb, hc);
+    jenkins_mix(ha, hb, hc);
+    const float k32 = 2.3283064365386963e-10f;                                  // 2^-32: exact scaling
+    const float off[3] = {__fmul_rn((float)ha, k32), __fmul_rn((float)hb, k32), __fmul_rn((float)hc, k32)};
+
+    unsigned r1 = 0, r2 = 0;
+    {
+        unsigned v1 = 1u << 31, v2 = 3u << 30;
+        for (int j = i; j; j >>= 1) {
+            if (j & 1) { r1 ^= v1; r2 ^= v2 << 1; }
+            v1 |= v1 >> 1;
+            v2 ^= v2 >> 1;
+        }
+    }
+    float pos[3] = {__fmul_rn((float)r1, k32), __fmul_rn((float)r2, k32), __fdiv_rn(__fadd_rn((float)i, 0.5f), (float)a.numSamples)};
+    const float light[3] = {a.lightPos[0], a.lightPos[1], a.lightPos[2]};
+    float dirv[3];
+    const float org[3] = {origin.x, origin.y, origin.z};
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        float p = __fadd_rn(pos[k], off[k]);
+        if (p >= 1.0f) p = __fsub_rn(p, 1.0f);
+        p = __fsub_rn(__fmul_rn(p, 2.0f), 1.0f);
+        const float target = __fadd_rn(light[k], __fmul_rn(a.lightRadius, p));
+        dirv[k] = __fsub_rn(target, org[k]);
+    }
+    const F3 d = mk(dirv[0], dirv[1], dirv[2]);
+    const F3 dir = normalize3(d);
+    a.outRays[o * 2 + 0] = make_float4(origin.x, origin.y, origin.z, 0.0f);
+    a.outRays[o * 2 + 1] = make_float4(dir.x, dir.y, dir.z, (tri == -1) ? -1.0f : __fsqrt_rn(dot3(d, d)));
+    if (a.outIDToSlot) a.outIDToSlot[o] = o;
+    if (a.outSlotToID) a.outSlotToID[o] = o;
+}
+
 __global__ void __launch_bounds__(256) count_hits_kernel(const int4* __restrict__ results, int numRays, int* __restrict__ counter)
 {
     int c = 0;
@@ -198,6 +251,14 @@ cudaError_t launch_raygen_ao(const AOArgs& a, cudaStream_t s)
     const long long n = (long long)a.numInputRays * a.numSamples;
     if (n <= 0) return cudaSuccess;
     raygen_ao_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_raygen_shadow(const ShadowArgs& a, cudaStream_t s)
+{
+    const long long n = (long long)a.numInputRays * a.numSamples;
+    if (n <= 0) return cudaSuccess;
+    raygen_shadow_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(a);
     return cudaGetLastError();
 }
 

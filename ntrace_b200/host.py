@@ -281,6 +281,7 @@ class RayGen:
     def __init__(self, maxBatchSize: int = 1 << 20):
         self.m_maxBatchSize = maxBatchSize
         self.m_aoStartIdx = 0
+        self.m_shadowStartIdx = 0
 
     def primary(self, orays: RayBuffer, origin, nscreenToWorld, w: int, h: int, maxDist: float, randomSeed: int = 0):
         orays.resize(w * h)
@@ -310,6 +311,19 @@ class RayGen:
         _sync()
         capi.raygen_ao(orays.getRayBuffer(), orays.getIDToSlotBuffer(), orays.getSlotToIDBuffer(), irays.getRayBuffer(),
                        irays.getResultBuffer(), scene.triNormal, lo, hi - lo, numSamples, maxDist, randomSeed)
+        return True, newBatch
+
+
+    def shadow(self, orays: RayBuffer, irays: RayBuffer, numSamples: int, lightPos, lightRadius: float, newBatch: bool, randomSeed: int = 0):
+        """RayGen::shadow (RayGen.cpp:114-147) -> (generated, newBatch): any-hit rays from the hit points towards a light."""
+        ok, lo, hi, self.m_shadowStartIdx, newBatch = self.batching(irays.getSize(), numSamples, self.m_shadowStartIdx, newBatch)
+        if not ok:
+            return False, newBatch
+        orays.resize((hi - lo) * numSamples)
+        orays.setNeedClosestHit(False)
+        _sync()
+        capi.raygen_shadow(orays.getRayBuffer(), orays.getIDToSlotBuffer(), orays.getSlotToIDBuffer(), irays.getRayBuffer(),
+                           irays.getResultBuffer(), lo, hi - lo, numSamples, lightPos, lightRadius, randomSeed)
         return True, newBatch
 
 

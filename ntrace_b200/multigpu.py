@@ -92,3 +92,50 @@ def trace_batch_sharded(tracer, rays, rank: int, world: int) -> float:
     from . import host
     host._sync()
     return capi.trace_batch(rays.getRayBuffer()[lo:hi], rays.getResultBuffer()[lo:hi], hi - lo, rays.getNeedClosestHit())
+
+
+# --------------------------------------------------------------------------------------------------
+# Host placement: one process per GPU wants its pinned ray / result buffers on the NUMA node the GPU hangs off, otherwise
+# every zero-copy read and DMA crosses the socket interconnect (measured at 8 GPUs: host-buffer Mrays/s per GPU drops
+# to a third without this).
+def _parse_cpulist(text: str):
+    cpus = set()
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        if "-" in part:
+            a, b = part.split("-")
+            cpus.update(range(int(a), int(b) + 1))
+        else:
+            cpus.add(int(part))
+    return cpus
+
+
+def gpu_numa_node(pci_domain: int, pci_bus: int, pci_device: int, sysfs: str = "/sys") -> int:
+    """NUMA node of a PCI device from sysfs, -1 when the platform does not say."""
+    path = f"{sysfs}/bus/pci/devices/{pci_domain:04x}:{pci_bus:02x}:{pci_device:02x}.0/numa_node"
+    try:
+        return int(open(path).read().strip())
+    except (OSError, ValueError):
+        return -1
+
+
+def bind_host_to_gpu(local_rank: int, sysfs: str = "/sys"):
+    """Restrict this process to the CPUs of the GPU's NUMA node (first-touch then places pinned memory there).
+    Returns (previous affinity, node) so a caller can restore it; (None, -1) when nothing was changed."""
+    import os
+    import torch
+    try:
+        p = torch.cuda.get_device_properties(local_rank)
+        node = gpu_numa_node(getattr(p, "pci_domain_id", 0), p.pci_bus_id, p.pci_device_id, sysfs)
+        if node < 0:
+            return None, -1
+        cpus = _parse_cpulist(open(f"{sysfs}/devices/system/node/node{node}/cpulist").read())
+        prev = os.sched_getaffinity(0)
+        want = cpus & prev
+        if not want:
+            return None, node
+        os.sched_setaffinity(0, want)
+        return prev, node
+    except (OSError, AttributeError, RuntimeError, ValueError):
+        return None, -1

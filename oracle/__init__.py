@@ -121,6 +121,20 @@ class CpuBVH:
         return nodes, woop, idx
 
 
+    def basic(self, layout: int):
+        """CudaBVH(bvh, layout) for layout 0..3 (AOS_AOS, AOS_SOA, SOA_AOS, SOA_SOA; CudaBVH.cpp:453-575)
+        -> (nodes, woop, triIndex) int32 arrays, 4096-byte padded like the reference's, padding zero."""
+        if layout not in (0, 1, 2, 3):
+            raise ValueError("basic layouts are 0..3")
+        sizes = np.zeros(3, dtype=np.int64)
+        lib().orc_bvh_basic(self._h, C.c_int(layout), _p(sizes), None, None, None)
+        nodes = np.zeros(sizes[0] // 4, dtype=np.int32)
+        woop = np.zeros(sizes[1] // 4, dtype=np.int32)
+        idx = np.zeros(sizes[2] // 4, dtype=np.int32)
+        lib().orc_bvh_basic(self._h, C.c_int(layout), _p(sizes), _p(nodes), _p(woop), _p(idx))
+        return nodes, woop, idx
+
+
 def compact_trace(nodes, woop, tri_index, rays, need_closest=True, counters=False, nthreads=0):
     """CudaBVH::trace<BVHLayout_Compact> (Woop test on the flat buffers)."""
     nodes, woop, tri_index = _i32(nodes), _i32(woop), _i32(tri_index)
@@ -275,6 +289,16 @@ def raygen_ao(in_rays, in_results, normals, first, count, samples, max_dist, see
     a = np.zeros(count * samples, dtype=np.int32); b = np.zeros(count * samples, dtype=np.int32)
     lib().orc_raygen_ao(_p(out), _p(a), _p(b), _p(in_rays), _p(in_results), _p(normals), C.c_int(first), C.c_int(count),
                         C.c_int(samples), C.c_float(max_dist), C.c_uint32(seed))
+    return out, a, b
+
+
+def raygen_shadow(in_rays, in_results, first, count, samples, light_pos, light_radius, seed):
+    """rayGenShadowKernel (RayGenKernels.cu:240-302) -> (rays, idToSlot, slotToID)."""
+    in_rays = _f32(in_rays).reshape(-1, 8); in_results = _i32(in_results).reshape(-1, 4); lp = _f32(light_pos)
+    out = np.zeros((count * samples, 8), dtype=np.float32)
+    a = np.zeros(count * samples, dtype=np.int32); b = np.zeros(count * samples, dtype=np.int32)
+    lib().orc_raygen_shadow(_p(out), _p(a), _p(b), _p(in_rays), _p(in_results), C.c_int(first), C.c_int(count), C.c_int(samples),
+                            _p(lp), C.c_float(light_radius), C.c_uint32(seed))
     return out, a, b
 
 

@@ -584,6 +584,64 @@ void create_compact(const BVH& bvh, CompactBVH& out, int div)
     }
 }
 
+// createNodeBasic / createTriWoopBasic / createTriIndexBasic — CudaBVH.cpp:453-575.  Every node, leaves included, is a
+// 64-byte record numbered in the order the depth-first stack hands indices out (both children at once, right child
+// popped first); leaves carry their bounds twice and (lo, hi) in the link words.  Note the -0.0f guard of createCompact
+// is NOT applied here (the basic layouts have no terminator to alias).
+void create_basic(const BVH& bvh, int layout, CompactBVH& out)
+{
+    const bool nodeSOA = (layout == 2 || layout == 3), triSOA = (layout == 1 || layout == 3);
+    const size_t Align = 4096;
+    size_t numNodes = 0;
+    {   // subtree node count from the root (the node pool may hold unreachable entries)
+        std::vector<int> st{bvh.root};
+        while (!st.empty()) { int n = st.back(); st.pop_back(); numNodes++; if (!bvh.nodes[n].leaf) { st.push_back(bvh.nodes[n].child[0]); st.push_back(bvh.nodes[n].child[1]); } }
+    }
+    const size_t nodeBytes = (numNodes * 64 + Align - 1) & ~(Align - 1);
+    out.nodes.assign(nodeBytes / 4, 0);
+    struct Entry { int node; int idx; };
+    int next = 0;
+    std::vector<Entry> stack;
+    stack.push_back({bvh.root, next++});
+    auto fb = [](float f) { return (int32_t)f2u(f); };
+    while (!stack.empty()) {
+        Entry e = stack.back();
+        stack.pop_back();
+        const Node& n = bvh.nodes[e.node];
+        const AABB *b0, *b1;
+        int c0, c1, split = 0;
+        if (n.leaf) { b0 = b1 = &n.bounds; c0 = n.lo; c1 = n.hi; }
+        else {
+            Entry e0{n.child[0], next++}, e1{n.child[1], next++};
+            stack.push_back(e0); stack.push_back(e1);
+            b0 = &bvh.nodes[e0.node].bounds; b1 = &bvh.nodes[e1.node].bounds;
+            c0 = bvh.nodes[e0.node].leaf ? ~e0.idx : e0.idx;
+            c1 = bvh.nodes[e1.node].leaf ? ~e1.idx : e1.idx;
+            split = (n.axis | (n.splitType << 2));
+        }
+        const int32_t data[16] = {fb(b0->mn.x), fb(b0->mx.x), fb(b0->mn.y), fb(b0->mx.y), fb(b1->mn.x), fb(b1->mx.x), fb(b1->mn.y), fb(b1->mx.y),
+                                  fb(b0->mn.z), fb(b0->mx.z), fb(b1->mn.z), fb(b1->mx.z), c0, c1, split, 0};
+        for (int j = 0; j < 4; j++) {
+            int32_t* dst = nodeSOA ? &out.nodes[(size_t)e.idx * 4 + (nodeBytes / 16) * j] : &out.nodes[(size_t)e.idx * 16 + 4 * j];
+            for (int k = 0; k < 4; k++) dst[k] = data[4 * j + k];
+        }
+    }
+    const size_t R = bvh.triIndices.size();
+    const size_t woopBytes = (R * 64 + Align - 1) & ~(Align - 1);
+    out.woop.assign(woopBytes / 4, 0);
+    out.triIndex.assign(R, 0);
+    for (size_t i = 0; i < R; i++) {
+        int tri = bvh.triIndices[i];
+        float w[12];
+        woopify_tri(bvh.scene.v(tri, 0), bvh.scene.v(tri, 1), bvh.scene.v(tri, 2), w);
+        for (int j = 0; j < 3; j++) {
+            int32_t* dst = triSOA ? &out.woop[i * 4 + (woopBytes / 16) * j] : &out.woop[i * 16 + 4 * j];
+            for (int k = 0; k < 4; k++) dst[k] = (int32_t)f2u(w[4 * j + k]);
+        }
+        out.triIndex[i] = tri;
+    }
+}
+
 // =========================================================================================
 // CudaBVH::trace<BVHLayout_Compact> — CudaBVH.cpp:698-784, 1083-1126, 1183-1225, 1251-1265
 // =========================================================================================

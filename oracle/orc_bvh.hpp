@@ -79,6 +79,8 @@ struct CompactBVH {
 };
 void woopify_tri(V3 v0, V3 v1, V3 v2, float out[12]);                  // CudaBVH.cpp:667-687
 void create_compact(const BVH& bvh, CompactBVH& out, int nodeOffsetSizeDiv = 1);   // CudaBVH.cpp:579-664
+// layout: 0 AOS_AOS, 1 AOS_SOA, 2 SOA_AOS, 3 SOA_SOA (CudaTracerKernels.hpp:54-57).  Buffers 4096-byte padded, padding zero.
+void create_basic(const BVH& bvh, int layout, CompactBVH& out);                    // CudaBVH.cpp:453-575
 
 void trace_compact(const int32_t* nodes, const int32_t* woop, const int32_t* triIndex,
                    const Ray* rays, RayResult* results, int n, bool needClosestHit,

@@ -85,6 +85,18 @@ void orc_bvh_compact_copy(void* p, void* nodes, void* woop, void* triIndex)
     std::memcpy(triIndex, h->compact.triIndex.data(), h->compact.triIndex.size() * 4);
 }
 
+// CudaBVH(bvh, layout) for the basic layouts; call with null buffers to get the sizes
+void orc_bvh_basic(void* p, int layout, int64_t* sizes, void* nodes, void* woop, void* triIndex)
+{
+    BvhHandle* h = (BvhHandle*)p;
+    CompactBVH b;
+    create_basic(h->bvh, layout, b);
+    sizes[0] = (int64_t)b.nodes.size() * 4; sizes[1] = (int64_t)b.woop.size() * 4; sizes[2] = (int64_t)b.triIndex.size() * 4;
+    if (nodes) std::memcpy(nodes, b.nodes.data(), b.nodes.size() * 4);
+    if (woop) std::memcpy(woop, b.woop.data(), b.woop.size() * 4);
+    if (triIndex) std::memcpy(triIndex, b.triIndex.data(), b.triIndex.size() * 4);
+}
+
 void orc_compact_trace(const int32_t* nodes, const int32_t* woop, const int32_t* triIndex,
                        const float* rays, int n, int needClosest, int32_t* results, uint32_t* counters, int nthreads)
 {
@@ -191,6 +203,12 @@ void orc_raygen_ao(float* outRays, int32_t* outIDToSlot, int32_t* outSlotToID, c
 {
     raygen_ao((Ray*)outRays, outIDToSlot, outSlotToID, (const Ray*)inRays, (const RayResult*)inResults, (const V3*)normals,
               firstInputSlot, numInputRays, numSamples, maxDist, seed);
+}
+void orc_raygen_shadow(float* outRays, int32_t* outIDToSlot, int32_t* outSlotToID, const float* inRays, const int32_t* inResults,
+                       int firstInputSlot, int numInputRays, int numSamples, const float* lightPos, float lightRadius, uint32_t seed)
+{
+    raygen_shadow((Ray*)outRays, outIDToSlot, outSlotToID, (const Ray*)inRays, (const RayResult*)inResults,
+                  firstInputSlot, numInputRays, numSamples, V3(lightPos[0], lightPos[1], lightPos[2]), lightRadius, seed);
 }
 int orc_count_hits(const int32_t* results, int n) { return count_hits((const RayResult*)results, n); }
 void orc_tri_normals(const float* vtx, int nv, const int32_t* tri, int nt, float* out)

@@ -154,6 +154,53 @@ void raygen_ao(Ray* outRays, int32_t* outIDToSlot, int32_t* outSlotToID,
     }
 }
 
+// rayGenShadowKernel — RayGenKernels.cu:47-73 (hammersley, sobol2D), 240-302
+void raygen_shadow(Ray* outRays, int32_t* outIDToSlot, int32_t* outSlotToID, const Ray* inRays, const RayResult* inResults,
+                   int firstInputSlot, int numInputRays, int numSamples, V3 lightPos, float lightRadius, uint32_t randomSeed)
+{
+    const float k32 = 2.3283064365386963e-10f;     // exp2(-32): scaling by a power of two is exact, so float == the kernel's double product
+    for (int task = 0; task < numInputRays; task++) {
+        int inSlot = task + firstInputSlot;
+        const Ray& inRay = inRays[inSlot];
+        const RayResult& inRes = inResults[inSlot];
+        int outSlot = task * numSamples;
+        float epsilon = 1.0e-2f;
+        V3 origin = inRay.o + inRay.d * std::fmax(inRes.t - epsilon, 0.0f);
+        uint32_t a = randomSeed + (uint32_t)task, b = 0x9e3779b9u, c = 0x9e3779b9u;
+        jenkins_mix(a, b, c);
+        jenkins_mix(a, b, c);
+        V3 offset((float)a * k32, (float)b * k32, (float)c * k32);
+        int tri = inRes.id;
+        for (int i = 0; i < numSamples; i++) {
+            uint32_t r1 = 0, r2 = 0;
+            {
+                uint32_t v1 = 1u << 31, v2 = 3u << 30;
+                for (int j = i; j; j >>= 1) {
+                    if (j & 1) { r1 ^= v1; r2 ^= v2 << 1; }
+                    v1 |= v1 >> 1;
+                    v2 ^= v2 >> 1;
+                }
+            }
+            float p[3] = {(float)r1 * k32, (float)r2 * k32, ((float)i + 0.5f) / (float)numSamples};
+            float o[3] = {offset.x, offset.y, offset.z};
+            for (int k = 0; k < 3; k++) {
+                p[k] = p[k] + o[k];
+                if (p[k] >= 1.0f) p[k] -= 1.0f;
+                p[k] = p[k] * 2.0f - 1.0f;
+            }
+            V3 target = lightPos + V3(p[0], p[1], p[2]) * lightRadius;
+            V3 direction = target - origin;
+            Ray& o2 = outRays[outSlot + i];
+            o2.o = origin;
+            o2.d = normalize(direction);
+            o2.tmin = 0.0f;
+            o2.tmax = (tri == -1) ? -1.0f : length(direction);
+            if (outIDToSlot) outIDToSlot[outSlot + i] = i + outSlot;
+            if (outSlotToID) outSlotToID[outSlot + i] = i + outSlot;
+        }
+    }
+}
+
 int count_hits(const RayResult* results, int n)
 {
     int c = 0;

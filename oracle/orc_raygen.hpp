@@ -10,6 +10,8 @@ void raygen_primary(Ray* rays, int32_t* idToSlot, int32_t* slotToID, V3 origin, 
 void raygen_ao(Ray* outRays, int32_t* outIDToSlot, int32_t* outSlotToID,
                const Ray* inRays, const RayResult* inResults, const V3* normals,
                int firstInputSlot, int numInputRays, int numSamples, float maxDist, uint32_t randomSeed);  // RayGenKernels.cu:129-236
+void raygen_shadow(Ray* outRays, int32_t* outIDToSlot, int32_t* outSlotToID, const Ray* inRays, const RayResult* inResults,
+                   int firstInputSlot, int numInputRays, int numSamples, V3 lightPos, float lightRadius, uint32_t randomSeed);  // RayGenKernels.cu:240-302
 int  count_hits(const RayResult* results, int n);                                              // RendererKernels.cu:174-224
 void tri_normals(const Scene& sc, V3* out);                                                    // Scene.cpp:112
 

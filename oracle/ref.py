@@ -100,6 +100,26 @@ class RefBVH:
         lib().ref_compact_copy(self._h, _p(nodes), _p(woop), _p(idx))
         return nodes, woop, idx
 
+    def layout(self, layout: int):
+        """CudaBVH(bvh, layout) for any BVHLayout value (0 AOS_AOS, 1 AOS_SOA, 2 SOA_AOS, 3 SOA_SOA, 4 Compact, 5 Compact2)
+        -> (nodes, woop, triIndex) int32 arrays, 4096-byte padded as the reference allocates them (padding zero-filled)."""
+        sizes = np.zeros(3, dtype=np.int64)
+        if lib().ref_layout_sizes(self._h, C.c_int(layout), _p(sizes)):
+            raise ValueError("bad layout")
+        nodes = np.zeros(sizes[0] // 4, dtype=np.int32)
+        woop = np.zeros(sizes[1] // 4, dtype=np.int32)
+        idx = np.zeros(sizes[2] // 4, dtype=np.int32)
+        lib().ref_layout_copy(self._h, C.c_int(layout), _p(nodes), _p(woop), _p(idx))
+        return nodes, woop, idx
+
+    def layout_trace(self, layout: int, rays, need_closest=True) -> np.ndarray:
+        """CudaBVH::trace on the AOS_AOS (0) or Compact (4) buffers."""
+        rays = _f32(rays).reshape(-1, 8)
+        res = np.zeros((len(rays), 4), dtype=np.int32)
+        if lib().ref_layout_trace(self._h, C.c_int(layout), _p(rays), C.c_int(len(rays)), C.c_int(1 if need_closest else 0), _p(res)):
+            raise ValueError("CudaBVH::trace handles AOS_AOS and Compact only")
+        return res
+
     def compact_trace(self, rays, need_closest=True, nthreads=1) -> np.ndarray:
         """CudaBVH::trace on the Compact layout (CudaBVH.cpp:213-302)."""
         rays = _f32(rays).reshape(-1, 8)

@@ -59,7 +59,15 @@ struct RefHandle
 {
     Scene* scene; Platform platform; BVH::Stats stats; BVH* bvh; CudaBVH* compact;
     std::vector<CudaBVH*> perThread;     // CudaBVH::trace keeps per-call state in members: one object per worker thread
+    CudaBVH* byLayout[BVHLayout_Max];    // CudaBVH(bvh, layout) for the basic layouts (createNodeBasic / createTriWoopBasic / createTriIndexBasic)
 };
+
+static CudaBVH* layout_bvh(RefHandle* h, int layout)
+{
+    if (layout < 0 || layout >= BVHLayout_Max) return NULL;
+    if (!h->byLayout[layout]) h->byLayout[layout] = new CudaBVH(*h->bvh, (BVHLayout)layout);
+    return h->byLayout[layout];
+}
 
 static void fill_rays(RayBuffer& rb, const float* rays, int n, bool closest)
 {
@@ -90,9 +98,10 @@ void* ref_build(const float* verts, int nv, const int* tris, int nt, int splitBV
     params.splitAlpha = alpha;
     h->bvh = new BVH(h->scene, h->platform, params);
     h->compact = NULL;
+    for (int i = 0; i < BVHLayout_Max; i++) h->byLayout[i] = NULL;
     return h;
 }
-void ref_free(void* p) { RefHandle* h = (RefHandle*)p; for (size_t i = 0; i < h->perThread.size(); i++) delete h->perThread[i]; delete h->compact; delete h->bvh; delete h->scene; delete h; }
+void ref_free(void* p) { RefHandle* h = (RefHandle*)p; for (size_t i = 0; i < h->perThread.size(); i++) delete h->perThread[i]; for (int i = 0; i < BVHLayout_Max; i++) delete h->byLayout[i]; delete h->compact; delete h->bvh; delete h->scene; delete h; }
 
 // out: [SAHCost, numInner, numLeaf, numTris, maxDepth, numTriIndices]
 void ref_stats(void* p, double* out)
@@ -138,6 +147,34 @@ void ref_compact_trace(void* p, const float* rays, int n, int closest, int* resu
     Buffer visibility;
     h->compact->trace(rb, visibility, false, NULL);                   // CudaBVH.cpp:213-302
     for (int i = 0; i < n; i++) memcpy(results + 4 * i, &rb.getResultForSlot(i), 16);
+}
+// CudaBVH(bvh, layout) for any BVHLayout (CudaBVH.cpp:60-101, 453-575): buffers and, for AOS_AOS / Compact, the CPU trace
+int ref_layout_sizes(void* p, int layout, long long* sizes)
+{
+    CudaBVH* b = layout_bvh((RefHandle*)p, layout);
+    if (!b) return 1;
+    sizes[0] = b->getNodeBuffer().getSize(); sizes[1] = b->getTriWoopBuffer().getSize(); sizes[2] = b->getTriIndexBuffer().getSize();
+    return 0;
+}
+int ref_layout_copy(void* p, int layout, void* nodes, void* woop, void* idx)
+{
+    CudaBVH* b = layout_bvh((RefHandle*)p, layout);
+    if (!b) return 1;
+    memcpy(nodes, b->getNodeBuffer().getPtr(), (size_t)b->getNodeBuffer().getSize());
+    memcpy(woop, b->getTriWoopBuffer().getPtr(), (size_t)b->getTriWoopBuffer().getSize());
+    memcpy(idx, b->getTriIndexBuffer().getPtr(), (size_t)b->getTriIndexBuffer().getSize());
+    return 0;
+}
+int ref_layout_trace(void* p, int layout, const float* rays, int n, int closest, int* results)
+{
+    CudaBVH* b = layout_bvh((RefHandle*)p, layout);
+    if (!b || (layout != BVHLayout_AOS_AOS && layout != BVHLayout_Compact)) return 1;     // the layouts CudaBVH::trace switches on
+    RayBuffer rb;
+    fill_rays(rb, rays, n, closest != 0);
+    Buffer visibility;
+    b->trace(rb, visibility, false, NULL);
+    for (int i = 0; i < n; i++) memcpy(results + 4 * i, &rb.getResultForSlot(i), 16);
+    return 0;
 }
 // the same call fanned out over host threads (the reference is single-threaded; bench.py --impl reference uses every core
 // the box gives it).  Each worker owns a CudaBVH built from the same BVH and a contiguous slice of the rays.

@@ -75,7 +75,10 @@ def main():
             flat = b.compact_trace(rays, True)
             flat_any = b.compact_trace(rays, False)
             tree_any = b.trace(rays, False)
-            meta[name]["configs"][cfg] = dict(st, tri_indices_sha=sha(b.tri_indices()), woop_buffer_sha=sha(woop), tri_index_buffer_sha=sha(idx),
+            aos = b.layout_trace(0, rays, True)
+            assert np.array_equal(aos[:, :2], flat[:, :2]), "CudaBVH::trace<AOS_AOS> and <Compact> disagree"
+            layout_sha = {str(L): [sha(a) for a in b.layout(L)] for L in range(4)}
+            meta[name]["configs"][cfg] = dict(st, layout_sha=layout_sha, aos_aos_trace_equals_compact=True, tri_indices_sha=sha(b.tri_indices()), woop_buffer_sha=sha(woop), tri_index_buffer_sha=sha(idx),
                                               inner_sha=sha(c.inner), boxes_sha=sha(c.boxes), leaf_sizes_sha=sha(c.leaf_sizes),
                                               hits=int((flat[:, 0] >= 0).sum()))
             arrays[f"{cfg}.tree"] = tree[:, :2].copy()

@@ -150,3 +150,47 @@ SubdivisionRayCaster { numWarpsPerBlock 4
     if os.path.exists("/root/reference/config.conf"):
         e2 = Environment(); e2.ReadEnvFile("/root/reference/config.conf")
         assert e2.GetString("Renderer.dataStructure") == "KDTree" and e2.GetInt("Benchmark.measureRepeats") == 5
+
+
+def test_gpu_numa_lookup_reads_sysfs(tmp_path):
+    """multigpu.gpu_numa_node / _parse_cpulist: host placement of the pinned ray buffers next to the GPU."""
+    from ntrace_b200 import multigpu
+    dev = tmp_path / "bus" / "pci" / "devices" / "0000:1b:00.0"
+    dev.mkdir(parents=True)
+    (dev / "numa_node").write_text("1\n")
+    assert multigpu.gpu_numa_node(0, 0x1b, 0, sysfs=str(tmp_path)) == 1
+    assert multigpu.gpu_numa_node(0, 0x2c, 0, sysfs=str(tmp_path)) == -1          # unknown device
+    (dev / "numa_node").write_text("-1\n")
+    assert multigpu.gpu_numa_node(0, 0x1b, 0, sysfs=str(tmp_path)) == -1          # platform does not say (VMs)
+    assert multigpu._parse_cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11}
+    assert multigpu._parse_cpulist("") == set()
+
+
+def test_shadow_ray_generator_properties(orc):
+    """rayGenShadowKernel restated (RayGenKernels.cu:240-302): targets lie in the light's cube, tmax is the distance to
+    the target, misses give degenerate rays, sample sets are Cranley-Patterson rotations of one QMC pattern."""
+    rng = np.random.default_rng(3)
+    n, spp = 200, 16
+    o = rng.normal(size=(n, 3)); d = rng.normal(size=(n, 3)); d /= np.linalg.norm(d, axis=1, keepdims=True)
+    rays = np.concatenate([o, np.zeros((n, 1)), d, np.full((n, 1), 100.0)], axis=1).astype(np.float32)
+    res = np.zeros((n, 4), np.int32)
+    t = rng.uniform(0.5, 5.0, n).astype(np.float32)
+    res[:, 0] = np.where(np.arange(n) % 5 == 0, -1, np.arange(n))
+    res[:, 1] = t.view(np.int32)
+    light, radius = np.array([2.0, 9.0, -1.0], np.float32), 0.5
+    out, a, b = orc.raygen_shadow(rays, res, 0, n, spp, light, radius, 77)
+    assert np.array_equal(a, np.arange(n * spp)) and np.array_equal(b, np.arange(n * spp))
+    out = out.reshape(n, spp, 8)
+    origin = rays[:, :3] + rays[:, 4:7] * np.maximum(t - np.float32(1e-2), 0)[:, None]
+    assert np.allclose(out[:, :, :3], origin[:, None, :], atol=1e-6)
+    miss = res[:, 0] == -1
+    assert (out[miss, :, 7] == -1.0).all() and (out[~miss, :, 7] > 0).all()
+    assert np.allclose(np.linalg.norm(out[:, :, 4:7], axis=2), 1.0, atol=1e-5)
+    target = out[~miss, :, :3] + out[~miss, :, 4:7] * out[~miss, :, 7:8]
+    assert (np.abs(target - light) <= radius * (1 + 1e-4) + 1e-4).all()
+    # per input ray the 16 targets are distinct and spread over the cube (z = Hammersley: one per 1/16 slab, rotated)
+    z = np.sort(((target[:, :, 2] - light[2]) / radius + 1) / 2, axis=1)
+    assert (np.diff(z, axis=1) > 0.03).all()
+    # a different seed rotates the pattern
+    out2, _, _ = orc.raygen_shadow(rays, res, 0, n, spp, light, radius, 78)
+    assert not np.array_equal(out2.reshape(n, spp, 8)[~miss][:, :, 4:7], out[~miss][:, :, 4:7])

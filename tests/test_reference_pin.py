@@ -73,6 +73,9 @@ def test_oracle_reproduces_frozen_reference_outputs(orc, name, cfg):
     assert sha(woop) == e["woop_buffer_sha"] and sha(idx) == e["tri_index_buffer_sha"]
     c = orc.canonical(nodes, woop, idx)
     assert (sha(c.inner), sha(c.boxes), sha(c.leaf_sizes)) == (e["inner_sha"], e["boxes_sha"], e["leaf_sizes_sha"])
+    # the basic layouts (createNodeBasic / createTriWoopBasic / createTriIndexBasic): byte-identical buffers
+    for L in range(4):
+        assert [sha(a) for a in b.basic(L)] == e["layout_sha"][str(L)]
     # tracers: ids and t bit patterns, closest-hit and any-hit
     z = np.load(os.path.join(HERE, f"ref_{name}.npz"))
     assert np.array_equal(b.trace(rays, True)[:, :2], z[f"{cfg}.tree"])
@@ -130,6 +133,10 @@ def test_oracle_matches_live_reference(orc, ref, scene, seed, cfg):
     rc, oc = orc.canonical(rn, rw, ri), orc.canonical(nodes, woop, idx)
     assert np.array_equal(rc.inner, oc.inner) and np.array_equal(rc.boxes.view(np.int32), oc.boxes.view(np.int32))
     assert np.array_equal(rc.leaf_sizes, oc.leaf_sizes) and np.array_equal(rc.tris, oc.tris)
+    for L in range(4):
+        for x, y in zip(r.layout(L), b.basic(L)):
+            assert np.array_equal(x, y)
+    assert np.array_equal(r.layout_trace(0, rays, True)[:, :2], r.compact_trace(rays, True)[:, :2])
     for closest in (True, False):
         assert np.array_equal(r.trace(rays, closest)[:, :2], b.trace(rays, closest)[:, :2])
         assert np.array_equal(r.compact_trace(rays, closest)[:, :2], orc.compact_trace(nodes, woop, idx, rays, closest)[:, :2])
