@@ -119,6 +119,13 @@ int nt_bvh_build_debug(uint32_t* sortedKeys, int32_t* sortedIdx, int numTris);
  * needClosestHit == 0 -> any-hit.  outSeconds = CUDA-event time around the kernel only. */
 int nt_trace_batch(const float* rays, int32_t* results, int numRays, int needClosestHit,
                    float* outSeconds);
+/* Asynchronous form of traceBatch (NEW; the reference's call is synchronous): submit a batch into one of 4 slots and
+ * collect it later, so a host loop can keep independent batches of a frame in flight.  Buffers must be device memory or
+ * pinned host memory and must stay valid until nt_trace_wait(slot) returns.  Host rays are DMA'd in on a copy stream,
+ * results DMA'd out on another: with two or more slots in flight copy-in, traversal and copy-out of consecutive batches
+ * overlap.  nt_trace_wait returns the kernel seconds of that batch like nt_trace_batch; waiting on an idle slot is a no-op. */
+int nt_trace_batch_async(const float* rays, int32_t* results, int numRays, int needClosestHit, int slot);
+int nt_trace_wait(int slot, float* outSeconds);
 
 /* ---- ray generation: FW::RayGen (src/rt/ray/RayGen.cpp) ------------------------------------ */
 /* RayGen::primary (RayGen.cpp:45-74): slot i -> pixel PixelTable[i]; idToSlot / slotToID may be NULL. */

@@ -28,7 +28,7 @@ EXPORTS = [
     "nt_set_kernel", "nt_desired_layout", "nt_kernel_config",
     "nt_bvh_upload", "nt_bvh_alloc", "nt_bvh_build", "nt_bvh_set_collapse", "nt_bvh_convert", "nt_bvh_sizes", "nt_bvh_download",
     "nt_bvh_device_ptrs", "nt_bvh_build_debug",
-    "nt_trace_batch", "nt_raygen_primary", "nt_raygen_ao", "nt_raygen_shadow", "nt_ray_sort", "nt_count_hits", "nt_tri_normals",
+    "nt_trace_batch", "nt_trace_batch_async", "nt_trace_wait", "nt_raygen_primary", "nt_raygen_ao", "nt_raygen_shadow", "nt_ray_sort", "nt_count_hits", "nt_tri_normals",
 ]
 
 
@@ -200,6 +200,21 @@ def trace_batch(rays, results, num_rays: int, need_closest_hit: bool) -> float:
     sec = C.c_float(0.0)
     _check(lib().nt_trace_batch(ptr(rays, np.float32, num_rays * 32), ptr(results, np.int32, num_rays * 16), C.c_int(num_rays),
                                 C.c_int(1 if need_closest_hit else 0), C.byref(sec)))
+    return float(sec.value)
+
+
+ASYNC_SLOTS = 4
+
+
+def trace_batch_async(rays, results, num_rays: int, need_closest_hit: bool, slot: int):
+    """Submit a batch into `slot` (device or pinned host buffers); collect with trace_wait(slot)."""
+    _check(lib().nt_trace_batch_async(ptr(rays, np.float32, num_rays * 32), ptr(results, np.int32, num_rays * 16), C.c_int(num_rays),
+                                      C.c_int(1 if need_closest_hit else 0), C.c_int(slot)))
+
+
+def trace_wait(slot: int) -> float:
+    sec = C.c_float(0.0)
+    _check(lib().nt_trace_wait(C.c_int(slot), C.byref(sec)))
     return float(sec.value)
 
 

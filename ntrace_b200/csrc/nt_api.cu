@@ -55,6 +55,13 @@ struct Context {
     cudaEvent_t evIn[kMaxChunks] = {}, evKa[kMaxChunks] = {}, evKb[kMaxChunks] = {};
     bool deferred = false;
     int64_t launches = 0;
+    // asynchronous submission (nt_trace_batch_async / nt_trace_wait): per-slot staging + events
+    static constexpr int kAsyncSlots = 4;
+    struct AsyncSlot {
+        DevBuf rays, results;
+        cudaEvent_t evIn = nullptr, evKa = nullptr, evKb = nullptr, evOut = nullptr;
+        bool busy = false, copyOut = false;
+    } async[kAsyncSlots];
 
     int kernel = Kernel_PersistentSpeculative;
     int kernelLayout = Layout_Compact;
@@ -242,6 +249,12 @@ int nt_init(int device_ordinal)
         NT_CUDA(cudaEventCreate(&g.evKa[i]));
         NT_CUDA(cudaEventCreate(&g.evKb[i]));
     }
+    for (int i = 0; i < Context::kAsyncSlots; i++) {
+        NT_CUDA(cudaEventCreateWithFlags(&g.async[i].evIn, cudaEventDisableTiming));
+        NT_CUDA(cudaEventCreate(&g.async[i].evKa));
+        NT_CUDA(cudaEventCreate(&g.async[i].evKb));
+        NT_CUDA(cudaEventCreateWithFlags(&g.async[i].evOut, cudaEventDisableTiming));
+    }
     NT_CUDA(g.counters.reserve(256));
     NT_CUDA(cudaMemsetAsync(g.counters.p, 0, 256, g.stream));
     NT_CUDA(cudaStreamSynchronize(g.stream));
@@ -256,9 +269,16 @@ void nt_shutdown(void)
     if (!g.inited) return;
     cudaSetDevice(g.device);
     cudaStreamSynchronize(g.stream);
+    cudaStreamSynchronize(g.sIn);
+    cudaStreamSynchronize(g.sOut);
     DevBuf* bufs[] = {&g.nodes, &g.woop, &g.triIndex, &g.sortedKeys, &g.sortedIdx, &g.stRays, &g.stResults, &g.stA, &g.stB,
-                      &g.stC, &g.stD, &g.stE, &g.counters, &g.pixelTable, &g.sceneVerts, &g.sceneTris};
+                      &g.stC, &g.stD, &g.stE, &g.counters, &g.pixelTable, &g.sceneVerts, &g.sceneTris,
+                      &g.srcNodes, &g.srcWoop, &g.srcIdx, &g.layoutScratch};
     for (DevBuf* b : bufs) b->release();
+    for (int i = 0; i < Context::kAsyncSlots; i++) {
+        g.async[i].rays.release(); g.async[i].results.release();
+        cudaEventDestroy(g.async[i].evIn); cudaEventDestroy(g.async[i].evKa); cudaEventDestroy(g.async[i].evKb); cudaEventDestroy(g.async[i].evOut);
+    }
     cudaEventDestroy(g.evA); cudaEventDestroy(g.evB);
     for (int i = 0; i < 8; i++) cudaEventDestroy(g.userEv[i]);
     for (int i = 0; i < Context::kMaxChunks; i++) { cudaEventDestroy(g.evIn[i]); cudaEventDestroy(g.evKa[i]); cudaEventDestroy(g.evKb[i]); }
@@ -599,6 +619,82 @@ int nt_trace_batch(const float* rays, int32_t* results, int numRays, int needClo
     float ms = 0.0f;
     NT_CUDA(cudaEventElapsedTime(&ms, g.evA, g.evB));
     if (outSeconds) *outSeconds = ms * 1.0e-3f;
+    return 0;
+}
+
+// Asynchronous form of nt_trace_batch for a host loop that keeps several independent batches in flight (the batches of a
+// frame are independent once the primary results exist).  Rays in pinned host memory are DMA'd into the slot's device
+// staging on the copy-in stream, the kernel runs on the compute stream, results go back by DMA on the copy-out stream:
+// with >= 2 slots the H2D copy of batch i+1, the traversal of batch i and the D2H copy of batch i-1 overlap, so the
+// steady state is bound by the larger PCIe direction (32 B/ray in) instead of the sum of the three stages.
+int nt_trace_batch_async(const float* rays, int32_t* results, int numRays, int needClosestHit, int slot)
+{
+    std::lock_guard<std::mutex> lock(g_mutex);
+    if (require_init()) return 1;
+    if (slot < 0 || slot >= Context::kAsyncSlots) { set_error("ntrace_b200: async slot out of range"); return 1; }
+    Context::AsyncSlot& s = g.async[slot];
+    if (s.busy) { set_error("ntrace_b200: async slot still in flight; call nt_trace_wait first"); return 1; }
+    if (numRays <= 0 || !rays || !results) { set_error("ntrace_b200: invalid ray batch"); return 1; }
+    if (!g.haveBVH) { set_error("CudaBVHTracer: No BVH!"); return 1; }
+    if (g.bvhLayout != g.kernelLayout) { set_error("CudaBVHTracer: Incorrect BVH layout!"); return 1; }
+    if (ensure_traversal_form()) return 1;
+    const bool raysDev = is_device_ptr(rays), resDev = is_device_ptr(results);
+    if ((!raysDev && !mapped_device_ptr(rays)) || (!resDev && !mapped_device_ptr(results))) {
+        set_error("ntrace_b200: asynchronous submission needs device or pinned (page-locked) host buffers");
+        return 1;
+    }
+    static const bool zeroCopyResults = [] { const char* e = getenv("NT_ASYNC_RESULTS"); return e && strcmp(e, "zc") == 0; }();
+    const float4* dRays = (const float4*)rays;
+    if (!raysDev) {
+        NT_CUDA(s.rays.reserve((size_t)numRays * 32));
+        NT_CUDA(cudaMemcpyAsync(s.rays.p, rays, (size_t)numRays * 32, cudaMemcpyHostToDevice, g.sIn));
+        NT_CUDA(cudaEventRecord(s.evIn, g.sIn));
+        NT_CUDA(cudaStreamWaitEvent(g.stream, s.evIn, 0));
+        dRays = s.rays.as<float4>();
+    }
+    int4* dRes = (int4*)results;
+    s.copyOut = false;
+    if (!resDev) {
+        if (zeroCopyResults) dRes = (int4*)mapped_device_ptr(results);
+        else { NT_CUDA(s.results.reserve((size_t)numRays * 16)); dRes = s.results.as<int4>(); s.copyOut = true; }
+    }
+    TraceLaunch a;
+    a.kernel = g.kernel; a.layout = g.basic ? (int)Layout_Compact : g.kernelLayout; a.anyHit = needClosestHit ? 0 : 1;
+    a.nodes = g.nodes.as<float4>(); a.woop = g.woop.as<float4>(); a.triIndices = g.triIndex.as<int>();
+    a.numSMs = g.numSMs; a.stream = g.stream;
+    a.numRays = numRays; a.rays = dRays; a.results = dRes;
+    a.warpCounter = g.counters.as<int>() + 32 + slot;
+    NT_CUDA(cudaMemsetAsync(a.warpCounter, 0, sizeof(int), g.stream));
+    NT_CUDA(cudaEventRecord(s.evKa, g.stream));
+    int launches = 0;
+    NT_CUDA(launch_trace(a, &launches));
+    g.launches += launches;
+    NT_CUDA(cudaEventRecord(s.evKb, g.stream));
+    if (s.copyOut) {
+        NT_CUDA(cudaStreamWaitEvent(g.sOut, s.evKb, 0));
+        NT_CUDA(cudaMemcpyAsync(results, dRes, (size_t)numRays * 16, cudaMemcpyDeviceToHost, g.sOut));
+        NT_CUDA(cudaEventRecord(s.evOut, g.sOut));
+    }
+    s.busy = true;
+    return 0;
+}
+
+int nt_trace_wait(int slot, float* outSeconds)
+{
+    std::lock_guard<std::mutex> lock(g_mutex);
+    if (outSeconds) *outSeconds = 0.0f;
+    if (require_init()) return 1;
+    if (slot < 0 || slot >= Context::kAsyncSlots) { set_error("ntrace_b200: async slot out of range"); return 1; }
+    Context::AsyncSlot& s = g.async[slot];
+    if (!s.busy) return 0;
+    s.busy = false;
+    if (s.copyOut) {
+        NT_CUDA(cudaEventSynchronize(s.evOut));
+        NT_CUDA(cudaStreamWaitEvent(g.stream, s.evOut, 0));     // later work / events on the compute stream order after the copy-out
+    } else NT_CUDA(cudaEventSynchronize(s.evKb));
+    float ms = 0.0f;
+    NT_CUDA(cudaEventElapsedTime(&ms, s.evKa, s.evKb));
+    if (outSeconds) *outSeconds = ms * 1.0e-3f;                 // kernel time only, like nt_trace_batch
     return 0;
 }
 

@@ -194,3 +194,51 @@ def test_raygen_ao_matches_oracle(gpu_host, orc, small_scene):
     assert np.array_equal(sec.getSlotToIDBuffer().cpu().numpy(), a)
     hits = gpu_host.capi.count_hits(prim.getResultBuffer(), prim.getSize())
     assert hits == orc.count_hits(prim.results_host())
+
+
+def test_async_submission_matches_synchronous_calls(gpu_host, orc, small_scene):
+    """nt_trace_batch_async / nt_trace_wait: several batches in flight give exactly the results of one synchronous call each."""
+    import torch
+    from ntrace_b200 import capi
+    verts, tris, cpu, (nodes, woop, idx) = small_scene
+    tracer = gpu_host.CudaBVHTracer()
+    tracer.setKernel("b200_persistent_speculative_while_while")
+    tracer.setBVH(gpu_host.CudaBVH(nodes, woop, idx))
+    cam = camera.named_camera("conference")
+    base, _, _ = orc.raygen_primary(cam.position, camera.nscreen_to_world(cam, 256, 192), 256, 192, cam.far)
+    rng = np.random.default_rng(1)
+    batches = []
+    for k in range(7):                                            # more batches than slots, ragged sizes
+        n = int(rng.integers(1000, len(base)))
+        r = base[rng.permutation(len(base))[:n]].copy()
+        batches.append((r, k % 2 == 0))
+    want = [orc.compact_trace(nodes, woop, idx, r, closest) for r, closest in batches]
+    pinned_in = [torch.from_numpy(r).pin_memory() for r, _ in batches]
+    pinned_out = [torch.zeros((len(r), 4), dtype=torch.int32).pin_memory() for r, _ in batches]
+    nslot = capi.ASYNC_SLOTS
+    for i, (r, closest) in enumerate(batches):
+        s = i % nslot
+        capi.trace_wait(s)
+        capi.trace_batch_async(pinned_in[i], pinned_out[i], len(r), closest, s)
+    secs = [capi.trace_wait(s) for s in range(nslot)]
+    assert all(x > 0 for x in secs)
+    for (r, closest), out, w in zip(batches, pinned_out, want):
+        got = out.numpy()
+        if closest:
+            _check_closest(got, w)
+        else:
+            assert ((got[:, 0] >= 0) == (w[:, 0] >= 0)).mean() >= 0.9999
+    # device buffers go straight to the kernel
+    d_in = torch.from_numpy(batches[0][0]).cuda(); d_out = torch.zeros((len(batches[0][0]), 4), dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()
+    capi.trace_batch_async(d_in, d_out, len(d_in), True, 0)
+    with pytest.raises(capi.NtError, match="still in flight"):
+        capi.trace_batch_async(d_in, d_out, len(d_in), True, 0)
+    capi.trace_wait(0)
+    _check_closest(d_out.cpu().numpy(), want[0])
+    assert capi.trace_wait(0) == 0.0                              # idle slot
+    # pageable host memory cannot be used asynchronously; bad slots are refused
+    with pytest.raises(capi.NtError, match="pinned"):
+        capi.trace_batch_async(batches[0][0], np.zeros((len(batches[0][0]), 4), np.int32), len(batches[0][0]), True, 1)
+    with pytest.raises(capi.NtError, match="slot out of range"):
+        capi.trace_batch_async(d_in, d_out, len(d_in), True, 9)
