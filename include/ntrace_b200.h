@@ -52,6 +52,15 @@ const char* nt_last_error(void);
 /* number of this library's kernel launches since nt_init (bench.py's gpu_launches). */
 int64_t nt_launch_count(void);
 
+/* Memory (reference: FW::Buffer over cuMemAlloc / cuMemAllocHost / cuMemcpy*, src/framework/gpu/Buffer.cpp:383-520):
+ * the C++ host above this ABI (ntrace_b200/host_cpp) keeps its FW::Buffer mirrors through these calls and links no
+ * CUDA library itself.  nt_memcpy takes any mix of host / device pointers and returns when the copy is complete. */
+int nt_mem_alloc(size_t bytes, void** outDevicePtr);
+int nt_mem_free(void* devicePtr);
+int nt_mem_alloc_host(size_t bytes, void** outHostPtr);      /* page-locked, device-mapped */
+int nt_mem_free_host(void* hostPtr);
+int nt_memcpy(void* dst, const void* src, size_t bytes);
+int nt_memset(void* devicePtr, int value, size_t bytes);
 /* CUDA-event timing on the library's stream (reference: CudaKernel::launchTimed brackets launches with
  * cuEventRecord / cuEventElapsedTime, src/framework/gpu/CudaKernel.cpp:188-221).  slot in [0, 8). */
 int nt_event_record(int slot);

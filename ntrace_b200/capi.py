@@ -24,6 +24,7 @@ BUILDER_HLBVH = 1
 # every symbol include/ntrace_b200.h declares (checked by tests/test_abi.py)
 EXPORTS = [
     "nt_init", "nt_shutdown", "nt_last_error", "nt_launch_count",
+    "nt_mem_alloc", "nt_mem_free", "nt_mem_alloc_host", "nt_mem_free_host", "nt_memcpy", "nt_memset",
     "nt_event_record", "nt_event_elapsed", "nt_set_deferred", "nt_synchronize",
     "nt_set_kernel", "nt_desired_layout", "nt_kernel_config",
     "nt_bvh_upload", "nt_bvh_alloc", "nt_bvh_build", "nt_bvh_set_collapse", "nt_bvh_convert", "nt_bvh_sizes", "nt_bvh_download",

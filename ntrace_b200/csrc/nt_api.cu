@@ -291,6 +291,62 @@ const char* nt_last_error(void) { return t_error.c_str(); }
 
 int64_t nt_launch_count(void) { return g.launches; }
 
+// ---- memory: what FW::Buffer needs from the CUDA runtime, so that a host above this ABI links no CUDA library itself
+int nt_mem_alloc(size_t bytes, void** outDevicePtr)
+{
+    std::lock_guard<std::mutex> lock(g_mutex);
+    if (require_init()) return 1;
+    if (!outDevicePtr) { set_error("ntrace_b200: null output pointer"); return 1; }
+    *outDevicePtr = nullptr;
+    if (bytes == 0) return 0;
+    NT_CUDA(cudaMalloc(outDevicePtr, bytes));
+    return 0;
+}
+int nt_mem_free(void* devicePtr)
+{
+    std::lock_guard<std::mutex> lock(g_mutex);
+    if (require_init()) return 1;
+    if (devicePtr) { NT_CUDA(cudaStreamSynchronize(g.stream)); NT_CUDA(cudaFree(devicePtr)); }
+    return 0;
+}
+int nt_mem_alloc_host(size_t bytes, void** outHostPtr)
+{
+    std::lock_guard<std::mutex> lock(g_mutex);
+    if (require_init()) return 1;
+    if (!outHostPtr) { set_error("ntrace_b200: null output pointer"); return 1; }
+    *outHostPtr = nullptr;
+    if (bytes == 0) return 0;
+    NT_CUDA(cudaHostAlloc(outHostPtr, bytes, cudaHostAllocPortable | cudaHostAllocMapped));
+    return 0;
+}
+int nt_mem_free_host(void* hostPtr)
+{
+    std::lock_guard<std::mutex> lock(g_mutex);
+    if (require_init()) return 1;
+    if (hostPtr) { NT_CUDA(cudaStreamSynchronize(g.stream)); NT_CUDA(cudaFreeHost(hostPtr)); }
+    return 0;
+}
+int nt_memcpy(void* dst, const void* src, size_t bytes)
+{
+    std::lock_guard<std::mutex> lock(g_mutex);
+    if (require_init()) return 1;
+    if (bytes == 0) return 0;
+    if (!dst || !src) { set_error("ntrace_b200: null pointer in nt_memcpy"); return 1; }
+    NT_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, g.stream));
+    NT_CUDA(cudaStreamSynchronize(g.stream));
+    return 0;
+}
+int nt_memset(void* devicePtr, int value, size_t bytes)
+{
+    std::lock_guard<std::mutex> lock(g_mutex);
+    if (require_init()) return 1;
+    if (bytes == 0) return 0;
+    if (!devicePtr) { set_error("ntrace_b200: null pointer in nt_memset"); return 1; }
+    NT_CUDA(cudaMemsetAsync(devicePtr, value, bytes, g.stream));
+    NT_CUDA(cudaStreamSynchronize(g.stream));
+    return 0;
+}
+
 int nt_event_record(int slot)
 {
     std::lock_guard<std::mutex> lock(g_mutex);

@@ -1,0 +1,68 @@
+// FW::CudaVirtualTracer / FW::CudaBVHTracer — the tracer object Renderer drives.
+// Reference: src/rt/cuda/CudaVirtualTracer.hpp:11-26 (interface), src/rt/cuda/CudaBVHTracer.cpp:52-84 (setKernel +
+// queryConfig), :88-168 (traceBatch: empty batch -> 0, "No BVH!", "Incorrect BVH layout!", GPU seconds around the kernel).
+#pragma once
+#include "ntrace/CudaBVH.hpp"
+#include "ntrace/RayBuffer.hpp"
+
+namespace FW
+{
+struct KernelConfig { int bvhLayout, blockWidth, blockHeight, usePersistentThreads; };    // CudaTracerKernels.hpp:69-75
+
+class CudaVirtualTracer
+{
+public:
+    virtual ~CudaVirtualTracer() {}
+    virtual void setKernel(const String& name) = 0;
+    virtual BVHLayout getDesiredBVHLayout() const = 0;
+    virtual void setBVH(CudaAS* bvh) = 0;
+    virtual void setScene(Scene* scene) = 0;
+    virtual F32 traceBatch(RayBuffer& rays) = 0;                     // GPU seconds
+};
+
+class CudaBVHTracer : public CudaVirtualTracer
+{
+public:
+    CudaBVHTracer() : m_bvh(NULL), m_scene(NULL) { setKernel("b200_persistent_speculative_while_while"); }
+
+    virtual void setKernel(const String& name)
+    {
+        if (name == m_kernelName) return;
+        ntCheck(nt_set_kernel(name.c_str()));
+        m_kernelName = name;
+        int32_t c[4];
+        ntCheck(nt_kernel_config(c));
+        m_kernelConfig.bvhLayout = c[0]; m_kernelConfig.blockWidth = c[1]; m_kernelConfig.blockHeight = c[2]; m_kernelConfig.usePersistentThreads = c[3];
+    }
+    virtual BVHLayout getDesiredBVHLayout() const { return (BVHLayout)m_kernelConfig.bvhLayout; }
+    const KernelConfig& getKernelConfig() const { return m_kernelConfig; }
+
+    virtual void setBVH(CudaAS* as)
+    {
+        m_bvh = as;
+        CudaBVH* bvh = dynamic_cast<CudaBVH*>(as);
+        if (!as || (bvh && bvh->isResident())) return;           // GPU-built: already inside the library
+        Buffer& n = as->getNodeBuffer(); Buffer& w = as->getTriWoopBuffer(); Buffer& i = as->getTriIndexBuffer();
+        ntCheck(nt_bvh_upload((int)as->getLayout(), n.getPtr(), (size_t)n.getSize(), w.getPtr(), (size_t)w.getSize(),
+                              (const int32_t*)i.getPtr(), (size_t)i.getSize()));
+    }
+    virtual void setScene(Scene* scene) { m_scene = scene; }
+
+    virtual F32 traceBatch(RayBuffer& rays)
+    {
+        if (!rays.getSize()) return 0.0f;                          // CudaBVHTracer.cpp:92-94
+        if (!m_bvh) fail("CudaBVHTracer: No BVH!");
+        if (m_bvh->getLayout() != getDesiredBVHLayout()) fail("CudaBVHTracer: Incorrect BVH layout!");
+        float sec = 0.0f;
+        ntCheck(nt_trace_batch((const float*)rays.getRayBuffer().getCudaPtr(), (int32_t*)rays.getResultBuffer().getMutableCudaPtrDiscard(),
+                               rays.getSize(), rays.getNeedClosestHit() ? 1 : 0, &sec));
+        return sec;
+    }
+
+private:
+    CudaAS* m_bvh;
+    Scene* m_scene;
+    String m_kernelName;
+    KernelConfig m_kernelConfig;
+};
+}

@@ -1,0 +1,137 @@
+// FW::Renderer — the frame / batch loop of the reference renderer, restricted to the tracing path (no display, no shading).
+// Reference: src/rt/cuda/Renderer.hpp:44-190, Renderer.cpp:134-160 (setParams), :168-232 (getCudaBVH incl. the bvhcache file),
+// :405-579 (beginFrame / nextBatch / traceBatch), :676-710 (getTotalNumRays).
+#pragma once
+#include "ntrace/CameraControls.hpp"
+#include "ntrace/CudaBVHTracer.hpp"
+#include "ntrace/Environment.hpp"
+#include "ntrace/RayGen.hpp"
+#include <fstream>
+#include <memory>
+
+namespace FW
+{
+class Renderer
+{
+public:
+    enum RayType { RayType_Primary = 0, RayType_AO, RayType_Diffuse, RayType_Max };
+
+    struct Params
+    {
+        String kernelName; RayType rayType; F32 aoRadius; S32 numSamples; bool sortSecondary;
+        Params() : kernelName("b200_persistent_speculative_while_while"), rayType(RayType_Primary), aoRadius(5.0f), numSamples(32), sortSecondary(false) {}
+    };
+
+    // the seed used when Raygen.random is false: the reference hashes Random(0).getU32() (a RANROT value); every parity
+    // check of this repo uses this constant on both sides instead
+    enum { FixedSecondarySeed = 0x9E3779B9 };
+
+    Renderer() : m_raygen(1 << 20), m_scene(NULL), m_cameraFar(0.0f), m_newBatch(true), m_batchRays(NULL), m_batchStart(0)   // Renderer.cpp:45
+    {
+        m_cudaTracer.reset(new CudaBVHTracer());
+        m_builder = "HLBVH";
+        Environment::GetSingleton()->GetStringValue("Renderer.builder", m_builder);
+        m_cachePath = "bvhcache";
+    }
+
+    void setScene(Scene* scene) { m_scene = scene; m_accelStruct.reset(); m_cudaTracer->setScene(scene); }
+    Scene* getScene() const { return m_scene; }
+    void setParams(const Params& p) { m_params = p; m_cudaTracer->setKernel(p.kernelName); }
+    const Params& getParams() const { return m_params; }
+    void setHLBVHParams(const HLBVHParams& p) { m_hlbvh = p; m_accelStruct.reset(); }
+    void setCudaBVH(CudaBVH* bvh) { m_accelStruct.reset(bvh); }           // takes ownership: a prebuilt / deserialised BVH
+    CudaBVHTracer& getCudaTracer() { return *m_cudaTracer; }
+    RayBuffer& getPrimaryRays() { return m_primaryRays; }
+
+    // Renderer.cpp:168-232.  GPU builders only (the CPU SAH / Split builders are the oracle's business); a BVH whose cache
+    // file exists is loaded from it, a freshly built one is written when Renderer.cacheDataStructure is set.
+    CudaAS* getCudaBVH()
+    {
+        BVHLayout layout = m_cudaTracer->getDesiredBVHLayout();
+        if (m_accelStruct && m_accelStruct->getLayout() == layout) return m_accelStruct.get();
+        if (!m_scene) fail("Renderer: no scene");
+        if (m_builder != "HLBVH" && m_builder != "LBVH") fail("Unsupported BVH builder %s (this host builds HLBVH | LBVH on the GPU)", m_builder.c_str());
+        if (layout != BVHLayout_Compact) fail("HLBVHBuilder output is BVHLayout_Compact only (HLBVHBuilder.cpp:33)");
+        bool cache = false;
+        Environment::GetSingleton()->GetBoolValue("Renderer.cacheDataStructure", cache);
+        String cacheFile = m_cacheFileOverride;
+        if (cache && !cacheFile.empty()) {
+            std::ifstream in(cacheFile.c_str(), std::ios::binary);
+            if (in) { m_accelStruct.reset(new CudaBVH(in)); if (m_accelStruct->getLayout() == layout) return m_accelStruct.get(); }
+        }
+        HLBVHParams p = m_hlbvh;
+        if (m_builder == "LBVH") { p.hlbvh = false; p.hlbvhBits = 10; }
+        m_accelStruct.reset(new HLBVHBuilder(m_scene, p));             // Renderer.cpp:201-209
+        if (cache && !cacheFile.empty()) { std::ofstream out(cacheFile.c_str(), std::ios::binary); if (out) m_accelStruct->serialize(out); }
+        return m_accelStruct.get();
+    }
+    // reference naming is "bvhcache/<hash of scene + builder + layout>.dat" (Renderer.cpp:173-178); the file is chosen by the caller here
+    void setCacheFile(const String& path) { m_cacheFileOverride = path; }
+
+    void beginFrame(const CameraControls& camera, int w, int h)           // Renderer.cpp:405-500 without GL
+    {
+        m_cudaTracer->setBVH(getCudaBVH());
+        m_raygen.primary(m_primaryRays, camera.getPosition(), camera.getNScreenToWorld(w, h), w, h, camera.getFar(), 0);
+        if (m_params.rayType != RayType_Primary) m_cudaTracer->traceBatch(m_primaryRays);     // :481-484
+        m_cameraFar = camera.getFar();
+        m_newBatch = true;
+        m_batchRays = NULL;
+        m_batchStart = 0;
+    }
+
+    bool nextBatch()                                                        // Renderer.cpp:504-566
+    {
+        if (m_batchRays) m_batchStart += m_batchRays->getSize();
+        m_batchRays = NULL;
+        switch (m_params.rayType) {
+        case RayType_Primary:
+            if (!m_newBatch) return false;
+            m_newBatch = false;
+            m_batchRays = &m_primaryRays;
+            break;
+        case RayType_AO:
+            if (!m_raygen.ao(m_secondaryRays, m_primaryRays, *m_scene, m_params.numSamples, m_params.aoRadius, m_newBatch, FixedSecondarySeed)) return false;
+            m_batchRays = &m_secondaryRays;
+            break;
+        case RayType_Diffuse:
+            if (!m_raygen.ao(m_secondaryRays, m_primaryRays, *m_scene, m_params.numSamples, m_cameraFar, m_newBatch, FixedSecondarySeed)) return false;
+            m_secondaryRays.setNeedClosestHit(true);
+            m_batchRays = &m_secondaryRays;
+            break;
+        default:
+            fail("Renderer: unsupported ray type");
+        }
+        if (m_params.sortSecondary) m_batchRays->mortonSort();             // :561-562 (the reference's condition is a tautology)
+        return true;
+    }
+
+    F32 traceBatch()                                                        // Renderer.cpp:568-579
+    {
+        if (!m_batchRays) fail("Renderer: no batch");
+        return m_cudaTracer->traceBatch(*m_batchRays);
+    }
+    RayBuffer* getBatchRays() { return m_batchRays; }
+
+    S32 getTotalNumRays()                                                   // Renderer.cpp:676-710
+    {
+        if (m_params.rayType == RayType_Primary) return m_primaryRays.getSize();
+        int hits = 0;
+        ntCheck(nt_count_hits((const int32_t*)m_primaryRays.getResultBuffer().getCudaPtr(), m_primaryRays.getSize(), &hits));
+        return hits * m_params.numSamples;
+    }
+
+private:
+    RayGen m_raygen;
+    std::unique_ptr<CudaBVHTracer> m_cudaTracer;
+    std::unique_ptr<CudaBVH> m_accelStruct;
+    Scene* m_scene;
+    Params m_params;
+    HLBVHParams m_hlbvh;
+    String m_builder, m_cachePath, m_cacheFileOverride;
+    RayBuffer m_primaryRays, m_secondaryRays;
+    F32 m_cameraFar;
+    bool m_newBatch;
+    RayBuffer* m_batchRays;
+    S32 m_batchStart;
+};
+}

@@ -1,0 +1,170 @@
+// ntrace_bench — the reference's benchmark mode on the B200 tracing path, in C++ over the C ABI.
+//
+// Mirror of FW::runBenchmark (src/rt/App.cpp:842-1007) with the option plumbing of FW::init (App.cpp:1011-1083): for every
+// kernel x ray type x camera: setParams -> beginFrame -> getTotalNumRays -> while nextBatch(): traceBatch once, then
+// warmupRepeats untimed and measureRepeats timed repeats; per (kernel, ray type) the #SUM_RENDER_TIME / #SUM_RENDER_KRAYS
+// records that the reference's tests/table-tests.sh greps are appended to App.stats (the reference's "Mrays" variable holds
+// Krays/s, App.cpp:969-975: the record keeps that unit, the printed table shows true Mrays/s).
+//
+//   ntrace_bench config.conf -DBenchmark.scene=scene.obj -DBenchmark.camera=<signature>[;<signature>...]
+//                -DRenderer.rayType=primary;AO;diffuse -DRenderer.builder=HLBVH -DBenchmark.kernel=<name>[;<name>...]
+//
+// Keys beyond the reference's: Benchmark.dumpPrefix=<path> writes, for the last camera of every (kernel, ray type), the rays
+// and results of the LAST batch as raw arrays (<path>.<kernel>.<type>.rays / .results) so a test can check them;
+// Benchmark.device=<ordinal>.
+#include "ntrace/NTrace.hpp"
+#include <algorithm>
+#include <cstdlib>
+
+using namespace FW;
+
+static std::vector<std::string> splitList(const std::string& s, const char* seps)
+{
+    std::vector<std::string> out;
+    std::string cur;
+    for (size_t i = 0; i <= s.size(); i++) {
+        bool sep = (i == s.size()) || strchr(seps, s[i]) != NULL;
+        if (sep) { if (!cur.empty()) out.push_back(cur); cur.clear(); }
+        else cur += s[i];
+    }
+    return out;
+}
+
+static const char* namedSignature(const std::string& name)
+{
+    // src/rt/App.cpp:51-58, config.conf:11
+    static const char* table[][2] = {
+        {"conference", "6omr/04j3200bR6Z/0/3ZEAz/x4smy19///c/05frY109Qx7w////m100"},
+        {"fairyforest", "cIxMx/sK/Ty/EFu3z/5m9mWx/YPA5z/8///m007toC10AnAHx///Uy200"},
+        {"sibenik", "ytIa02G35kz1i:ZZ/0//iSay/5W6Ex19///c/05frY109Qx7w////m100"},
+        {"sanmiguel", "Yciwz1oRQmz/Xvsm005CwjHx/b70nx18tVI7005frY108Y/:x/v3/z100"}};
+    for (size_t i = 0; i < sizeof(table) / sizeof(table[0]); i++)
+        if (name == table[i][0]) return table[i][1];
+    return NULL;
+}
+
+static void dumpBuffer(const std::string& path, Buffer& b, S64 bytes)
+{
+    FILE* f = fopen(path.c_str(), "wb");
+    if (!f) fail("Cannot write '%s'", path.c_str());
+    fwrite(b.getPtr(), 1, (size_t)bytes, f);
+    fclose(f);
+}
+
+static void runBenchmark(Environment& env)
+{
+    int device = 0, w = 1024, h = 768, warmupRepeats = 1, measureRepeats = 5, samples = 8;
+    float aoRadius = 5.0f;
+    bool sortRays = true;
+    std::string sceneFile, cameraSpec, kernelSpec = "b200_persistent_speculative_while_while", rayTypeSpec = "primary", ds, statsFile = "stats.log", dumpPrefix;
+    env.GetIntValue("Benchmark.device", device);
+    env.GetIntValue("App.frameWidth", w); env.GetIntValue("App.frameHeight", h);
+    env.GetIntValue("Benchmark.warmupRepeats", warmupRepeats); env.GetIntValue("Benchmark.measureRepeats", measureRepeats);
+    env.GetIntValue("Renderer.samples", samples); env.GetFloatValue("Raygen.aoRadius", aoRadius); env.GetBoolValue("Renderer.sortRays", sortRays);
+    env.GetStringValue("Benchmark.kernel", kernelSpec); env.GetStringValue("Renderer.rayType", rayTypeSpec);
+    env.GetStringValue("App.stats", statsFile); env.GetStringValue("Benchmark.dumpPrefix", dumpPrefix);
+    if (env.GetStringValue("Renderer.dataStructure", ds) && ds != "BVH") fail("Incorrect data structure type!  (only Renderer.dataStructure=BVH is on this path)");
+    if (!env.GetStringValue("Benchmark.scene", sceneFile) || sceneFile.empty()) fail("Benchmark.scene is not set");
+    if (!env.GetStringValue("Benchmark.camera", cameraSpec) || cameraSpec.empty()) fail("Benchmark.camera is empty");
+
+    ntCheck(nt_init(device));
+    std::vector<CameraControls> cameras;
+    std::vector<std::string> camTokens = splitList(cameraSpec, ";");
+    for (size_t i = 0; i < camTokens.size(); i++) {
+        std::string c = camTokens[i];
+        while (!c.empty() && isspace((unsigned char)c[0])) c.erase(0, 1);
+        while (!c.empty() && isspace((unsigned char)c[c.size() - 1])) c.erase(c.size() - 1);
+        if (c.empty()) continue;
+        CameraControls cam;
+        cam.decodeSignature(namedSignature(c) ? namedSignature(c) : c);
+        cameras.push_back(cam);
+    }
+    if (cameras.empty()) fail("Benchmark.camera is empty");
+    std::vector<std::string> kernels = splitList(kernelSpec, ";");
+    std::vector<std::string> rayTypes = splitList(rayTypeSpec, "; ");
+    std::vector<Renderer::RayType> rayTypeIds;
+    for (size_t i = 0; i < rayTypes.size(); i++) {
+        std::string r = rayTypes[i];
+        std::transform(r.begin(), r.end(), r.begin(), ::tolower);
+        if (r == "primary") rayTypeIds.push_back(Renderer::RayType_Primary);
+        else if (r == "ao") rayTypeIds.push_back(Renderer::RayType_AO);
+        else if (r == "diffuse") rayTypeIds.push_back(Renderer::RayType_Diffuse);
+        else fail("Unsupported ray type %s", rayTypes[i].c_str());
+    }
+
+    printf("Running benchmark for \"%s\".\n\n", sceneFile.c_str());
+    std::unique_ptr<Scene> scene(Scene::importMesh(sceneFile));
+    Renderer renderer;
+    renderer.setScene(scene.get());
+    std::string cacheFile;
+    if (env.GetStringValue("Benchmark.cacheFile", cacheFile)) renderer.setCacheFile(cacheFile);
+    int hlbvhBits = 4, leafSize = 8;
+    env.GetIntValue("HLBVH.bits", hlbvhBits); env.GetIntValue("HLBVH.leafSize", leafSize);
+    renderer.setHLBVHParams(HLBVHParams(true, hlbvhBits, leafSize, 0.001f));
+
+    FILE* stats = fopen(statsFile.c_str(), "a");
+    if (!stats) fail("Cannot open stats file '%s'", statsFile.c_str());
+    std::vector<double> results;
+    for (size_t k = 0; k < kernels.size(); k++)
+        for (size_t r = 0; r < rayTypeIds.size(); r++) {
+            long long totalRays = 0;
+            double totalTime = 0.0;
+            for (size_t c = 0; c < cameras.size(); c++) {
+                printf("%s, %s, camera %d...\n", kernels[k].c_str(), rayTypes[r].c_str(), (int)c);
+                Renderer::Params params;
+                params.kernelName = kernels[k]; params.rayType = rayTypeIds[r]; params.numSamples = samples;
+                params.aoRadius = aoRadius; params.sortSecondary = sortRays;
+                renderer.setParams(params);
+                renderer.beginFrame(cameras[c], w, h);
+                totalRays += (long long)renderer.getTotalNumRays() * measureRepeats;
+                RayBuffer* last = NULL;
+                while (renderer.nextBatch()) {
+                    renderer.traceBatch();
+                    for (int i = 0; i < warmupRepeats; i++) renderer.traceBatch();
+                    for (int i = 0; i < measureRepeats; i++) totalTime += renderer.traceBatch();
+                    last = renderer.getBatchRays();
+                }
+                if (!dumpPrefix.empty() && c + 1 == cameras.size() && last) {
+                    std::string base = dumpPrefix + "." + kernels[k] + "." + rayTypes[r];
+                    dumpBuffer(base + ".rays", last->getRayBuffer(), (S64)last->getSize() * 32);
+                    dumpBuffer(base + ".results", last->getResultBuffer(), (S64)last->getSize() * 16);
+                }
+            }
+            double krays = totalTime > 0.0 ? (double)totalRays / totalTime * 1.0e-3 : 0.0;
+            results.push_back(krays);
+            fprintf(stats, "#SUM_RENDER_TIME\n%g\n#SUM_RENDER_KRAYS\n%g\n", totalTime, krays);      // pushStat (Defs.hpp:166-172)
+        }
+    fclose(stats);
+
+    printf("Done.\n\n%-42s", "Kernel");
+    for (size_t r = 0; r < rayTypes.size(); r++) printf("%-14s", rayTypes[r].c_str());
+    printf("  [Mrays/s]\n%-42s", "---");
+    for (size_t r = 0; r < rayTypes.size(); r++) printf("%-14s", "---");
+    printf("\n");
+    for (size_t k = 0; k < kernels.size(); k++) {
+        printf("%-42s", kernels[k].c_str());
+        for (size_t r = 0; r < rayTypes.size(); r++) printf("%-14.2f", results[k * rayTypes.size() + r] * 1.0e-3);
+        printf("\n");
+    }
+    printf("%-42s", "---");
+    for (size_t r = 0; r < rayTypes.size(); r++) printf("%-14s", "---");
+    printf("\n\n");
+    nt_shutdown();
+}
+
+int main(int argc, char** argv)
+{
+    try {
+        Environment env;
+        env.Parse(argc, argv);
+        Environment::SetSingleton(&env);
+        bool benchmark = true;
+        env.GetBoolValue("App.benchmark", benchmark);
+        if (!benchmark) fail("only App.benchmark=true is supported (the interactive GUI is out of scope)");
+        runBenchmark(env);
+    } catch (const std::exception& e) {
+        fprintf(stderr, "ntrace_bench: %s\n", e.what());
+        return 1;
+    }
+    return 0;
+}
