@@ -108,6 +108,12 @@ int nt_bvh_build(int builder, const float* vtxPos, int numVerts,
  * collapse: the tree is emitted down to single triangles and subtrees are folded back into leaves of at most
  * maxLeafSize triangles (0 = leafSize) wherever that does not increase the SAH cost (Platform costs Cn = Ct = 1). */
 int nt_bvh_set_collapse(int mode, int maxLeafSize);
+/* Layout nt_bvh_build emits (NEW): BVHLayout_Compact (4, default; what the reference's HLBVHBuilder emits,
+ * HLBVHBuilder.cpp:33) or BVHLayout_Compact2 (5).  Compact stores inner-child links as 32-bit BYTE offsets, which caps the
+ * node buffer below the EntrypointSentinel 0x76543210 (1.98 GB = 31 M inner nodes); Compact2 stores offset / 16
+ * (createCompact(bvh, 16), CudaBVH.cpp:86,614) and lifts that to 496 M nodes.  Trace a Compact2 BVH with
+ * "kepler_dynamic_fetch" / "b200_persistent_speculative_while_while_compact2". */
+int nt_bvh_set_build_layout(int layout);
 /* Make the resident BVH BVHLayout_Compact (4) or BVHLayout_Compact2 (5) in place: AOS/SOA uploads are replaced by their
  * Compact form (CudaBVH.cpp:579-664 semantics: implicit leaves, terminator-delimited Woop lists), Compact <-> Compact2
  * rescales the inner-child offsets (createCompact's nodeOffsetSizeDiv, CudaBVH.cpp:86,614). */

@@ -27,7 +27,7 @@ EXPORTS = [
     "nt_mem_alloc", "nt_mem_free", "nt_mem_alloc_host", "nt_mem_free_host", "nt_memcpy", "nt_memset",
     "nt_event_record", "nt_event_elapsed", "nt_set_deferred", "nt_synchronize",
     "nt_set_kernel", "nt_desired_layout", "nt_kernel_config",
-    "nt_bvh_upload", "nt_bvh_alloc", "nt_bvh_build", "nt_bvh_set_collapse", "nt_bvh_convert", "nt_bvh_sizes", "nt_bvh_download",
+    "nt_bvh_upload", "nt_bvh_alloc", "nt_bvh_build", "nt_bvh_set_collapse", "nt_bvh_set_build_layout", "nt_bvh_convert", "nt_bvh_sizes", "nt_bvh_download",
     "nt_bvh_device_ptrs", "nt_bvh_build_debug",
     "nt_trace_batch", "nt_trace_batch_async", "nt_trace_wait", "nt_raygen_primary", "nt_raygen_ao", "nt_raygen_shadow", "nt_ray_sort", "nt_count_hits", "nt_tri_normals",
 ]
@@ -155,6 +155,11 @@ def bvh_build(builder: int, verts, tris, bbox_lo, bbox_hi, hlbvh_bits=4, leaf_si
     _check(lib().nt_bvh_build(C.c_int(builder), ptr(verts, np.float32), C.c_int(nv), ptr(tris, np.int32), C.c_int(nt), lo, hi,
                               C.c_int(hlbvh_bits), C.c_int(leaf_size), C.c_float(epsilon), C.byref(sec)))
     return float(sec.value)
+
+
+def bvh_set_build_layout(layout: int):
+    """Layout nt_bvh_build emits: 4 Compact (default) or 5 Compact2 (needed beyond 31 M inner nodes)."""
+    _check(lib().nt_bvh_set_build_layout(C.c_int(layout)))
 
 
 def bvh_convert(layout: int):

@@ -79,6 +79,7 @@ struct Context {
     DevBuf sortedKeys, sortedIdx;
     int builtTris = 0;
     int collapseMode = 0, collapseMaxLeaf = 0;
+    int buildLayout = Layout_Compact;
 
     // staging
     DevBuf stRays, stResults, stA, stB, stC, stD, stE;
@@ -487,6 +488,7 @@ int nt_bvh_build(int builder, const float* vtxPos, int numVerts, const int32_t* 
     BuildParams p;
     p.builder = builder; p.hlbvhBits = hlbvhBits; p.leafSize = leafSize; p.epsilon = epsilon;
     p.collapse = g.collapseMode; p.collapseMaxLeaf = g.collapseMaxLeaf;
+    p.layout = g.buildLayout;
     for (int i = 0; i < 3; i++) { p.lo[i] = bboxLo[i]; p.hi[i] = bboxHi[i]; }
     BuildOutput out;
     out.nodes = &g.nodes; out.woop = &g.woop; out.triIndex = &g.triIndex;
@@ -509,7 +511,7 @@ int nt_bvh_build(int builder, const float* vtxPos, int numVerts, const int32_t* 
     NT_CUDA(cudaEventElapsedTime(&ms, g.evA, g.evB));
     if (outGpuSeconds) *outGpuSeconds = ms * 1.0e-3f;
     g.nodeBytes = out.nodeBytes; g.woopBytes = out.woopBytes; g.idxBytes = out.idxBytes;
-    g.bvhLayout = Layout_Compact;           // HLBVHBuilder output is Compact only (HLBVHBuilder.cpp:33)
+    g.bvhLayout = g.buildLayout;            // the reference's HLBVHBuilder emits Compact only (HLBVHBuilder.cpp:33); Compact2 is new
     g.haveBVH = true;
     g.builtTris = numTris;
     return 0;
@@ -521,6 +523,14 @@ int nt_bvh_set_collapse(int mode, int maxLeafSize)
     if (mode != 0 && mode != 1) { set_error("ntrace_b200: collapse mode must be 0 (reference leaf rule) or 1 (SAH)"); return 1; }
     if (maxLeafSize < 0) { set_error("ntrace_b200: negative maxLeafSize"); return 1; }
     g.collapseMode = mode; g.collapseMaxLeaf = maxLeafSize;
+    return 0;
+}
+
+int nt_bvh_set_build_layout(int layout)
+{
+    std::lock_guard<std::mutex> lock(g_mutex);
+    if (layout != Layout_Compact && layout != Layout_Compact2) { set_error("ntrace_b200: the GPU builder emits BVHLayout_Compact or BVHLayout_Compact2"); return 1; }
+    g.buildLayout = layout;
     return 0;
 }
 

@@ -210,7 +210,7 @@ __global__ void __launch_bounds__(256) pack_kernel(int n, const int* __restrict_
 
 // Final node numbering.  LBVH: gap nodes by scan rank with the root moved to slot 0.  HLBVH: the numTop top-level
 // nodes come first (root = top node 0), gap nodes follow in scan order.
-struct Numbering { int numTop; int rootGap; uint rootRank; };
+struct Numbering { int numTop; int rootGap; uint rootRank; int linkMul; };   // linkMul: inner-child link per node index, 64 (Compact, byte offset) or 4 (Compact2, offset / 16)
 __device__ __forceinline__ int gap_node_id(const Numbering& nb, int g, uint rank)
 {
     if (nb.numTop > 0) return nb.numTop + (int)rank;
@@ -296,10 +296,10 @@ __global__ void __launch_bounds__(256) emit_kernel(int n, const int* __restrict_
     const int par = c.parent[g];
     if (par >= 0) {
         const int pg = par >> 1;
-        c.nodes[(size_t)gap_node_id(c.nb, pg, (uint)c.ex[pg]) * 16 + 12 + (par & 1)] = id * 64;     // byte offset (Compact)
+        c.nodes[(size_t)gap_node_id(c.nb, pg, (uint)c.ex[pg]) * 16 + 12 + (par & 1)] = id * c.nb.linkMul;   // byte offset (Compact) or / 16 (Compact2)
     } else if (par <= -3) {
         const int code = -3 - par;
-        c.nodes[(size_t)(code >> 1) * 16 + 12 + (code & 1)] = id * 64;                               // cluster root under a top-level node
+        c.nodes[(size_t)(code >> 1) * 16 + 12 + (code & 1)] = id * c.nb.linkMul;                               // cluster root under a top-level node
     }
 
     int arrivals = 0;
@@ -427,7 +427,7 @@ constexpr int kTopThreads = 256;
 constexpr int kSmemTasks = 32;      // levels with at most this many tasks bin through shared memory first
 
 struct TopArgs {
-    int C, leafSize;
+    int C, leafSize, linkMul;
     const int* clsStart; const int* clsBoxI;
     int* clsTask[2];          // current / next task of each cluster (-1 = done)
     int* clsBin;              // C * 3
@@ -640,14 +640,14 @@ __global__ void __launch_bounds__(kTopThreads) hlbvh_top_kernel(TopArgs a)
             const float* bx = a.rBoxes + (size_t)t * 12;
             int val = 0, l = 0, r = 0;
             if (cntL > 1) {
-                l = idN * 64;
+                l = idN * a.linkMul;
                 for (int k = 0; k < 6; k++) oBox[(size_t)ofs * 6 + k] = bx[k];
                 oCnt[ofs] = cntL; oId[ofs] = idN;
                 a.topParent[idN] = top_parent_code(tId[t], 0);
                 val = 1;
             }
             if (cntR > 1) {
-                r = (idN + val) * 64;
+                r = (idN + val) * a.linkMul;
                 for (int k = 0; k < 6; k++) oBox[(size_t)(ofs + val) * 6 + k] = bx[6 + k];
                 oCnt[ofs + val] = cntR; oId[ofs + val] = idN + val;
                 a.topParent[idN + val] = top_parent_code(tId[t], 1);
@@ -869,6 +869,7 @@ cudaError_t build_bvh_device(const float* dVerts, int numVerts, const int* dTris
     (void)numVerts;
     int launches = 0;
     cudaError_t e;
+    const int linkMul = (p.layout == Layout_Compact2) ? 4 : 64;
 #define NT_TRY(call) do { e = (call); if (e != cudaSuccess) { *outLaunches = launches; return e; } } while (0)
 
     bool hl = (p.builder != 0) && (p.hlbvhBits != 10);            // HLBVHBuilder.cpp:44-47
@@ -962,7 +963,7 @@ cudaError_t build_bvh_device(const float* dVerts, int numVerts, const int* dTris
         const int grid = numSMs * topBlocksPerSM;
         NT_TRY(sc.blockSum.reserve((size_t)grid * 4));
         TopArgs ta;
-        ta.C = C; ta.leafSize = p.leafSize;
+        ta.C = C; ta.leafSize = p.leafSize; ta.linkMul = linkMul;
         ta.clsStart = sc.clsStart.as<int>(); ta.clsBoxI = sc.clsBox.as<int>();
         ta.clsTask[0] = sc.clsTask0.as<int>(); ta.clsTask[1] = sc.clsTask1.as<int>();
         ta.clsBin = sc.clsBin.as<int>(); ta.clsParent = sc.clsParent.as<int>();
@@ -1026,7 +1027,12 @@ cudaError_t build_bvh_device(const float* dVerts, int numVerts, const int* dTris
     const size_t numTop = hl ? (size_t)hs[5] : 0;
     const size_t numInner = (size_t)(tot & 0xffffffffull) + numTop, numLeaves = (size_t)(tot >> 32);
     if (numInner == 0 || numLeaves == 0) { if (err) *err = "internal error: empty tree"; return cudaErrorUnknown; }
-    if (numInner * 64 >= 0x76543210ull) { if (err) *err = "node buffer exceeds the 32-bit byte-offset range of BVHLayout_Compact"; return cudaErrorInvalidValue; }
+    // links must stay below the EntrypointSentinel 0x76543210 the traversal stack uses (CudaTracerKernels.hpp:36-39)
+    if (numInner * (size_t)linkMul >= 0x76543210ull) {
+        if (err) *err = p.layout == Layout_Compact2 ? "node buffer exceeds the 32-bit offset range of BVHLayout_Compact2"
+                                                    : "node buffer exceeds the 32-bit byte-offset range of BVHLayout_Compact (build into BVHLayout_Compact2: nt_bvh_set_build_layout)";
+        return cudaErrorInvalidValue;
+    }
     out.nodeBytes = numInner * 64;
     out.woopBytes = ((size_t)n * 3 + numLeaves) * 16;
     out.idxBytes = ((size_t)n * 3 + numLeaves) * 4;
@@ -1037,7 +1043,7 @@ cudaError_t build_bvh_device(const float* dVerts, int numVerts, const int* dTris
     ClimbCtx cc;
     cc.nodes = out.nodes->as<int>(); cc.parent = sc.parent.as<int>(); cc.ex = sc.ex.as<u64>(); cc.gapCounters = sc.counters.as<int>();
     cc.topParent = hl ? sc.topParent.as<int>() : nullptr; cc.topCounters = hl ? sc.topCounters.as<int>() : nullptr;
-    cc.nb.numTop = (int)numTop; cc.nb.rootGap = 0; cc.nb.rootRank = 0;
+    cc.nb.numTop = (int)numTop; cc.nb.rootGap = 0; cc.nb.rootRank = 0; cc.nb.linkMul = linkMul;
     if (hl) NT_TRY(cudaMemcpyAsync(out.nodes->p, sc.topNodes.p, numTop * 64, cudaMemcpyDeviceToDevice, stream));
 
     emit_kernel<<<(gaps + 255) / 256, 256, 0, stream>>>(n, sc.nodeS.as<int>(), sc.nodeE.as<int>(), sc.flags.as<uint>(), rootGap,

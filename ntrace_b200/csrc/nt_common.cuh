@@ -86,6 +86,7 @@ struct BuildParams {
     int builder;              // 0 = LBVH, 1 = HLBVH
     int hlbvhBits, leafSize; float epsilon;
     float lo[3], hi[3];
+    int layout = Layout_Compact;   // Layout_Compact (byte offsets, < 1.98 GB of nodes) or Layout_Compact2 (offsets / 16)
     int collapse = 0;         // 0 = reference leaf rule (count <= leafSize), 1 = SAH-guided collapse
     int collapseMaxLeaf = 0;  // largest leaf the collapse may create (0 = leafSize)
 };

@@ -294,3 +294,37 @@ def test_trace_through_a_30_level_chain(gpu_host, orc):
         assert np.array_equal(got[:, 0], ref[:, 0]) and np.array_equal(got[:, 1], ref[:, 1])
         assert (ref[:, 0] >= 0).mean() > 0.3
     tracer.setKernel("b200_persistent_speculative_while_while")
+
+
+def test_builder_emits_compact2_on_request(gpu_host, orc):
+    """nt_bvh_set_build_layout(Compact2): same tree, inner links are offsets / 16 (what lifts the 1.98 GB node limit of Compact)."""
+    from ntrace_b200 import capi
+    verts, tris = scenes.room(40_000, seed=17, wall_frac=0.3)
+    lo, hi = scenes.bbox(verts)
+    scene = gpu_host.Scene(verts, tris)
+    cam = camera.named_camera("conference")
+    rays, _, _ = orc.raygen_primary(cam.position, camera.nscreen_to_world(cam, 256, 192), 256, 192, cam.far)
+    out = {}
+    try:
+        for layout, kernel in ((4, "b200_persistent_speculative_while_while"), (5, "b200_persistent_speculative_while_while_compact2")):
+            for builder, bits in ((capi.BUILDER_LBVH, 10), (capi.BUILDER_HLBVH, 4)):
+                capi.bvh_set_build_layout(layout)
+                capi.bvh_build(builder, scene.vtxPos, scene.triVtxIndex, lo, hi, bits, 8, 0.001)
+                nodes, woop, idx, got_layout = capi.bvh_download()
+                assert got_layout == layout
+                tracer = gpu_host.CudaBVHTracer(); tracer.setKernel(kernel)
+                bvh = gpu_host.CudaBVH(layout=layout); bvh.resident = True
+                tracer.setBVH(bvh)
+                rb = gpu_host.RayBuffer(); rb.setRays(rays)
+                tracer.traceBatch(rb)
+                out[(layout, builder)] = (nodes.reshape(-1, 16), woop, idx, rb.results_host()[:, :2].copy())
+    finally:
+        capi.bvh_set_build_layout(4)
+    for builder in (capi.BUILDER_LBVH, capi.BUILDER_HLBVH):
+        n4, w4, i4, r4 = out[(4, builder)]
+        n5, w5, i5, r5 = out[(5, builder)]
+        assert np.array_equal(w4, w5) and np.array_equal(i4, i5) and np.array_equal(r4, r5)
+        assert np.array_equal(n4[:, :12], n5[:, :12]) and np.array_equal(n4[:, 14:], n5[:, 14:])
+        assert np.array_equal(np.where(n4[:, 12:14] >= 0, n4[:, 12:14] // 16, n4[:, 12:14]), n5[:, 12:14])
+    with pytest.raises(capi.NtError, match="Compact"):
+        capi.bvh_set_build_layout(0)
