@@ -1,0 +1,56 @@
+"""ORACLE — TEST INFRASTRUCTURE ONLY.
+
+ctypes loader for ``oracle/_ref/libref_<kernel>.so``: the reference's OWN traversal kernels
+(``src/rt/kernels/fermi_speculative_while_while.cu``, ``kepler_dynamic_fetch.cu``) compiled for sm_100a from where
+they lie under ``/root/reference`` (``make -C oracle ref_gpu``; shims and the two syntactic patches are listed in
+``oracle/Makefile`` / ``oracle/ref_shim/ref_gpu_trace.cu``).  They run on the GPU box only.
+
+Used by ``tests/test_gpu_reference_kernels.py`` (the B200 kernel against the recompiled reference kernels on the same BVH
+and rays) and by ``bench.py`` to report the recompiled reference's Mrays/s beside the B200 kernel's.  Nothing under
+``ntrace_b200/`` may import this module.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+KERNELS = ("fermi_speculative_while_while", "kepler_dynamic_fetch")
+_libs = {}
+
+
+def lib_path(kernel: str) -> str:
+    return os.path.join(_HERE, "_ref", f"libref_{kernel}.so")
+
+
+def available(kernel: str = KERNELS[0]) -> bool:
+    return os.path.exists(lib_path(kernel))
+
+
+def _lib(kernel: str):
+    if kernel not in _libs:
+        if kernel not in KERNELS or not available(kernel):
+            raise RuntimeError(f"oracle/_ref/libref_{kernel}.so not built (needs /root/reference; run `make -C oracle ref_gpu`)")
+        l = C.CDLL(lib_path(kernel), mode=os.RTLD_LOCAL)
+        l.ref_gpu_error.restype = C.c_char_p
+        _libs[kernel] = l
+    return _libs[kernel]
+
+
+def _dp(t):
+    return C.c_void_p(int(t.data_ptr()))
+
+
+def trace(kernel: str, rays, results, nodes, woop, tri_index, any_hit: bool = False, desired_warps: int = 0, repeats: int = 1):
+    """Launch the reference kernel on torch CUDA tensors (rays [N,8] f32, results [N,4] i32, Compact / Compact2 BVH buffers).
+    desired_warps = 0 keeps the reference's own launch size (CudaBVHTracer.cpp:151-156: one warp per 32 rays, or the hard-coded
+    720 warps for persistent kernels).  Returns (best milliseconds over `repeats`, KernelConfig as a dict)."""
+    import torch
+    torch.cuda.synchronize()
+    ms = C.c_float(0.0)
+    cfg = (C.c_int * 4)()
+    rc = _lib(kernel).ref_gpu_trace(_dp(rays), _dp(results), C.c_int(int(rays.shape[0])), C.c_int(1 if any_hit else 0), _dp(nodes), _dp(woop), _dp(tri_index),
+                                    C.c_int(desired_warps), C.c_int(repeats), C.byref(ms), cfg)
+    if rc != 0:
+        raise RuntimeError("reference kernel failed: " + _lib(kernel).ref_gpu_error().decode())
+    return float(ms.value), dict(bvhLayout=cfg[0], blockWidth=cfg[1], blockHeight=cfg[2], usePersistentThreads=cfg[3])
