@@ -333,6 +333,7 @@ def run_b200(args):
             stride = max(1, traced[k] // 500_000)
             samples.append((k, torch.cat([b[1][::stride] for b in batches if b[0] == k]).cpu().numpy(), closest))
         cpu = cpu_baseline_leg(verts, tris, cam, args, gpu_bvh=capi.bvh_download()[:3], sample_batches=samples)
+        ref_gpu_rows = reference_gpu_leg(torch, capi, batches)
         # algorithmic bytes of one step = sum over ray types of mean B_ray (oracle counters on the
         # GPU-built BVH, ~500K-ray strided sample per type) x rays traced of that type
         alg_bytes_step = sum(cpu["bytes_per_ray"][k] * traced[k] for k in traced)
@@ -367,6 +368,7 @@ def run_b200(args):
                                  "so DRAM traffic is far below the algorithmic bytes and frac can exceed 1 (see profiles/)",
                          "bytes_per_ray": cpu["bytes_per_ray"]},
             "cpu_baseline": cpu["baseline"],
+            "reference_gpu": ref_gpu_rows,
         }
         print(json.dumps(out), flush=True)
     if world > 1:
@@ -410,6 +412,44 @@ def cpu_baseline_leg(verts, tris, cam, args, gpu_bvh=None, sample_batches=None):
                           + ", ".join(f"{len(r)} {n}" for n, r, _ in sample_batches) + " rays",
                 "build_s_1thread": build_s, "build_mtris_1thread": len(tris) / build_s * 1e-6, "splitbvh_sah": st.sah}
     return {"baseline": baseline, "bytes_per_ray": bpr}
+
+
+def reference_gpu_leg(torch, capi, batches):
+    """Baseline beside the CPU one: the reference's OWN traversal kernels recompiled for sm_100a (oracle/ref_gpu.py,
+    test infrastructure) on the bench's BVH and on the first batch of each ray type, kernel time only.  `as_shipped` is the
+    launch the reference's host would do (fermi: one thread per ray; kepler: its hard-coded 720 persistent warps),
+    `resized_launch` gives the persistent kernel 148 SMs x {16..64} warps with its code untouched.  None when the
+    recompiled kernels are not present."""
+    try:
+        from oracle import ref_gpu
+        if not all(ref_gpu.available(k) for k in ref_gpu.KERNELS):
+            return None
+        first = {}
+        for name, rays, n, closest in batches:
+            first.setdefault(name, (rays, n, closest))
+        sms = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
+        rows = {"note": "reference kernels (src/rt/kernels/*.cu) compiled unmodified for sm_100a with the reference's -use_fast_math; same BVH, first batch of each ray type; Mrays/s = rays traced / kernel time"}
+        for kernel, layout in (("fermi_speculative_while_while", 4), ("kepler_dynamic_fetch", 5)):
+            capi.bvh_convert(layout)
+            nodes, woop, idx, _ = capi.bvh_download()
+            d = [torch.from_numpy(a).cuda() for a in (nodes, woop, idx)]
+            row = {}
+            for name, (rays, n, closest) in first.items():
+                res = torch.zeros((n, 4), dtype=torch.int32, device="cuda")
+                ms, cfg = ref_gpu.trace(kernel, rays[:n], res, d[0], d[1], d[2], any_hit=not closest, repeats=5)
+                row[name + "_as_shipped"] = n / ms * 1e-3
+                if cfg["usePersistentThreads"]:
+                    row[name + "_resized_launch"] = max(n / ref_gpu.trace(kernel, rays[:n], res, d[0], d[1], d[2], any_hit=not closest,
+                                                                          desired_warps=sms * w, repeats=3)[0] * 1e-3 for w in (16, 32, 48, 64))
+            rows[kernel] = row
+        capi.bvh_convert(4)
+        return rows
+    except Exception as e:                       # a baseline leg must never take the bench line down
+        try:
+            capi.bvh_convert(4)
+        except Exception:
+            pass
+        return {"error": str(e)}
 
 
 def run_reference(args):

@@ -41,6 +41,57 @@ def _dp(t):
     return C.c_void_p(int(t.data_ptr()))
 
 
+def _raygen_lib(ieee: bool):
+    name = "raygen_ieee" if ieee else "raygen_fast"
+    if name not in _libs:
+        path = os.path.join(_HERE, "_ref", f"libref_{name}.so")
+        if not os.path.exists(path):
+            raise RuntimeError(f"{path} not built (run `make -C oracle ref_gpu`)")
+        l = C.CDLL(path, mode=os.RTLD_LOCAL)
+        l.ref_gpu_error.restype = C.c_char_p
+        _libs[name] = l
+    return _libs[name]
+
+
+def raygen_available() -> bool:
+    return all(os.path.exists(os.path.join(_HERE, "_ref", f"libref_raygen_{v}.so")) for v in ("fast", "ieee"))
+
+
+def _ck(l, rc):
+    if rc != 0:
+        raise RuntimeError("reference kernel failed: " + l.ref_gpu_error().decode())
+
+
+def raygen_primary(rays, id_to_slot, slot_to_id, index_to_pixel, origin, n2w, w, h, max_dist, seed=0, ieee=True):
+    """rayGenPrimaryKernel (RayGenKernels.cu:77-125) on torch CUDA tensors; n2w = 4x4 row-major numpy."""
+    import numpy as np
+    import torch
+    torch.cuda.synchronize()
+    l = _raygen_lib(ieee)
+    o = (C.c_float * 3)(*[float(v) for v in origin])
+    m = (C.c_float * 16)(*[float(v) for v in np.asarray(n2w, dtype=np.float32).reshape(-1)])
+    _ck(l, l.ref_raygen_primary(_dp(rays), _dp(id_to_slot), _dp(slot_to_id), _dp(index_to_pixel), o, m, C.c_int(w), C.c_int(h), C.c_float(max_dist), C.c_uint(seed)))
+
+
+def raygen_ao(out_rays, out_i2s, out_s2i, in_rays, in_results, normals, first, count, samples, max_dist, seed, ieee=True):
+    """rayGenAOKernel (RayGenKernels.cu:129-236)."""
+    import torch
+    torch.cuda.synchronize()
+    l = _raygen_lib(ieee)
+    _ck(l, l.ref_raygen_ao(_dp(out_rays), _dp(out_i2s), _dp(out_s2i), _dp(in_rays), _dp(in_results), _dp(normals), C.c_int(first), C.c_int(count),
+                           C.c_int(samples), C.c_float(max_dist), C.c_uint(seed)))
+
+
+def raygen_shadow(out_rays, out_i2s, out_s2i, in_rays, in_results, first, count, samples, light_pos, light_radius, seed, ieee=True):
+    """rayGenShadowKernel (RayGenKernels.cu:240-302)."""
+    import torch
+    torch.cuda.synchronize()
+    l = _raygen_lib(ieee)
+    lp = (C.c_float * 3)(*[float(v) for v in light_pos])
+    _ck(l, l.ref_raygen_shadow(_dp(out_rays), _dp(out_i2s), _dp(out_s2i), _dp(in_rays), _dp(in_results), C.c_int(first), C.c_int(count), C.c_int(samples),
+                               lp, C.c_float(light_radius), C.c_uint(seed)))
+
+
 def trace(kernel: str, rays, results, nodes, woop, tri_index, any_hit: bool = False, desired_warps: int = 0, repeats: int = 1):
     """Launch the reference kernel on torch CUDA tensors (rays [N,8] f32, results [N,4] i32, Compact / Compact2 BVH buffers).
     desired_warps = 0 keeps the reference's own launch size (CudaBVHTracer.cpp:151-156: one warp per 32 rays, or the hard-coded

@@ -100,3 +100,57 @@ def test_b200_kernel_matches_recompiled_reference_kernel(gpu_host, orc, refgpu, 
         assert (want[:, 0] != -7).all(), "the reference kernel did not write every result"
         _compare(mine, want, closest, rb.rays_host(), float(np.linalg.norm(verts.max(0) - verts.min(0))))
     capi.bvh_convert(4)
+
+
+def test_raygen_kernels_match_the_reference_kernels(gpu_host, orc, refgpu, workload):
+    """The B200 ray generators against the reference's rayGenPrimaryKernel / rayGenAOKernel / rayGenShadowKernel compiled for
+    sm_100a: bit-identical to the IEEE build of the same source (no -use_fast_math: the arithmetic this repo and its oracle
+    restate), and equal to rounding to the reference's own -use_fast_math build."""
+    import torch
+    if not refgpu.raygen_available():
+        pytest.skip("libref_raygen_*.so not present")
+    verts, tris, scene, cpu, batches = workload
+    cam = camera.named_camera("conference")
+    w, h = 512, 384
+    n2w = camera.nscreen_to_world(cam, w, h)
+    i2p = torch.from_numpy(orc.pixel_table(w, h)[0]).cuda()                 # PixelTable is pinned against the reference (CPU)
+    for seed in (0, 12345):
+        mine = gpu_host.RayBuffer()
+        gpu_host.RayGen().primary(mine, cam.position, n2w, w, h, cam.far, seed)
+        for ieee in (True, False):
+            rays = torch.zeros((w * h, 8), dtype=torch.float32, device="cuda")
+            a = torch.zeros(w * h, dtype=torch.int32, device="cuda"); b = torch.zeros(w * h, dtype=torch.int32, device="cuda")
+            refgpu.raygen_primary(rays, a, b, i2p, cam.position, n2w, w, h, cam.far, seed, ieee=ieee)
+            assert torch.equal(a, mine.getIDToSlotBuffer()) and torch.equal(b, mine.getSlotToIDBuffer())
+            if ieee:
+                assert torch.equal(rays.view(torch.int32), mine.getRayBuffer().view(torch.int32)), f"primary seed {seed}"
+                assert np.array_equal(rays.cpu().numpy().view(np.int32), orc.raygen_primary(cam.position, n2w, w, h, cam.far, seed)[0].view(np.int32))
+            else:
+                assert torch.allclose(rays, mine.getRayBuffer(), rtol=0, atol=1e-4)     # fast-math division + rsqrt: ~1e-5
+    prim = batches["primary"]
+    n_in, spp, seed = 20_000, 8, gpu_host.FIXED_AO_SEED
+    for max_dist in (5.0, cam.far):
+        out = torch.zeros((n_in * spp, 8), dtype=torch.float32, device="cuda")
+        ia = torch.zeros(n_in * spp, dtype=torch.int32, device="cuda"); ib = torch.zeros_like(ia)
+        capi.raygen_ao(out, ia, ib, prim.getRayBuffer(), prim.getResultBuffer(), scene.triNormal, 1000, n_in, spp, max_dist, seed)
+        for ieee in (True, False):
+            ref_out = torch.zeros_like(out); ra = torch.zeros_like(ia); rb = torch.zeros_like(ia)
+            refgpu.raygen_ao(ref_out, ra, rb, prim.getRayBuffer(), prim.getResultBuffer(), scene.triNormal, 1000, n_in, spp, max_dist, seed, ieee=ieee)
+            assert torch.equal(ra, ia) and torch.equal(rb, ib)
+            assert torch.equal(ref_out[:, [0, 1, 2, 3, 7]], out[:, [0, 1, 2, 3, 7]]) or not ieee            # origins, tmin, tmax
+            if ieee:
+                assert torch.equal(ref_out.view(torch.int32), out.view(torch.int32)), "AO rays differ from the IEEE build of the reference kernel"
+            else:
+                assert torch.allclose(ref_out, out, rtol=1e-4, atol=1e-4)
+    light, radius = (3.0, 12.0, 4.0), 0.75
+    out = torch.zeros((n_in * spp, 8), dtype=torch.float32, device="cuda")
+    ia = torch.zeros(n_in * spp, dtype=torch.int32, device="cuda"); ib = torch.zeros_like(ia)
+    capi.raygen_shadow(out, ia, ib, prim.getRayBuffer(), prim.getResultBuffer(), 500, n_in, spp, light, radius, 777)
+    for ieee in (True, False):
+        ref_out = torch.zeros_like(out); ra = torch.zeros_like(ia); rb = torch.zeros_like(ia)
+        refgpu.raygen_shadow(ref_out, ra, rb, prim.getRayBuffer(), prim.getResultBuffer(), 500, n_in, spp, light, radius, 777, ieee=ieee)
+        assert torch.equal(ra, ia) and torch.equal(rb, ib)
+        if ieee:
+            assert torch.equal(ref_out.view(torch.int32), out.view(torch.int32)), "shadow rays differ from the IEEE build of the reference kernel"
+        else:
+            assert torch.allclose(ref_out, out, rtol=1e-4, atol=1e-4)
