@@ -92,6 +92,54 @@ def raygen_shadow(out_rays, out_i2s, out_s2i, in_rays, in_results, first, count,
                                lp, C.c_float(light_radius), C.c_uint(seed)))
 
 
+def _named_lib(name: str):
+    if name not in _libs:
+        path = os.path.join(_HERE, "_ref", f"libref_{name}.so")
+        if not os.path.exists(path):
+            raise RuntimeError(f"{path} not built (run `make -C oracle ref_gpu`)")
+        l = C.CDLL(path, mode=os.RTLD_LOCAL)
+        l.ref_gpu_error.restype = C.c_char_p
+        _libs[name] = l
+    return _libs[name]
+
+
+def hlbvh_available() -> bool:
+    return all(os.path.exists(os.path.join(_HERE, "_ref", f"libref_hlbvh_{v}.so")) for v in ("fast", "ieee"))
+
+
+def morton(verts, tris, lo, hi, ieee=True):
+    """calcMorton (emitTreeKernel.cu:647-691) on torch CUDA tensors -> uint32 codes per triangle (numpy)."""
+    import numpy as np
+    import torch
+    torch.cuda.synchronize()
+    l = _named_lib("hlbvh_ieee" if ieee else "hlbvh_fast")
+    n = int(tris.shape[0])
+    out = np.zeros(n, dtype=np.uint32)
+    flo = (C.c_float * 3)(*[float(v) for v in lo]); fhi = (C.c_float * 3)(*[float(v) for v in hi])
+    _ck(l, l.ref_morton(_dp(verts), _dp(tris), C.c_int(n), flo, fhi, out.ctypes.data_as(C.c_void_p)))
+    return out
+
+
+def lbvh_build(verts, tris, lo, hi, leaf_size=8, epsilon=0.001, ieee=True):
+    """HLBVHBuilder::buildLBVH with the reference's own kernels -> dict(nodes, woop, tri_index, sorted_keys, sorted_idx,
+    num_nodes, num_leaves, levels); node / leaf numbering depends on the order of atomics, compare in canonical form."""
+    import numpy as np
+    import torch
+    torch.cuda.synchronize()
+    l = _named_lib("hlbvh_ieee" if ieee else "hlbvh_fast")
+    n = int(tris.shape[0])
+    flo = (C.c_float * 3)(*[float(v) for v in lo]); fhi = (C.c_float * 3)(*[float(v) for v in hi])
+    info = (C.c_int * 3)()
+    _ck(l, l.ref_lbvh_build(_dp(verts), _dp(tris), C.c_int(n), flo, fhi, C.c_int(leaf_size), C.c_float(epsilon), info))
+    sizes = (C.c_longlong * 3)()
+    _ck(l, l.ref_build_sizes(sizes))
+    nodes = np.zeros(sizes[0] // 4, dtype=np.int32); woop = np.zeros(sizes[1] // 4, dtype=np.int32); idx = np.zeros(sizes[2] // 4, dtype=np.int32)
+    keys = np.zeros(n, dtype=np.uint32); order = np.zeros(n, dtype=np.int32)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    _ck(l, l.ref_build_download(p(nodes), p(woop), p(idx), p(keys), p(order)))
+    return dict(nodes=nodes, woop=woop, tri_index=idx, sorted_keys=keys, sorted_idx=order, num_nodes=info[0], num_leaves=info[1], levels=info[2])
+
+
 def trace(kernel: str, rays, results, nodes, woop, tri_index, any_hit: bool = False, desired_warps: int = 0, repeats: int = 1):
     """Launch the reference kernel on torch CUDA tensors (rays [N,8] f32, results [N,4] i32, Compact / Compact2 BVH buffers).
     desired_warps = 0 keeps the reference's own launch size (CudaBVHTracer.cpp:151-156: one warp per 32 rays, or the hard-coded

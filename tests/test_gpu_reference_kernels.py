@@ -154,3 +154,47 @@ def test_raygen_kernels_match_the_reference_kernels(gpu_host, orc, refgpu, workl
             assert torch.equal(ref_out.view(torch.int32), out.view(torch.int32)), "shadow rays differ from the IEEE build of the reference kernel"
         else:
             assert torch.allclose(ref_out, out, rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize("scene_name", ["room", "soup_dups", "teapot"])
+@pytest.mark.parametrize("leaf", [8, 1])
+def test_gpu_builder_matches_the_reference_build_kernels(gpu_host, orc, refgpu, scene_name, leaf):
+    """The B200 LBVH build against the reference's own calcMorton / thrust sort / calcWoopKernel / emitTreeKernel / calcAABB
+    run on this GPU (HLBVHBuilder::buildLBVH launch sequence).  IEEE build of the reference source: Morton codes, sorted
+    order, the tree in canonical form, child boxes and Woop rows must all be bit-identical.  The reference's own
+    -use_fast_math build differs only where approximate division moves a centroid across a Morton cell boundary."""
+    if not refgpu.hlbvh_available():
+        pytest.skip("libref_hlbvh_*.so not present")
+    verts, tris = {"room": lambda: scenes.room(50_000, seed=31, wall_frac=0.3), "soup_dups": lambda: scenes.soup_uniform(40_000, seed=9, clustered=True),
+                   "teapot": lambda: scenes.teapot_in_stadium(30_000, seed=3)}[scene_name]()
+    lo, hi = scenes.bbox(verts)
+    scene = gpu_host.Scene(verts, tris)
+    capi.bvh_set_collapse(0, 0)
+    capi.bvh_build(capi.BUILDER_LBVH, scene.vtxPos, scene.triVtxIndex, lo, hi, 10, leaf, 0.001)
+    nodes, woop, idx, _ = capi.bvh_download()
+    keys, order = capi.bvh_build_debug(len(tris))
+    mine = orc.canonical(nodes, woop, idx)
+    # --- IEEE build of the reference kernels: everything identical
+    assert np.array_equal(refgpu.morton(scene.vtxPos, scene.triVtxIndex, lo, hi, ieee=True), orc.morton(verts, tris, lo, hi))
+    r = refgpu.lbvh_build(scene.vtxPos, scene.triVtxIndex, lo, hi, leaf, 0.001, ieee=True)
+    assert np.array_equal(r["sorted_keys"], keys)
+    if len(np.unique(keys)) == len(keys):
+        assert np.array_equal(r["sorted_idx"], order)
+    else:                                                           # thrust's radix sort is stable too: same order within equal keys
+        assert np.array_equal(r["sorted_idx"], order)
+    assert (len(r["nodes"]) // 16, r["num_leaves"]) == (len(nodes) // 16, len(mine.leaf_sizes))
+    ref_c = orc.canonical(r["nodes"], r["woop"], r["tri_index"])
+    assert np.array_equal(ref_c.inner, mine.inner) and np.array_equal(ref_c.leaf_sizes, mine.leaf_sizes) and np.array_equal(ref_c.tris, mine.tris)
+    assert np.array_equal(ref_c.boxes.view(np.int32), mine.boxes.view(np.int32))
+    rw, mw = ref_c.woop.view(np.int32), mine.woop.view(np.int32)
+    same_rows = (rw == mw) | (np.isnan(ref_c.woop) & np.isnan(mine.woop))
+    assert same_rows.all()
+    # --- the reference's own flags (-use_fast_math): Morton codes differ for a handful of centroids on cell boundaries
+    fast = refgpu.morton(scene.vtxPos, scene.triVtxIndex, lo, hi, ieee=False)
+    assert (fast != orc.morton(verts, tris, lo, hi)).mean() <= 2e-3
+    rf = refgpu.lbvh_build(scene.vtxPos, scene.triVtxIndex, lo, hi, leaf, 0.001, ieee=False)
+    cf = orc.canonical(rf["nodes"], rf["woop"], rf["tri_index"])
+    assert sorted(cf.tris.tolist()) == list(range(len(tris)))
+    sah_fast = orc.compact_sah(rf["nodes"], rf["woop"])["sah"]
+    sah_mine = orc.compact_sah(nodes, woop)["sah"]
+    assert abs(sah_fast - sah_mine) <= 0.005 * sah_mine            # north_star: builder SAH within 0.5 % of the reference build
