@@ -10,8 +10,9 @@ Parity status: the reference ships no tests with golden values, so the CPU part 
 restatement (builders, SAH metric, createCompact/Woop, both tracers, Intersect primitives, pixel
 table) is PINNED bit-for-bit against the reference's own sources compiled unmodified
 (``oracle/ref.py``, ``oracle/_ref/libref.so``; ``tests/test_reference_pin.py``).  The restated
-HLBVH builder and ray generators mirror device code that cannot run here: parity UNPINNED for
-those, cross-validated in ``tests/test_oracle_*.py``.
+HLBVH builder and ray generators mirror device code: they are pinned on the GPU box against the
+reference's own kernels compiled for sm_100a (``oracle/ref_gpu.py``,
+``tests/test_gpu_reference_kernels.py``) and cross-validated in ``tests/test_oracle_*.py`` here.
 """
 from __future__ import annotations
 

@@ -1,7 +1,10 @@
-// ORACLE — TEST INFRASTRUCTURE ONLY (see orc_math.hpp header).  Parity UNPINNED: the reference's
-// HLBVH builder is device code (emitTreeKernel.cu: shared memory, warp scans, atomics) and cannot run here, and it has
-// no tests of its own; see tests/test_oracle_lbvh.py for the invariants used instead.  The pieces it shares with the
-// pinned CPU path (SAH metric, Compact node encoding, flat tracer that consumes the result) are pinned (orc_math.hpp).
+// ORACLE — TEST INFRASTRUCTURE ONLY (see orc_math.hpp header).  Parity PINNED ON THE GPU BOX: the reference's
+// HLBVH builder is device code (emitTreeKernel.cu) and cannot run in the build container, but it compiles for sm_100a
+// (oracle/ref_gpu.py, `make -C oracle ref_gpu`) and tests/test_gpu_reference_kernels.py runs it on the B200 beside the
+// product builder: Morton codes, sorted order, LBVH and HLBVH trees (canonical form), child boxes and Woop rows are
+// bit-identical to the IEEE build of the reference kernels; the product builder is in turn bit-identical to this
+// restatement (tests/test_gpu_build.py), which closes the triangle.  In the container (no GPU) this file is constrained by
+// tests/test_oracle_lbvh.py only.
 //
 // CPU restatement of the reference GPU LBVH / HLBVH builder, executed with a *serial
 // schedule* (threads in queue order), which is one of the schedules the reference's

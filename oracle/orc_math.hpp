@@ -8,9 +8,10 @@
 // own CPU sources (SAHBVHBuilder, SplitBVHBuilder, BVHNode SAH, BVH::trace, CudaBVH createCompact /
 // woopifyTri / trace, Intersect::*, PixelTable) compiled unmodified (oracle/Makefile `ref`), and
 // tests/test_reference_pin.py requires bit-identical results from this restatement, live and against
-// frozen fixtures (tests/golden/ref_*).  PINNED: orc_math, orc_bvh, pixel_table.  Still UNPINNED
-// (device-only code in the reference, not buildable here): orc_lbvh (HLBVH kernels) and the rest of
-// orc_raygen; those are cross-validated in tests/test_oracle_*.py instead.
+// frozen fixtures (tests/golden/ref_*).  PINNED on the CPU: orc_math, orc_bvh, pixel_table.  orc_lbvh (HLBVH
+// kernels) and the ray generators of orc_raygen restate DEVICE code: they are pinned on the GPU box, where the
+// reference's own kernels, compiled for sm_100a (oracle/ref_gpu.py), run beside the product kernels
+// (tests/test_gpu_reference_kernels.py); in the container they are cross-validated in tests/test_oracle_*.py.
 //
 // Compile with: -O2 -ffp-contract=off -fno-fast-math  (IEEE fp32, no FMA contraction).
 //

@@ -1,4 +1,4 @@
-// ORACLE — TEST INFRASTRUCTURE ONLY (see orc_math.hpp header).  pixel_table PINNED against the compiled reference (oracle/_ref); ray generation parity unpinned (device code).
+// ORACLE — TEST INFRASTRUCTURE ONLY (see orc_math.hpp header).  pixel_table PINNED against the compiled reference (oracle/_ref, CPU); ray generators PINNED on the GPU box (see orc_raygen.hpp).
 //
 // Ray generation restated on the CPU from:
 //   src/rt/ray/PixelTable.cpp:57-141          index <-> pixel tables

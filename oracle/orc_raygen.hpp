@@ -1,4 +1,4 @@
-// ORACLE — TEST INFRASTRUCTURE ONLY (see orc_math.hpp header).  pixel_table PINNED against the compiled reference (oracle/_ref); ray generation parity unpinned (device code).
+// ORACLE — TEST INFRASTRUCTURE ONLY (see orc_math.hpp header).  pixel_table PINNED against the compiled reference (oracle/_ref, CPU); ray generators PINNED on the GPU box: bit-identical to the IEEE build of the reference's RayGenKernels.cu run on the B200 (tests/test_gpu_reference_kernels.py).
 #pragma once
 #include "orc_bvh.hpp"
 

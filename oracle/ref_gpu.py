@@ -137,7 +137,30 @@ def lbvh_build(verts, tris, lo, hi, leaf_size=8, epsilon=0.001, ieee=True):
     keys = np.zeros(n, dtype=np.uint32); order = np.zeros(n, dtype=np.int32)
     p = lambda a: a.ctypes.data_as(C.c_void_p)
     _ck(l, l.ref_build_download(p(nodes), p(woop), p(idx), p(keys), p(order)))
-    return dict(nodes=nodes, woop=woop, tri_index=idx, sorted_keys=keys, sorted_idx=order, num_nodes=info[0], num_leaves=info[1], levels=info[2])
+    l.ref_build_gpu_ms.restype = C.c_float
+    return dict(nodes=nodes, woop=woop, tri_index=idx, sorted_keys=keys, sorted_idx=order, num_nodes=info[0], num_leaves=info[1], levels=info[2],
+                gpu_ms=float(l.ref_build_gpu_ms()))
+
+
+def hlbvh_build(verts, tris, lo, hi, hlbvh_bits=4, leaf_size=8, epsilon=0.001, ieee=True):
+    """HLBVHBuilder::buildHLBVH with the reference's own kernels (clusters + binned-SAH top level + LBVH below)."""
+    import numpy as np
+    import torch
+    torch.cuda.synchronize()
+    l = _named_lib("hlbvh_ieee" if ieee else "hlbvh_fast")
+    n = int(tris.shape[0])
+    flo = (C.c_float * 3)(*[float(v) for v in lo]); fhi = (C.c_float * 3)(*[float(v) for v in hi])
+    info = (C.c_int * 6)()
+    _ck(l, l.ref_hlbvh_build(_dp(verts), _dp(tris), C.c_int(n), flo, fhi, C.c_int(hlbvh_bits), C.c_int(leaf_size), C.c_float(epsilon), info))
+    sizes = (C.c_longlong * 3)()
+    _ck(l, l.ref_build_sizes(sizes))
+    nodes = np.zeros(sizes[0] // 4, dtype=np.int32); woop = np.zeros(sizes[1] // 4, dtype=np.int32); idx = np.zeros(sizes[2] // 4, dtype=np.int32)
+    keys = np.zeros(n, dtype=np.uint32); order = np.zeros(n, dtype=np.int32)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    _ck(l, l.ref_build_download(p(nodes), p(woop), p(idx), p(keys), p(order)))
+    l.ref_build_gpu_ms.restype = C.c_float
+    return dict(nodes=nodes, woop=woop, tri_index=idx, sorted_keys=keys, sorted_idx=order, num_nodes=info[0], num_leaves=info[1], levels=info[2],
+                num_clusters=info[3], num_top_nodes=info[4], num_lbvh_roots=info[5], gpu_ms=float(l.ref_build_gpu_ms()))
 
 
 def trace(kernel: str, rays, results, nodes, woop, tri_index, any_hit: bool = False, desired_warps: int = 0, repeats: int = 1):
