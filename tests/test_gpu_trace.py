@@ -242,3 +242,40 @@ def test_async_submission_matches_synchronous_calls(gpu_host, orc, small_scene):
         capi.trace_batch_async(batches[0][0], np.zeros((len(batches[0][0]), 4), np.int32), len(batches[0][0]), True, 1)
     with pytest.raises(capi.NtError, match="slot out of range"):
         capi.trace_batch_async(d_in, d_out, len(d_in), True, 9)
+
+
+@pytest.mark.timeout(120)
+def test_non_finite_and_extreme_rays_terminate_and_match_the_cpu_tracer(gpu_host, orc, small_scene):
+    """NaN / Inf / zero-direction / denormal / huge rays: the persistent kernel must terminate and give what the reference's
+    CPU tracer gives on the same buffers (for NaN that is 'no hit': every comparison is false)."""
+    verts, tris, cpu, (nodes, woop, idx) = small_scene
+    rng = np.random.default_rng(4)
+    n = 4096
+    lo, hi = scenes.bbox(verts)
+    o = rng.uniform(lo, hi, (n, 3)).astype(np.float32)
+    d = rng.normal(size=(n, 3)).astype(np.float32)
+    rays = np.concatenate([o, np.zeros((n, 1), np.float32), d, np.full((n, 1), 1e30, np.float32)], axis=1).astype(np.float32)
+    rays[0:64, 4] = np.nan                      # NaN direction component
+    rays[64:128, 0] = np.nan                    # NaN origin
+    rays[128:192, 4:7] = 0.0                    # zero direction
+    rays[192:256, 5] = np.inf                   # infinite direction component
+    rays[256:320, 7] = np.inf                   # tmax = inf
+    rays[320:384, 4:7] *= np.float32(1e-42)     # denormal direction
+    rays[384:448, 0:3] *= np.float32(1e30)      # origin far away
+    rays[448:512, 3] = np.float32(1e30); rays[448:512, 7] = np.float32(-1.0)   # tmin > tmax
+    rays[512:576, 7] = np.nan                   # NaN tmax
+    tracer = gpu_host.CudaBVHTracer()
+    tracer.setBVH(gpu_host.CudaBVH(nodes, woop, idx))
+    for kernel in KERNELS:
+        tracer.setKernel(kernel)
+        for closest in (True, False):
+            rb = gpu_host.RayBuffer(); rb.setRays(rays); rb.setNeedClosestHit(closest)
+            tracer.traceBatch(rb)
+            got = rb.results_host()
+            want = orc.compact_trace(nodes, woop, idx, rays, closest)
+            assert (got[:128, 0] == -1).all()                                   # NaN rays hit nothing
+            if closest:
+                assert (got[:, 0] == want[:, 0]).mean() >= 0.999
+                assert np.array_equal(got[576:, 0], want[576:, 0]) or (got[576:, 0] == want[576:, 0]).mean() >= 0.9999
+            else:
+                assert ((got[:, 0] >= 0) == (want[:, 0] >= 0)).mean() >= 0.999
