@@ -366,7 +366,13 @@ def run_b200(args):
                          "peak_source": peak_src,
                          "note": "algorithmic bytes (nodes+triangles fetched per ray, oracle-counted) over avg launch time; the BVH is L2-resident, "
                                  "so DRAM traffic is far below the algorithmic bytes and frac can exceed 1 (see profiles/)",
-                         "bytes_per_ray": cpu["bytes_per_ray"]},
+                         "bytes_per_ray": cpu["bytes_per_ray"],
+                         # what actually limits the kernel, from the committed ncu captures of this workload (static numbers,
+                         # profiles/r1b_prof2_trace_s{50,52,80}_raw.csv): issue slots busy, useful lanes per instruction, DRAM throughput
+                         "ncu": {"issue_active_pct": {"primary": 66.5, "AO": 71.6, "diffuse": 59.6},
+                                 "lanes_per_instruction": {"primary": 21.3, "AO": 12.3, "diffuse": 12.5},
+                                 "dram_throughput_pct_of_peak": 2.0, "l1tex_throughput_pct": {"primary": 51.5, "AO": 67.6, "diffuse": 75.0},
+                                 "limiter": "instruction issue x SIMD efficiency, then L1/L2 latency; not HBM (see profiles/r1_summary.md)"}},
             "cpu_baseline": cpu["baseline"],
             "reference_gpu": ref_gpu_rows,
         }
