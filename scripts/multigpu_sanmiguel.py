@@ -70,6 +70,26 @@ def main():
         out[f"diffuse_{key}_batches_mrays"] = hits * 32 / float(t[0]) * 1e-6
         out[f"diffuse_{key}_frame_ms"] = float(t[0]) * 1e3
         out["rays_traced"] = traced
+    # the frame's batches dealt out round-robin instead of cutting every batch: rank r generates and traces batches r, r+N, ...
+    # (each a full <= 1 Mi-ray launch, so no rank runs under-filled waves)
+    gen = host.RayGen(1 << 20)
+    new, total_s, i = True, 0.0, 0
+    while True:
+        rb = host.RayBuffer()
+        ok, new = gen.ao(rb, prim, scene, 32, cam.far, new, host.FIXED_AO_SEED)
+        if not ok:
+            break
+        if i % world == rank:
+            rb.setNeedClosestHit(True)
+            tracer.traceBatch(rb)
+            total_s += min(tracer.traceBatch(rb) for _ in range(3))
+        i += 1
+    t = torch.tensor([total_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    out["diffuse_1Mi_batches_round_robin_mrays"] = hits * 32 / float(t[0]) * 1e-6
+    out["diffuse_1Mi_batches_round_robin_frame_ms"] = float(t[0]) * 1e3
+    out["batches_per_frame"] = i
     if rank == 0:
         os.makedirs("gpurun_out", exist_ok=True)
         json.dump(out, open(f"gpurun_out/multigpu_sanmiguel_n{world}.json", "w"), indent=1)
