@@ -73,8 +73,11 @@ int nt_set_deferred(int enabled);
 int nt_synchronize(void);
 
 /* ---- kernel selection: CudaBVHTracer::setKernel + queryConfig (CudaBVHTracer.cpp:52-84) --- */
-/* Names: "b200_persistent_speculative_while_while" (default), "b200_speculative_while_while",
- * and the reference's kernel file names as aliases: "fermi_speculative_while_while" (Compact),
+/* Names: "b200_persistent_speculative_while_while" (default), "b200_speculative_while_while": the triangle test in IEEE
+ * arithmetic, bit-identical to the reference's CPU tracer (CudaBVH::trace, Util.cpp:99-127).  A "_fastmath" suffix
+ * ("b200_persistent_speculative_while_while[_compact2]_fastmath") and the reference's own kernel file names select the
+ * arithmetic nvcc -use_fast_math gives the reference's GPU kernels (contracted FMAs, approximate reciprocal), bit-identical to
+ * those kernels recompiled for sm_100a.  Reference names accepted as aliases: "fermi_speculative_while_while" (Compact),
  * "kepler_dynamic_fetch" (Compact2), "tesla_persistent_while_while" / "tesla_persistent_speculative_while_while" /
  * "tesla_persistent_packet" (AOS_AOS, as those files ship); "b200_persistent_speculative_while_while_{aos_aos,aos_soa,
  * soa_aos,soa_soa}" select the other basic layouts.  Unknown names fail. */

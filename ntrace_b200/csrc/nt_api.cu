@@ -65,6 +65,7 @@ struct Context {
 
     int kernel = Kernel_PersistentSpeculative;
     int kernelLayout = Layout_Compact;
+    bool fastMath = false;
 
     // resident BVH
     DevBuf nodes, woop, triIndex;
@@ -390,27 +391,32 @@ int nt_set_kernel(const char* name)
 {
     std::lock_guard<std::mutex> lock(g_mutex);
     if (!name) { set_error("ntrace_b200: null kernel name"); return 1; }
-    struct Entry { const char* name; int kernel; int layout; };
+    struct Entry { const char* name; int kernel; int layout; bool fast; };
     static const Entry table[] = {
-        {"b200_persistent_speculative_while_while", Kernel_PersistentSpeculative, Layout_Compact},
-        {"b200_speculative_while_while", Kernel_PlainSpeculative, Layout_Compact},
-        {"b200_persistent_speculative_while_while_compact2", Kernel_PersistentSpeculative, Layout_Compact2},
-        // reference kernel file names (src/rt/kernels/*.cu) accepted as aliases with their layouts
-        {"fermi_speculative_while_while", Kernel_PlainSpeculative, Layout_Compact},
-        {"kepler_dynamic_fetch", Kernel_PersistentSpeculative, Layout_Compact2},
+        // IEEE arithmetic in the triangle test: bit-identical to the reference's CPU tracer (CudaBVH::trace / Intersect::RayTriangleWoop)
+        {"b200_persistent_speculative_while_while", Kernel_PersistentSpeculative, Layout_Compact, false},
+        {"b200_speculative_while_while", Kernel_PlainSpeculative, Layout_Compact, false},
+        {"b200_persistent_speculative_while_while_compact2", Kernel_PersistentSpeculative, Layout_Compact2, false},
+        // the arithmetic nvcc -use_fast_math gives the reference's GPU kernels (contracted FMAs, approximate 1/x): bit-identical to them
+        {"b200_persistent_speculative_while_while_fastmath", Kernel_PersistentSpeculative, Layout_Compact, true},
+        {"b200_persistent_speculative_while_while_compact2_fastmath", Kernel_PersistentSpeculative, Layout_Compact2, true},
+        // reference kernel file names (src/rt/kernels/*.cu) accepted as aliases with their layouts AND their arithmetic, so a config
+        // that names one of them gets the results that kernel produces
+        {"fermi_speculative_while_while", Kernel_PlainSpeculative, Layout_Compact, true},
+        {"kepler_dynamic_fetch", Kernel_PersistentSpeculative, Layout_Compact2, true},
         // tesla_* ship with NODES/TRIANGLES_ARRAY_OF_STRUCTURES defined (tesla_persistent_while_while.cu:40-41): AOS_AOS.
         // The BVH is rewritten to the Compact form on the device (nt_layout.cu) and traversed by the one B200 kernel.
-        {"tesla_persistent_while_while", Kernel_PersistentSpeculative, Layout_AOS_AOS},
-        {"tesla_persistent_speculative_while_while", Kernel_PersistentSpeculative, Layout_AOS_AOS},
-        {"tesla_persistent_packet", Kernel_PersistentSpeculative, Layout_AOS_AOS},
-        // the three variants those files select by commenting the defines out
-        {"b200_persistent_speculative_while_while_aos_aos", Kernel_PersistentSpeculative, Layout_AOS_AOS},
-        {"b200_persistent_speculative_while_while_aos_soa", Kernel_PersistentSpeculative, Layout_AOS_SOA},
-        {"b200_persistent_speculative_while_while_soa_aos", Kernel_PersistentSpeculative, Layout_SOA_AOS},
-        {"b200_persistent_speculative_while_while_soa_soa", Kernel_PersistentSpeculative, Layout_SOA_SOA},
+        {"tesla_persistent_while_while", Kernel_PersistentSpeculative, Layout_AOS_AOS, true},
+        {"tesla_persistent_speculative_while_while", Kernel_PersistentSpeculative, Layout_AOS_AOS, true},
+        {"tesla_persistent_packet", Kernel_PersistentSpeculative, Layout_AOS_AOS, true},
+        // the three variants those files select by commenting the defines out (IEEE arithmetic, like every b200_* name)
+        {"b200_persistent_speculative_while_while_aos_aos", Kernel_PersistentSpeculative, Layout_AOS_AOS, false},
+        {"b200_persistent_speculative_while_while_aos_soa", Kernel_PersistentSpeculative, Layout_AOS_SOA, false},
+        {"b200_persistent_speculative_while_while_soa_aos", Kernel_PersistentSpeculative, Layout_SOA_AOS, false},
+        {"b200_persistent_speculative_while_while_soa_soa", Kernel_PersistentSpeculative, Layout_SOA_SOA, false},
     };
     for (const Entry& e : table)
-        if (strcmp(e.name, name) == 0) { g.kernel = e.kernel; g.kernelLayout = e.layout; return 0; }
+        if (strcmp(e.name, name) == 0) { g.kernel = e.kernel; g.kernelLayout = e.layout; g.fastMath = e.fast; return 0; }
     set_error(std::string("ntrace_b200: unknown kernel '") + name + "'");
     return 1;
 }
@@ -623,7 +629,7 @@ int nt_trace_batch(const float* rays, int32_t* results, int numRays, int needClo
     const bool raysOnHost = (raysDev == nullptr), resOnHost = (resDev == nullptr);
 
     TraceLaunch a;
-    a.kernel = g.kernel; a.layout = g.basic ? (int)Layout_Compact : g.kernelLayout; a.anyHit = needClosestHit ? 0 : 1;
+    a.kernel = g.kernel; a.fast = g.fastMath ? 1 : 0; a.layout = g.basic ? (int)Layout_Compact : g.kernelLayout; a.anyHit = needClosestHit ? 0 : 1;
     a.nodes = g.nodes.as<float4>(); a.woop = g.woop.as<float4>(); a.triIndices = g.triIndex.as<int>();
     a.numSMs = g.numSMs; a.stream = g.stream;
     int launches = 0;
@@ -725,7 +731,7 @@ int nt_trace_batch_async(const float* rays, int32_t* results, int numRays, int n
         else { NT_CUDA(s.results.reserve((size_t)numRays * 16)); dRes = s.results.as<int4>(); s.copyOut = true; }
     }
     TraceLaunch a;
-    a.kernel = g.kernel; a.layout = g.basic ? (int)Layout_Compact : g.kernelLayout; a.anyHit = needClosestHit ? 0 : 1;
+    a.kernel = g.kernel; a.fast = g.fastMath ? 1 : 0; a.layout = g.basic ? (int)Layout_Compact : g.kernelLayout; a.anyHit = needClosestHit ? 0 : 1;
     a.nodes = g.nodes.as<float4>(); a.woop = g.woop.as<float4>(); a.triIndices = g.triIndex.as<int>();
     a.numSMs = g.numSMs; a.stream = g.stream;
     a.numRays = numRays; a.rays = dRays; a.results = dRes;

@@ -38,6 +38,7 @@ struct TraceLaunch {
     int layout;               // Layout_Compact or Layout_Compact2
     int numRays;
     int anyHit;
+    int fast;                 // 1: triangle test with the reference GPU kernels' -use_fast_math arithmetic instead of IEEE
     const float4* rays;       // device, 2 x float4 per ray
     int4* results;            // device, 1 x int4 per ray
     const float4* nodes;      // device, 4 x float4 per node

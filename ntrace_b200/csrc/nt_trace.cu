@@ -205,21 +205,36 @@ trace_kernel(int numRays, int anyHit, int fetchThreshold,
                     if (__float_as_int(v00.x) == (int)0x80000000) break;
                     if (TRI_MODE == 2) nxt = __ldg(woop + triAddr + 3);
 
-                    const float Oz = __fsub_rn(__fsub_rn(__fsub_rn(v00.w, __fmul_rn(origx, v00.x)), __fmul_rn(origy, v00.y)), __fmul_rn(origz, v00.z));
-                    const float dd = __fadd_rn(__fadd_rn(__fmul_rn(dirx, v00.x), __fmul_rn(diry, v00.y)), __fmul_rn(dirz, v00.z));
-                    const float t = __fmul_rn(Oz, __frcp_rn(dd));
+                    float t;
+                    if (TRI_MODE == 5) {
+                        // the arithmetic of the reference's GPU kernels as nvcc -use_fast_math compiles them: contracted FMAs, approximate 1/x
+                        const float Oz = v00.w - origx * v00.x - origy * v00.y - origz * v00.z;
+                        t = Oz * __fdividef(1.0f, dirx * v00.x + diry * v00.y + dirz * v00.z);
+                    } else {
+                        const float Oz = __fsub_rn(__fsub_rn(__fsub_rn(v00.w, __fmul_rn(origx, v00.x)), __fmul_rn(origy, v00.y)), __fmul_rn(origz, v00.z));
+                        const float dd = __fadd_rn(__fadd_rn(__fmul_rn(dirx, v00.x), __fmul_rn(diry, v00.y)), __fmul_rn(dirz, v00.z));
+                        t = __fmul_rn(Oz, __frcp_rn(dd));
+                    }
 
                     if (t > tmin && t < hitT) {
-                        if (TRI_MODE == 0) v11 = __ldg(woop + triAddr + 1);
-                        const float Ou = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(v11.x, origx), __fmul_rn(v11.y, origy)), __fmul_rn(v11.z, origz)), v11.w);
-                        const float Du = __fadd_rn(__fadd_rn(__fmul_rn(v11.x, dirx), __fmul_rn(v11.y, diry)), __fmul_rn(v11.z, dirz));
-                        const float u = __fadd_rn(Ou, __fmul_rn(t, Du));
+                        if (TRI_MODE == 0 || TRI_MODE == 5) v11 = __ldg(woop + triAddr + 1);
+                        float u;
+                        if (TRI_MODE == 5) u = (v11.w + origx * v11.x + origy * v11.y + origz * v11.z) + t * (dirx * v11.x + diry * v11.y + dirz * v11.z);
+                        else {
+                            const float Ou = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(v11.x, origx), __fmul_rn(v11.y, origy)), __fmul_rn(v11.z, origz)), v11.w);
+                            const float Du = __fadd_rn(__fadd_rn(__fmul_rn(v11.x, dirx), __fmul_rn(v11.y, diry)), __fmul_rn(v11.z, dirz));
+                            u = __fadd_rn(Ou, __fmul_rn(t, Du));
+                        }
                         if (u >= 0.0f) {
-                            if (TRI_MODE == 0) v22 = __ldg(woop + triAddr + 2);
-                            const float Ov = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(v22.x, origx), __fmul_rn(v22.y, origy)), __fmul_rn(v22.z, origz)), v22.w);
-                            const float Dv = __fadd_rn(__fadd_rn(__fmul_rn(v22.x, dirx), __fmul_rn(v22.y, diry)), __fmul_rn(v22.z, dirz));
-                            const float v = __fadd_rn(Ov, __fmul_rn(t, Dv));
-                            if (v >= 0.0f && __fadd_rn(u, v) <= 1.0f) {
+                            if (TRI_MODE == 0 || TRI_MODE == 5) v22 = __ldg(woop + triAddr + 2);
+                            float v;
+                            if (TRI_MODE == 5) v = (v22.w + origx * v22.x + origy * v22.y + origz * v22.z) + t * (dirx * v22.x + diry * v22.y + dirz * v22.z);
+                            else {
+                                const float Ov = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(v22.x, origx), __fmul_rn(v22.y, origy)), __fmul_rn(v22.z, origz)), v22.w);
+                                const float Dv = __fadd_rn(__fadd_rn(__fmul_rn(v22.x, dirx), __fmul_rn(v22.y, diry)), __fmul_rn(v22.z, dirz));
+                                v = __fadd_rn(Ov, __fmul_rn(t, Dv));
+                            }
+                            if (v >= 0.0f && ((TRI_MODE == 5) ? (u + v) : __fadd_rn(u, v)) <= 1.0f) {
                                 hitT = t; hitU = u; hitV = v;
                                 hitIndex = triAddr;
                                 if (anyHit) { nodeAddr = kEntrypointSentinel; break; }
@@ -303,8 +318,12 @@ cudaError_t launch_tri(const TraceLaunch& a, int* launches)
 template <int LAYOUT, bool PERSISTENT>
 cudaError_t launch_one(const TraceLaunch& a, int* launches)
 {
-    switch (tuning().triMode) {
+    const int triMode = a.fast ? 5 : tuning().triMode;
+    switch (triMode) {
     case 3:  return launch_variant<LAYOUT, 8, PERSISTENT, 0, true>(a, launches);
+    case 5:  if ((reinterpret_cast<size_t>(a.rays) & 31) == 0 && (reinterpret_cast<size_t>(a.nodes) & 63) == 0)
+                 return launch_variant<LAYOUT, 8, PERSISTENT, 5, false, true>(a, launches);
+             return launch_variant<LAYOUT, 8, PERSISTENT, 5>(a, launches);
     case 4:  if ((reinterpret_cast<size_t>(a.rays) & 31) == 0 && (reinterpret_cast<size_t>(a.nodes) & 63) == 0)
                  return launch_variant<LAYOUT, 8, PERSISTENT, 0, false, true>(a, launches);
              return launch_tri<LAYOUT, PERSISTENT, 0>(a, launches);

@@ -152,7 +152,7 @@ def test_aos_upload_reproduces_frozen_reference_trace(gpu_host, orc):
     cpu = orc.CpuBVH(verts, tris, orc.BUILDER_SAH, 1, 8, 1.0e-5)
     nodes, woop, idx = cpu.basic(0)
     assert [sha(nodes), sha(woop), sha(idx)] == meta["head"]["configs"]["sah_1_8"]["layout_sha"]["0"]
-    got = _trace(gpu_host, gpu_host.CudaBVH(nodes, woop, idx, layout=0), "tesla_persistent_while_while", rays)
+    got = _trace(gpu_host, gpu_host.CudaBVH(nodes, woop, idx, layout=0), "b200_persistent_speculative_while_while_aos_aos", rays)   # IEEE arithmetic
     want = np.load(os.path.join(HERE, "ref_head.npz"))["sah_1_8.flat"]
     same = got[:, 0] == want[:, 0]
     assert same.mean() >= 0.9999
