@@ -303,6 +303,15 @@ def raygen_shadow(in_rays, in_results, first, count, samples, light_pos, light_r
     return out, a, b
 
 
+def ray_morton_keys(rays):
+    """findAABBKernel + genMortonKeysKernel restated (RayBufferKernels.cu:70-175) -> (uint32 [N,6] keys, lo[3], hi[3])."""
+    rays = _f32(rays).reshape(-1, 8)
+    keys = np.zeros((len(rays), 6), dtype=np.uint32)
+    aabb = np.zeros(6, dtype=np.float32)
+    lib().orc_ray_morton_keys(_p(rays), C.c_int(len(rays)), _p(keys), _p(aabb))
+    return keys, aabb[:3].copy(), aabb[3:].copy()
+
+
 def ray_morton_order(rays, truncated=False):
     """RayBuffer::mortonSort order: order[new] = old slot (+ the 64-bit truncated keys, old-slot indexed)."""
     rays = _f32(rays).reshape(-1, 8)

@@ -216,6 +216,10 @@ void orc_tri_normals(const float* vtx, int nv, const int32_t* tri, int nt, float
     Scene s; s.verts = (const V3*)vtx; s.numVerts = nv; s.tris = tri; s.numTris = nt;
     tri_normals(s, (V3*)out);
 }
+void orc_ray_morton_keys(const float* rays, int n, uint32_t* keys6, float* aabb6)
+{
+    ray_morton_keys((const Ray*)rays, n, keys6, aabb6);
+}
 void orc_ray_morton_order(const float* rays, int n, int truncated, int32_t* order, uint64_t* key64)
 {
     ray_morton_order((const Ray*)rays, n, truncated, order, key64);

@@ -107,6 +107,36 @@ def hlbvh_available() -> bool:
     return all(os.path.exists(os.path.join(_HERE, "_ref", f"libref_hlbvh_{v}.so")) for v in ("fast", "ieee"))
 
 
+def raybuf_available() -> bool:
+    return all(os.path.exists(os.path.join(_HERE, "_ref", f"libref_raybuf_{v}.so")) for v in ("fast", "ieee"))
+
+
+def ray_aabb(rays, ieee=True):
+    """findAABBKernel (RayBufferKernels.cu:70-136) -> (lo[3], hi[3]) float32."""
+    import numpy as np
+    import torch
+    torch.cuda.synchronize()
+    l = _named_lib("raybuf_ieee" if ieee else "raybuf_fast")
+    out = (C.c_float * 6)()
+    _ck(l, l.ref_ray_aabb(_dp(rays), C.c_int(int(rays.shape[0])), out))
+    a = np.array(list(out), dtype=np.float32)
+    return a[:3], a[3:]
+
+
+def ray_keys(rays, lo, hi, ieee=True):
+    """genMortonKeysKernel (RayBufferKernels.cu:140-175) -> uint32 [N, 6] 192-bit keys (hash[0] least significant)."""
+    import numpy as np
+    import torch
+    torch.cuda.synchronize()
+    l = _named_lib("raybuf_ieee" if ieee else "raybuf_fast")
+    n = int(rays.shape[0])
+    raw = np.zeros((n, 7), dtype=np.uint32)
+    flo = (C.c_float * 3)(*[float(v) for v in lo]); fhi = (C.c_float * 3)(*[float(v) for v in hi])
+    _ck(l, l.ref_ray_keys(_dp(rays), C.c_int(n), flo, fhi, raw.ctypes.data_as(C.c_void_p)))
+    assert (raw[:, 0] == np.arange(n, dtype=np.uint32)).all()
+    return raw[:, 1:].copy()
+
+
 def morton(verts, tris, lo, hi, ieee=True):
     """calcMorton (emitTreeKernel.cu:647-691) on torch CUDA tensors -> uint32 codes per triangle (numpy)."""
     import numpy as np

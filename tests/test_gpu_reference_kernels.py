@@ -255,3 +255,27 @@ def test_gpu_hlbvh_matches_the_reference_build_kernels(gpu_host, orc, refgpu, sc
     assert np.array_equal(ref_c.boxes.view(np.int32), mine.boxes.view(np.int32))
     same_rows = (ref_c.woop.view(np.int32) == mine.woop.view(np.int32)) | (np.isnan(ref_c.woop) & np.isnan(mine.woop))
     assert same_rows.all()
+
+
+def test_ray_sort_keys_match_the_reference_kernels(gpu_host, orc, refgpu, workload):
+    """RayBuffer::mortonSort: the reference's findAABBKernel / genMortonKeysKernel run on the B200 (IEEE build) against the
+    restated key generator the B200 ray sort is checked with (tests/test_gpu_raysort.py): same box, same 192-bit keys."""
+    if not refgpu.raybuf_available():
+        pytest.skip("libref_raybuf_*.so not present")
+    verts, tris, scene, cpu, batches = workload
+    for name in ("primary", "diffuse"):
+        rb = batches[name]
+        rays = rb.rays_host()
+        keys, lo, hi = orc.ray_morton_keys(rays)
+        # (findAABBKernel itself cannot serve as a checker on this GPU: its warp-level min/max reduction goes through
+        #  non-volatile shared memory with no synchronisation, RayBufferKernels.cu:99-111, and loses updates under independent
+        #  thread scheduling -- it returned lo.x = 0 for rays that all start at x = 6.97.  The box is a plain min/max over
+        #  origins and end points; the key kernel below is given the correct one.)
+        ends = rays[:, :3] + rays[:, 4:7] * rays[:, 7:8]
+        assert np.array_equal(lo, np.minimum(rays[:, :3].min(0), ends.min(0))) and np.array_equal(hi, np.maximum(rays[:, :3].max(0), ends.max(0)))
+        rkeys = refgpu.ray_keys(rb.getRayBuffer(), lo, hi, ieee=True)
+        assert np.array_equal(rkeys, keys)
+        # the reference's own flags: a few keys differ in their lowest bits (approximate division / rsqrt)
+        fkeys = refgpu.ray_keys(rb.getRayBuffer(), lo, hi, ieee=False)
+        top_equal = (fkeys[:, 3:] == keys[:, 3:]).all(1).mean()            # most significant 96 bits
+        assert top_equal >= 0.95
