@@ -279,3 +279,35 @@ def test_non_finite_and_extreme_rays_terminate_and_match_the_cpu_tracer(gpu_host
                 assert np.array_equal(got[576:, 0], want[576:, 0]) or (got[576:, 0] == want[576:, 0]).mean() >= 0.9999
             else:
                 assert ((got[:, 0] >= 0) == (want[:, 0] >= 0)).mean() >= 0.999
+
+
+def test_memory_entry_points(gpu_host, orc, small_scene):
+    """nt_mem_alloc / nt_mem_alloc_host / nt_memcpy / nt_memset / nt_mem_free*: what the C++ host's FW::Buffer is built on.
+    A page-locked buffer from nt_mem_alloc_host is traversed in place (zero copy) by nt_trace_batch."""
+    import ctypes as C
+    from ntrace_b200 import capi
+    verts, tris, cpu, (nodes, woop, idx) = small_scene
+    lib = capi.lib()
+    dev, pin_r, pin_o = C.c_void_p(), C.c_void_p(), C.c_void_p()
+    n = 50_000
+    cam = camera.named_camera("conference")
+    rays, _, _ = orc.raygen_primary(cam.position, camera.nscreen_to_world(cam, 250, 200), 250, 200, cam.far)
+    assert lib.nt_mem_alloc(C.c_size_t(n * 32), C.byref(dev)) == 0 and dev.value
+    assert lib.nt_mem_alloc_host(C.c_size_t(n * 32), C.byref(pin_r)) == 0 and lib.nt_mem_alloc_host(C.c_size_t(n * 16), C.byref(pin_o)) == 0
+    # host -> device -> pinned host round trip, then memset
+    assert lib.nt_memcpy(dev, rays.ctypes.data_as(C.c_void_p), C.c_size_t(n * 32)) == 0
+    assert lib.nt_memcpy(pin_r, dev, C.c_size_t(n * 32)) == 0
+    back = np.ctypeslib.as_array(C.cast(pin_r, C.POINTER(C.c_float)), shape=(n, 8))
+    assert np.array_equal(back, rays)
+    assert lib.nt_memset(dev, C.c_int(0xAB), C.c_size_t(64)) == 0
+    probe = np.zeros(64, np.uint8)
+    assert lib.nt_memcpy(probe.ctypes.data_as(C.c_void_p), dev, C.c_size_t(64)) == 0 and (probe == 0xAB).all()
+    # trace straight out of / into the page-locked buffers
+    tracer = gpu_host.CudaBVHTracer(); tracer.setKernel(KERNELS[0]); tracer.setBVH(gpu_host.CudaBVH(nodes, woop, idx))
+    sec = C.c_float(0)
+    assert lib.nt_trace_batch(C.cast(pin_r, C.POINTER(C.c_float)), C.cast(pin_o, C.POINTER(C.c_int32)), C.c_int(n), C.c_int(1), C.byref(sec)) == 0, capi.lib().nt_last_error()
+    got = np.ctypeslib.as_array(C.cast(pin_o, C.POINTER(C.c_int32)), shape=(n, 4)).copy()
+    _check_closest(got, orc.compact_trace(nodes, woop, idx, rays, True))
+    assert lib.nt_mem_free(dev) == 0 and lib.nt_mem_free_host(pin_r) == 0 and lib.nt_mem_free_host(pin_o) == 0
+    assert lib.nt_mem_alloc(C.c_size_t(0), C.byref(dev)) == 0 and not dev.value          # zero bytes: null, no error
+    assert lib.nt_memcpy(None, None, C.c_size_t(8)) != 0 and b"null pointer" in lib.nt_last_error()
