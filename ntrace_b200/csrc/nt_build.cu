@@ -713,6 +713,7 @@ struct CollapseCtx {
     float* childBox;      // 12 floats per gap node: child 0 lo/hi, child 1 lo/hi
     float* childCost;     // 2 floats per gap node
     int* counters; int maxLeaf;
+    float triCost;        // cost of one triangle test relative to one child-box test (Platform: 1)
 };
 
 __device__ __forceinline__ float box_area(const float* lo, const float* hi)
@@ -735,7 +736,7 @@ __global__ void __launch_bounds__(256) collapse_analyse_kernel(int n, CollapseCt
         F3 lo, hi; leaf_box(verts, tris, idx, a, b, eps, lo, hi);
         float* cb = c.childBox + (size_t)g0 * 12 + side * 6;
         cb[0] = lo.x; cb[1] = lo.y; cb[2] = lo.z; cb[3] = hi.x; cb[4] = hi.y; cb[5] = hi.z;
-        c.childCost[(size_t)g0 * 2 + side] = box_area(cb, cb + 3) * (float)(b - a);
+        c.childCost[(size_t)g0 * 2 + side] = c.triCost * box_area(cb, cb + 3) * (float)(b - a);
         arrivals++;
     }
     if (arrivals == 0) return;
@@ -749,8 +750,8 @@ __global__ void __launch_bounds__(256) collapse_analyse_kernel(int n, CollapseCt
         const int count = c.nodeE[g] - c.nodeS[g];
         float cost = 2.0f * area + __ldcg(c.childCost + (size_t)g * 2) + __ldcg(c.childCost + (size_t)g * 2 + 1);
         const int p = c.parent[g];
-        if (p >= 0 && count <= c.maxLeaf && area * (float)count <= cost) {      // roots of clusters / of the tree never fold
-            cost = area * (float)count;
+        if (p >= 0 && count <= c.maxLeaf && c.triCost * area * (float)count <= cost) {      // roots of clusters / of the tree never fold
+            cost = c.triCost * area * (float)count;
             c.flags[g] |= F_COLLAPSED;
         }
         if (p < 0) return;
@@ -1005,6 +1006,7 @@ cudaError_t build_bvh_device(const float* dVerts, int numVerts, const int* dTris
         cx.nodeS = sc.nodeS.as<int>(); cx.nodeE = sc.nodeE.as<int>(); cx.parent = sc.parent.as<int>(); cx.flags = sc.flags.as<uint>();
         cx.childBox = sc.childBox.as<float>(); cx.childCost = sc.childCost.as<float>(); cx.counters = sc.counters.as<int>();
         cx.maxLeaf = (p.collapseMaxLeaf > 0) ? p.collapseMaxLeaf : p.leafSize;
+        cx.triCost = p.collapseTriCost;
         collapse_analyse_kernel<<<(gaps + 255) / 256, 256, 0, stream>>>(n, cx, dVerts, dTris, idxA, p.epsilon);
         NT_TRY(cudaMemcpyAsync(sc.flags2.p, sc.flags.p, (size_t)gaps * 4, cudaMemcpyDeviceToDevice, stream));
         collapse_resolve_kernel<<<(gaps + 255) / 256, 256, 0, stream>>>(n, sc.parent.as<int>(), sc.flags2.as<uint>(), sc.flags.as<uint>());

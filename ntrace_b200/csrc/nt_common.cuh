@@ -90,6 +90,7 @@ struct BuildParams {
     int layout = Layout_Compact;   // Layout_Compact (byte offsets, < 1.98 GB of nodes) or Layout_Compact2 (offsets / 16)
     int collapse = 0;         // 0 = reference leaf rule (count <= leafSize), 1 = SAH-guided collapse
     int collapseMaxLeaf = 0;  // largest leaf the collapse may create (0 = leafSize)
+    float collapseTriCost = 1.0f;   // SAH cost of a triangle test relative to a child-box test in the collapse (Platform default 1)
 };
 struct BuildOutput {          // device buffers owned by the context
     DevBuf* nodes; DevBuf* woop; DevBuf* triIndex;
