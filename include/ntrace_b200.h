@@ -12,9 +12,11 @@
  *   - no exceptions cross the boundary; all pointers are caller-owned and borrowed for the call;
  *   - pointers may be HOST or DEVICE addresses (the reference's FW::Buffer migrates lazily,
  *     src/framework/gpu/Buffer.hpp:107-113); the library detects which with
- *     cudaPointerGetAttributes and stages host buffers through its own device buffers;
+ *     cudaPointerGetAttributes; page-locked (pinned, device-mapped) host ray / result buffers are traversed in place over
+ *     PCIe, pageable ones are staged through the library's own device buffers;
  *   - calls are synchronous: when a call returns its outputs are complete
- *     (reference: CudaKernel::launchTimed syncs, src/framework/gpu/CudaKernel.cpp:188-221);
+ *     (reference: CudaKernel::launchTimed syncs, src/framework/gpu/CudaKernel.cpp:188-221).  The two opt-in exceptions
+ *     are nt_set_deferred(1) (device buffers only) and nt_trace_batch_async / nt_trace_wait;
  *   - one device per process (reference: one CUDA context, CudaModule.hpp:92-97); multi-GPU runs
  *     use one process per GPU and replicate the BVH (nt_bvh_device_ptrs + NCCL broadcast in the host);
  *   - not re-entrant: one caller thread at a time (guarded by an internal mutex);
