@@ -217,17 +217,40 @@ __device__ __forceinline__ int gap_node_id(const Numbering& nb, int g, uint rank
     return (g == nb.rootGap) ? 0 : (int)(rank < nb.rootRank ? rank + 1 : rank);
 }
 
-// leaf box = union of triangle vertices -/+ epsilon (calcLeaf, emitTreeKernel.cu:383-408)
-__device__ __forceinline__ void leaf_box(const float* __restrict__ verts, const int* __restrict__ tris, const int* __restrict__ idx,
-                                         int a, int b, float eps, F3& lo, F3& hi)
+// Per-triangle boxes in SORTED order (6 floats: min xyz, max xyz of the three vertices, no epsilon).  The geometry is gathered
+// once -- vertices are stored in input order, so a gather in Morton order fetches ~270 B of DRAM sectors for the 36 B it wants --
+// and every later consumer (cluster boxes, leaf boxes, collapse) streams these 24 B instead.
+__device__ __forceinline__ void tri_box_store(float* __restrict__ triBox, int p, F3 a, F3 b, F3 c)
+{
+    const F3 mn = min3v(a, min3v(b, c)), mx = max3v(a, max3v(b, c));
+    float2* o = reinterpret_cast<float2*>(triBox + (size_t)p * 6);
+    o[0] = make_float2(mn.x, mn.y); o[1] = make_float2(mn.z, mx.x); o[2] = make_float2(mx.y, mx.z);
+}
+
+__global__ void __launch_bounds__(256) tri_box_kernel(int n, const float* __restrict__ verts, const int* __restrict__ tris,
+                                                       const int* __restrict__ idx, float* __restrict__ triBox)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const int t = __ldg(idx + p);
+    tri_box_store(triBox, p, ld3(verts, __ldg(tris + 3 * t)), ld3(verts, __ldg(tris + 3 * t + 1)), ld3(verts, __ldg(tris + 3 * t + 2)));
+}
+
+// leaf box = union of triangle vertices -/+ epsilon (calcLeaf, emitTreeKernel.cu:383-408).  The reference subtracts / adds epsilon
+// per triangle before the min / max; rounding is monotone, so min_i fl(m_i - eps) == fl(min_i m_i - eps) bit for bit and the
+// epsilon is applied once to the union here.
+__device__ __forceinline__ void leaf_box(const float* __restrict__ triBox, int a, int b, float eps, F3& lo, F3& hi)
 {
     lo.x = lo.y = lo.z = kF32Max; hi.x = hi.y = hi.z = -kF32Max;
     for (int i = a; i < b; i++) {
-        const int t = __ldg(idx + i);
-        const F3 p = ld3(verts, __ldg(tris + 3 * t)), q = ld3(verts, __ldg(tris + 3 * t + 1)), r = ld3(verts, __ldg(tris + 3 * t + 2));
-        const F3 mn = min3v(p, min3v(q, r)), mx = max3v(p, max3v(q, r));
-        lo.x = fminf(lo.x, __fsub_rn(mn.x, eps)); lo.y = fminf(lo.y, __fsub_rn(mn.y, eps)); lo.z = fminf(lo.z, __fsub_rn(mn.z, eps));
-        hi.x = fmaxf(hi.x, __fadd_rn(mx.x, eps)); hi.y = fmaxf(hi.y, __fadd_rn(mx.y, eps)); hi.z = fmaxf(hi.z, __fadd_rn(mx.z, eps));
+        const float2* q = reinterpret_cast<const float2*>(triBox + (size_t)i * 6);
+        const float2 q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2);
+        lo.x = fminf(lo.x, q0.x); lo.y = fminf(lo.y, q0.y); lo.z = fminf(lo.z, q1.x);
+        hi.x = fmaxf(hi.x, q1.y); hi.y = fmaxf(hi.y, q2.x); hi.z = fmaxf(hi.z, q2.y);
+    }
+    if (b > a) {
+        lo.x = __fsub_rn(lo.x, eps); lo.y = __fsub_rn(lo.y, eps); lo.z = __fsub_rn(lo.z, eps);
+        hi.x = __fadd_rn(hi.x, eps); hi.y = __fadd_rn(hi.y, eps); hi.z = __fadd_rn(hi.z, eps);
     }
 }
 
@@ -276,8 +299,7 @@ __device__ __forceinline__ void climb(const ClimbCtx& c, int curId, int parCode)
 
 __global__ void __launch_bounds__(256) emit_kernel(int n, const int* __restrict__ nodeS, const int* __restrict__ nodeE,
                                                     const uint* __restrict__ flags, const int* __restrict__ scalars,
-                                                    const float* __restrict__ verts, const int* __restrict__ tris, const int* __restrict__ idx,
-                                                    float eps, ClimbCtx c)
+                                                    const float* __restrict__ triBox, float eps, ClimbCtx c)
 {
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= n - 1) return;
@@ -305,13 +327,13 @@ __global__ void __launch_bounds__(256) emit_kernel(int n, const int* __restrict_
     int arrivals = 0;
     if (f & F_LEFT_LEAF) {
         node[12] = ~(3 * s + (int)(c.ex[s] >> 32));
-        F3 lo, hi; leaf_box(verts, tris, idx, s, split, eps, lo, hi);
+        F3 lo, hi; leaf_box(triBox, s, split, eps, lo, hi);
         store_child_box(nodef, 0, lo, hi);
         arrivals++;
     }
     if (f & F_RIGHT_LEAF) {
         node[13] = ~(3 * split + (int)(c.ex[split] >> 32));
-        F3 lo, hi; leaf_box(verts, tris, idx, split, e, eps, lo, hi);
+        F3 lo, hi; leaf_box(triBox, split, e, eps, lo, hi);
         store_child_box(nodef, 1, lo, hi);
         arrivals++;
     }
@@ -327,8 +349,7 @@ __global__ void __launch_bounds__(256) emit_kernel(int n, const int* __restrict_
 // (distribute, emitTreeKernel.cu:990-996): link, leaf box, then join the refit.
 __global__ void __launch_bounds__(256) cluster_leaf_emit_kernel(int numClusters, int leafSize, const int* __restrict__ clsStart,
                                                                  const int* __restrict__ clsParent,
-                                                                 const float* __restrict__ verts, const int* __restrict__ tris, const int* __restrict__ idx,
-                                                                 float eps, ClimbCtx c)
+                                                                 const float* __restrict__ triBox, float eps, ClimbCtx c)
 {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= numClusters) return;
@@ -337,7 +358,7 @@ __global__ void __launch_bounds__(256) cluster_leaf_emit_kernel(int numClusters,
     const int code = clsParent[k];
     const int pid = code >> 1, side = code & 1;
     c.nodes[(size_t)pid * 16 + 12 + side] = ~(3 * cs + (int)(c.ex[cs] >> 32));
-    F3 lo, hi; leaf_box(verts, tris, idx, cs, ce, eps, lo, hi);
+    F3 lo, hi; leaf_box(triBox, cs, ce, eps, lo, hi);
     store_child_box(reinterpret_cast<float*>(c.nodes + (size_t)pid * 16), side, lo, hi);
     __threadfence();
     if (atomicAdd(c.topCounters + pid, 1) == 0) return;
@@ -387,8 +408,8 @@ __global__ void __launch_bounds__(256) cluster_box_init_kernel(int numClusters, 
     boxI[i] = ((i % 6) < 3) ? f2i_ord(kF32Max) : f2i_ord(-kF32Max);
 }
 
-__global__ void __launch_bounds__(256) cluster_box_kernel(int n, const uint* __restrict__ clusterOf, const float* __restrict__ verts,
-                                                           const int* __restrict__ tris, const int* __restrict__ idx, int* __restrict__ boxI)
+__global__ void __launch_bounds__(256) cluster_box_kernel(int n, const uint* __restrict__ clusterOf, const float* __restrict__ triBox,
+                                                           int* __restrict__ boxI)
 {
     // Sorted positions of one cluster are contiguous, so the lanes of a warp form a few contiguous segments: reduce each
     // segment with shuffles and let only its first lane touch memory (ordered-int atomics: the result is order independent).
@@ -399,10 +420,9 @@ __global__ void __launch_bounds__(256) cluster_box_kernel(int n, const uint* __r
     float lo[3] = {kF32Max, kF32Max, kF32Max}, hi[3] = {-kF32Max, -kF32Max, -kF32Max};
     if (valid) {
         cid = clusterOf[p];
-        const int t = __ldg(idx + p);
-        const F3 a = ld3(verts, __ldg(tris + 3 * t)), b = ld3(verts, __ldg(tris + 3 * t + 1)), c = ld3(verts, __ldg(tris + 3 * t + 2));
-        const F3 l = min3v(a, min3v(b, c)), h = max3v(a, max3v(b, c));
-        lo[0] = l.x; lo[1] = l.y; lo[2] = l.z; hi[0] = h.x; hi[1] = h.y; hi[2] = h.z;
+        const float2* q = reinterpret_cast<const float2*>(triBox + (size_t)p * 6);
+        const float2 q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2);
+        lo[0] = q0.x; lo[1] = q0.y; lo[2] = q1.x; hi[0] = q1.y; hi[1] = q2.x; hi[2] = q2.y;
     }
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -722,8 +742,7 @@ __device__ __forceinline__ float box_area(const float* lo, const float* hi)
     return 2.0f * (dx * dy + dy * dz + dz * dx);
 }
 
-__global__ void __launch_bounds__(256) collapse_analyse_kernel(int n, CollapseCtx c, const float* __restrict__ verts,
-                                                                const int* __restrict__ tris, const int* __restrict__ idx, float eps)
+__global__ void __launch_bounds__(256) collapse_analyse_kernel(int n, CollapseCtx c, const float* __restrict__ triBox, float eps)
 {
     const int g0 = blockIdx.x * blockDim.x + threadIdx.x;
     if (g0 >= n - 1) return;
@@ -733,7 +752,7 @@ __global__ void __launch_bounds__(256) collapse_analyse_kernel(int n, CollapseCt
     for (int side = 0; side < 2; side++) {
         if (!(f0 & (side ? F_RIGHT_LEAF : F_LEFT_LEAF))) continue;
         const int a = side ? g0 + 1 : c.nodeS[g0], b = side ? c.nodeE[g0] : g0 + 1;
-        F3 lo, hi; leaf_box(verts, tris, idx, a, b, eps, lo, hi);
+        F3 lo, hi; leaf_box(triBox, a, b, eps, lo, hi);
         float* cb = c.childBox + (size_t)g0 * 12 + side * 6;
         cb[0] = lo.x; cb[1] = lo.y; cb[2] = lo.z; cb[3] = hi.x; cb[4] = hi.y; cb[5] = hi.z;
         c.childCost[(size_t)g0 * 2 + side] = c.triCost * box_area(cb, cb + 3) * (float)(b - a);
@@ -815,7 +834,7 @@ __device__ __forceinline__ void calc_woop(F3 v0, F3 v1, F3 v2, float4& o0, float
 // triangle of each leaf (createLeaf, emitTreeKernel.cu:170-231)
 __global__ void __launch_bounds__(256) leaf_emit_kernel(int n, const u64* __restrict__ ex, const uint* __restrict__ pack32,
                                                          const float* __restrict__ verts, const int* __restrict__ tris, const int* __restrict__ idx,
-                                                         float4* __restrict__ woop, int* __restrict__ triIndex)
+                                                         float4* __restrict__ woop, int* __restrict__ triIndex, float* __restrict__ triBoxOut)
 {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n) return;
@@ -823,7 +842,9 @@ __global__ void __launch_bounds__(256) leaf_emit_kernel(int n, const u64* __rest
     const int out = 3 * p + leafRank;
     const int t = __ldg(idx + p);
     float4 o0, o1, o2;
-    calc_woop(ld3(verts, __ldg(tris + 3 * t)), ld3(verts, __ldg(tris + 3 * t + 1)), ld3(verts, __ldg(tris + 3 * t + 2)), o0, o1, o2);
+    const F3 va = ld3(verts, __ldg(tris + 3 * t)), vb = ld3(verts, __ldg(tris + 3 * t + 1)), vc = ld3(verts, __ldg(tris + 3 * t + 2));
+    if (triBoxOut) tri_box_store(triBoxOut, p, va, vb, vc);      // plain LBVH: this is the only pass that gathers the geometry
+    calc_woop(va, vb, vc, o0, o1, o2);
     woop[out] = o0; woop[out + 1] = o1; woop[out + 2] = o2;
     triIndex[out] = t; triIndex[out + 1] = 0; triIndex[out + 2] = 0;
     if (p == n - 1 || pack32[2 * (p + 1) + 1]) {
@@ -843,8 +864,12 @@ __global__ void single_triangle_kernel(const float* __restrict__ verts, const in
     woop[0] = make_float4(z, z, z, z); triIndex[0] = 0;
     woop[1] = o0; woop[2] = o1; woop[3] = o2; triIndex[1] = 0; triIndex[2] = 0; triIndex[3] = 0;
     woop[4] = make_float4(z, z, z, z); triIndex[4] = 0;
+    (void)idx;                                               // idx[0] == 0 (written by morton_kernel)
+    const F3 a = ld3(verts, tris[0]), b = ld3(verts, tris[1]), c3 = ld3(verts, tris[2]);
+    const F3 mn = min3v(a, min3v(b, c3)), mx = max3v(a, max3v(b, c3));
     F3 lo, hi;
-    leaf_box(verts, tris, idx, 0, 1, eps, lo, hi);          // idx[0] == 0 (written by morton_kernel)
+    lo.x = __fsub_rn(mn.x, eps); lo.y = __fsub_rn(mn.y, eps); lo.z = __fsub_rn(mn.z, eps);
+    hi.x = __fadd_rn(mx.x, eps); hi.y = __fadd_rn(mx.y, eps); hi.z = __fadd_rn(mx.z, eps);
     float* nf = reinterpret_cast<float*>(nodes);
     F3 elo, ehi; elo.x = elo.y = elo.z = kF32Max; ehi.x = ehi.y = ehi.z = -kF32Max;
     store_child_box(nf, 0, elo, ehi);
@@ -855,6 +880,7 @@ __global__ void single_triangle_kernel(const float* __restrict__ verts, const in
 struct Scratch {
     DevBuf keysB, idxB, hist, blockSums, nodeS, nodeE, parent, flags, pack, ex, counters, scalars;
     DevBuf childBox, childCost, flags2;      // SAH collapse
+    DevBuf triBox;                           // 6 floats per sorted position
     // HLBVH
     DevBuf clsHead, clusterOf, clsStart, clsBox, clsTask0, clsTask1, clsBin, clsParent;
     DevBuf tBox0, tBox1, tCnt0, tCnt1, tId0, tId1, rInts, rBoxes, binBox, binCnt, blockSum, topNodes, topParent, topCounters;
@@ -912,6 +938,15 @@ cudaError_t build_bvh_device(const float* dVerts, int numVerts, const int* dTris
     NT_TRY(sc.blockSums.reserve(scan_block_sums_bytes((long long)radix_hist_bytes(n) / 4) + scan_block_sums_bytes(n)));
     NT_TRY(radix_sort_pairs<uint>(keysA, idxA, sc.keysB.as<uint>(), sc.idxB.as<int>(), n, 4, sc.hist.as<uint>(), sc.blockSums.as<uint>(), stream, &launches));
 
+    // per-triangle boxes in sorted order.  HLBVH (cluster boxes) and the SAH collapse need them before the leaves are
+    // numbered: one early gather pass; the plain LBVH gets them from leaf_emit_kernel, its only gather.
+    NT_TRY(sc.triBox.reserve((size_t)n * 24));
+    const bool earlyTriBox = hl || (p.collapse != 0);
+    if (earlyTriBox) {
+        tri_box_kernel<<<(n + 255) / 256, 256, 0, stream>>>(n, dVerts, dTris, idxA, sc.triBox.as<float>());
+        launches++;
+    }
+
     NT_TRY(sc.scalars.reserve(64));
     NT_TRY(cudaMemsetAsync(sc.scalars.p, 0, 64, stream));
     int* rootGap = sc.scalars.as<int>();                 // int [0]
@@ -951,7 +986,7 @@ cudaError_t build_bvh_device(const float* dVerts, int numVerts, const int* dTris
 
         cluster_start_kernel<<<(n + 255) / 256, 256, 0, stream>>>(n, sc.clsHead.as<uint>(), sc.clusterOf.as<uint>(), sc.clsStart.as<int>(), C);
         cluster_box_init_kernel<<<(C * 6 + 255) / 256, 256, 0, stream>>>(C, sc.clsBox.as<int>());
-        cluster_box_kernel<<<(n + 255) / 256, 256, 0, stream>>>(n, sc.clusterOf.as<uint>(), dVerts, dTris, idxA, sc.clsBox.as<int>());
+        cluster_box_kernel<<<(n + 255) / 256, 256, 0, stream>>>(n, sc.clusterOf.as<uint>(), sc.triBox.as<float>(), sc.clsBox.as<int>());
         launches += 3;
         NT_TRY(cudaGetLastError());
 
@@ -1007,7 +1042,7 @@ cudaError_t build_bvh_device(const float* dVerts, int numVerts, const int* dTris
         cx.childBox = sc.childBox.as<float>(); cx.childCost = sc.childCost.as<float>(); cx.counters = sc.counters.as<int>();
         cx.maxLeaf = (p.collapseMaxLeaf > 0) ? p.collapseMaxLeaf : p.leafSize;
         cx.triCost = p.collapseTriCost;
-        collapse_analyse_kernel<<<(gaps + 255) / 256, 256, 0, stream>>>(n, cx, dVerts, dTris, idxA, p.epsilon);
+        collapse_analyse_kernel<<<(gaps + 255) / 256, 256, 0, stream>>>(n, cx, sc.triBox.as<float>(), p.epsilon);
         NT_TRY(cudaMemcpyAsync(sc.flags2.p, sc.flags.p, (size_t)gaps * 4, cudaMemcpyDeviceToDevice, stream));
         collapse_resolve_kernel<<<(gaps + 255) / 256, 256, 0, stream>>>(n, sc.parent.as<int>(), sc.flags2.as<uint>(), sc.flags.as<uint>());
         pack_kernel<<<(gaps + 255) / 256, 256, 0, stream>>>(n, sc.nodeS.as<int>(), sc.flags.as<uint>(), sc.pack.as<uint>());
@@ -1048,17 +1083,18 @@ cudaError_t build_bvh_device(const float* dVerts, int numVerts, const int* dTris
     cc.nb.numTop = (int)numTop; cc.nb.rootGap = 0; cc.nb.rootRank = 0; cc.nb.linkMul = linkMul;
     if (hl) NT_TRY(cudaMemcpyAsync(out.nodes->p, sc.topNodes.p, numTop * 64, cudaMemcpyDeviceToDevice, stream));
 
+    // Woop rows / indices / terminators.  Without an earlier tri_box pass (plain LBVH) this kernel is the one gather of the
+    // geometry and also leaves the per-triangle boxes behind for emit_kernel, so it runs first.
+    leaf_emit_kernel<<<(n + 255) / 256, 256, 0, stream>>>(n, sc.ex.as<u64>(), sc.pack.as<uint>(), dVerts, dTris, idxA,
+                                                           out.woop->as<float4>(), out.triIndex->as<int>(), earlyTriBox ? nullptr : sc.triBox.as<float>());
     emit_kernel<<<(gaps + 255) / 256, 256, 0, stream>>>(n, sc.nodeS.as<int>(), sc.nodeE.as<int>(), sc.flags.as<uint>(), rootGap,
-                                                         dVerts, dTris, idxA, p.epsilon, cc);
-    launches++;
+                                                         sc.triBox.as<float>(), p.epsilon, cc);
+    launches += 2;
     if (hl) {
         cluster_leaf_emit_kernel<<<(C + 255) / 256, 256, 0, stream>>>(C, p.leafSize, sc.clsStart.as<int>(), sc.clsParent.as<int>(),
-                                                                       dVerts, dTris, idxA, p.epsilon, cc);
+                                                                       sc.triBox.as<float>(), p.epsilon, cc);
         launches++;
     }
-    leaf_emit_kernel<<<(n + 255) / 256, 256, 0, stream>>>(n, sc.ex.as<u64>(), sc.pack.as<uint>(), dVerts, dTris, idxA,
-                                                           out.woop->as<float4>(), out.triIndex->as<int>());
-    launches++;
     NT_TRY(cudaGetLastError());
     *outLaunches = launches;
     return cudaSuccess;
