@@ -21,7 +21,7 @@
 //   * inner nodes and leaves are numbered by one 64-bit exclusive scan (nodes by gap index, root
 //     moved to slot 0; leaves by sorted position), so the output is deterministic and Morton-coherent;
 //   * AABBs are fitted bottom-up in the same kernel that emits the nodes, with one arrival counter per
-//     node (atomicAdd + __threadfence), writing child boxes straight into the parent's node words.
+//     node (one acq_rel atomic per arrival), writing child boxes straight into the parent's node words.
 // One host readback (node / leaf counts, to size the output buffers) instead of one per level.
 #include "nt_common.cuh"
 #include "nt_sort.cuh"
@@ -266,6 +266,15 @@ struct ClimbCtx {
     const int* topParent; int* topCounters; Numbering nb;
 };
 
+// One arrival at a refit counter: a single acq_rel RMW releases this thread's child-box stores and acquires the sibling's
+// (replaces membar.gl + relaxed atom; the fused form is cheaper and is the exact ordering the climb needs).
+__device__ __forceinline__ int arrive(int* counter)
+{
+    int old;
+    asm volatile("atom.acq_rel.gpu.global.add.s32 %0, [%1], 1;" : "=r"(old) : "l"(counter) : "memory");
+    return old;
+}
+
 // Bottom-up refit: node `curId` (both child boxes present) carries its box to its parent; whoever arrives second at a
 // node continues (one arrival counter per node).  parCode is the parent code of the current node.
 __device__ __forceinline__ void climb(const ClimbCtx& c, int curId, int parCode)
@@ -291,8 +300,7 @@ __device__ __forceinline__ void climb(const ClimbCtx& c, int curId, int parCode)
             counter = c.topCounters + pid; next = c.topParent[pid];
         }
         store_child_box(reinterpret_cast<float*>(c.nodes + (size_t)pid * 16), side, lo, hi);
-        __threadfence();
-        if (atomicAdd(counter, 1) == 0) return;
+        if (arrive(counter) == 0) return;
         curId = pid; parCode = next;
     }
 }
@@ -339,8 +347,7 @@ __global__ void __launch_bounds__(256) emit_kernel(int n, const int* __restrict_
     }
     if (arrivals == 0) return;
     if (arrivals == 1) {
-        __threadfence();
-        if (atomicAdd(c.gapCounters + g, 1) == 0) return;          // the inner child has not arrived yet
+        if (arrive(c.gapCounters + g) == 0) return;          // the inner child has not arrived yet
     }
     climb(c, id, par);
 }
@@ -360,8 +367,7 @@ __global__ void __launch_bounds__(256) cluster_leaf_emit_kernel(int numClusters,
     c.nodes[(size_t)pid * 16 + 12 + side] = ~(3 * cs + (int)(c.ex[cs] >> 32));
     F3 lo, hi; leaf_box(triBox, cs, ce, eps, lo, hi);
     store_child_box(reinterpret_cast<float*>(c.nodes + (size_t)pid * 16), side, lo, hi);
-    __threadfence();
-    if (atomicAdd(c.topCounters + pid, 1) == 0) return;
+    if (arrive(c.topCounters + pid) == 0) return;
     climb(c, pid, c.topParent[pid]);
 }
 
@@ -759,7 +765,7 @@ __global__ void __launch_bounds__(256) collapse_analyse_kernel(int n, CollapseCt
         arrivals++;
     }
     if (arrivals == 0) return;
-    if (arrivals == 1) { __threadfence(); if (atomicAdd(c.counters + g0, 1) == 0) return; }
+    if (arrivals == 1) { if (arrive(c.counters + g0) == 0) return; }
     int g = g0;
     for (;;) {
         const float* cb = c.childBox + (size_t)g * 12;
@@ -778,8 +784,7 @@ __global__ void __launch_bounds__(256) collapse_analyse_kernel(int n, CollapseCt
         float* pb = c.childBox + (size_t)pg * 12 + side * 6;
         for (int k = 0; k < 3; k++) { pb[k] = lo[k]; pb[3 + k] = hi[k]; }
         c.childCost[(size_t)pg * 2 + side] = cost;
-        __threadfence();
-        if (atomicAdd(c.counters + pg, 1) == 0) return;
+        if (arrive(c.counters + pg) == 0) return;
         g = pg;
     }
 }
