@@ -305,17 +305,19 @@ __device__ __forceinline__ void climb(const ClimbCtx& c, int curId, int parCode)
     }
 }
 
-__global__ void __launch_bounds__(256) emit_kernel(int n, const int* __restrict__ nodeS, const int* __restrict__ nodeE,
-                                                    const uint* __restrict__ flags, const int* __restrict__ scalars,
-                                                    const float* __restrict__ triBox, float eps, ClimbCtx c)
+// One thread per KEPT gap (= inner node), taken from the rank-ordered list leaf_emit_kernel leaves behind: with leafSize 8
+// only ~18 % of the gaps survive, and a thread per gap ran this latency-bound kernel with 6 of 32 lanes alive.
+__global__ void __launch_bounds__(256) emit_kernel(int numKept, const int* __restrict__ keptGap, const int* __restrict__ nodeS,
+                                                    const int* __restrict__ nodeE, const uint* __restrict__ flags,
+                                                    const int* __restrict__ scalars, const float* __restrict__ triBox, float eps, ClimbCtx c)
 {
-    const int g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= n - 1) return;
+    const int rank = blockIdx.x * blockDim.x + threadIdx.x;
+    if (rank >= numKept) return;
+    const int g = __ldg(keptGap + rank);
     const uint f = flags[g];
-    if (!(f & F_KEPT)) return;
     c.nb.rootGap = scalars[0];
     c.nb.rootRank = (c.nb.numTop > 0) ? 0u : (uint)c.ex[c.nb.rootGap];
-    const int id = gap_node_id(c.nb, g, (uint)c.ex[g]);
+    const int id = gap_node_id(c.nb, g, (uint)rank);
     const int s = nodeS[g], e = nodeE[g], split = g + 1;
     int* node = c.nodes + (size_t)id * 16;
     float* nodef = reinterpret_cast<float*>(node);
@@ -839,11 +841,15 @@ __device__ __forceinline__ void calc_woop(F3 v0, F3 v1, F3 v2, float4& o0, float
 // triangle of each leaf (createLeaf, emitTreeKernel.cu:170-231)
 __global__ void __launch_bounds__(256) leaf_emit_kernel(int n, const u64* __restrict__ ex, const uint* __restrict__ pack32,
                                                          const float* __restrict__ verts, const int* __restrict__ tris, const int* __restrict__ idx,
-                                                         float4* __restrict__ woop, int* __restrict__ triIndex, float* __restrict__ triBoxOut)
+                                                         float4* __restrict__ woop, int* __restrict__ triIndex, float* __restrict__ triBoxOut,
+                                                         int* __restrict__ keptGap)
 {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n) return;
-    const int leafRank = (int)(ex[p] >> 32) + (int)pack32[2 * p + 1] - 1;      // leaves started at or before p, minus one
+    const u64 e = ex[p];
+    const uint2 pk = *reinterpret_cast<const uint2*>(pack32 + 2 * p);           // (gap p kept, a leaf starts at p)
+    if (pk.x) keptGap[(uint)e] = p;                                            // kept gaps in rank order, for emit_kernel
+    const int leafRank = (int)(e >> 32) + (int)pk.y - 1;                       // leaves started at or before p, minus one
     const int out = 3 * p + leafRank;
     const int t = __ldg(idx + p);
     float4 o0, o1, o2;
@@ -886,6 +892,7 @@ struct Scratch {
     DevBuf keysB, idxB, hist, blockSums, nodeS, nodeE, parent, flags, pack, ex, counters, scalars;
     DevBuf childBox, childCost, flags2;      // SAH collapse
     DevBuf triBox;                           // 6 floats per sorted position
+    DevBuf keptGap;                          // kept gaps (inner nodes) in rank order
     // HLBVH
     DevBuf clsHead, clusterOf, clsStart, clsBox, clsTask0, clsTask1, clsBin, clsParent;
     DevBuf tBox0, tBox1, tCnt0, tCnt1, tId0, tId1, rInts, rBoxes, binBox, binCnt, blockSum, topNodes, topParent, topCounters;
@@ -1028,7 +1035,7 @@ cudaError_t build_bvh_device(const float* dVerts, int numVerts, const int* dTris
     // ---- topology, forced leaves, numbering
     const int gaps = n - 1;
     NT_TRY(sc.nodeS.reserve((size_t)n * 4)); NT_TRY(sc.nodeE.reserve((size_t)n * 4)); NT_TRY(sc.parent.reserve((size_t)n * 4));
-    NT_TRY(sc.flags.reserve((size_t)n * 4)); NT_TRY(sc.pack.reserve((size_t)n * 8)); NT_TRY(sc.ex.reserve((size_t)n * 8));
+    NT_TRY(sc.flags.reserve((size_t)n * 4)); NT_TRY(sc.pack.reserve((size_t)n * 8)); NT_TRY(sc.ex.reserve((size_t)n * 8)); NT_TRY(sc.keptGap.reserve((size_t)n * 4));
     NT_TRY(sc.counters.reserve((size_t)n * 4));
     NT_TRY(cudaMemsetAsync(sc.pack.p, 0, (size_t)n * 8, stream));
     NT_TRY(cudaMemsetAsync(sc.counters.p, 0, (size_t)n * 4, stream));
@@ -1091,9 +1098,12 @@ cudaError_t build_bvh_device(const float* dVerts, int numVerts, const int* dTris
     // Woop rows / indices / terminators.  Without an earlier tri_box pass (plain LBVH) this kernel is the one gather of the
     // geometry and also leaves the per-triangle boxes behind for emit_kernel, so it runs first.
     leaf_emit_kernel<<<(n + 255) / 256, 256, 0, stream>>>(n, sc.ex.as<u64>(), sc.pack.as<uint>(), dVerts, dTris, idxA,
-                                                           out.woop->as<float4>(), out.triIndex->as<int>(), earlyTriBox ? nullptr : sc.triBox.as<float>());
-    emit_kernel<<<(gaps + 255) / 256, 256, 0, stream>>>(n, sc.nodeS.as<int>(), sc.nodeE.as<int>(), sc.flags.as<uint>(), rootGap,
-                                                         sc.triBox.as<float>(), p.epsilon, cc);
+                                                           out.woop->as<float4>(), out.triIndex->as<int>(), earlyTriBox ? nullptr : sc.triBox.as<float>(),
+                                                           sc.keptGap.as<int>());
+    const int numKept = (int)(numInner - numTop);
+    if (numKept > 0)
+        emit_kernel<<<(numKept + 255) / 256, 256, 0, stream>>>(numKept, sc.keptGap.as<int>(), sc.nodeS.as<int>(), sc.nodeE.as<int>(), sc.flags.as<uint>(),
+                                                                rootGap, sc.triBox.as<float>(), p.epsilon, cc);
     launches += 2;
     if (hl) {
         cluster_leaf_emit_kernel<<<(C + 255) / 256, 256, 0, stream>>>(C, p.leafSize, sc.clsStart.as<int>(), sc.clsParent.as<int>(),

@@ -8,8 +8,8 @@
 // Design (B200-first, no texture references, no video-instruction min/max, no local-memory stack):
 //  * persistent grid = SMs x resident CTAs; each warp pulls rays from one global counter with a
 //    single atomicAdd per refill (ballot + popc rank, leader broadcast with shfl);
-//  * nodes are 64 B (two child AABBs + two child links): fetched as 4 x ld.global.nc.v4 per lane;
-//    Woop triangles as up to 3 x ld.global.nc.v4 with the reference's early-outs;
+//  * nodes are 64 B (two child AABBs + two child links): fetched as 2 x 256-bit ld.global.nc per lane (4 x 128-bit
+//    for a buffer that is not 64-byte aligned); Woop triangles as up to 3 x ld.global.nc.v4 with the reference's early-outs;
 //  * traversal stack: top entries in shared memory laid out [entry][thread] (bank = lane, conflict
 //    free for any mix of depths), remainder spills to a per-thread local array (rarely touched);
 //  * slab test on FMNMX3 (3-input min/max exists on sm_100a);
@@ -21,7 +21,8 @@
 // (src/rt/Util.cpp:99-127) operation for operation in IEEE fp32 (no FMA contraction, IEEE reciprocal), so
 // per-triangle hit decisions and the reported t/u/v are bit-identical to the CPU path traversing the same
 // buffers.  The slab test keeps the reference GPU form n*idir - ood (fermi...cu:120-145) with FMA: it only
-// decides which nodes are visited, never what a hit is.
+// decides which nodes are visited, never what a hit is.  FAST selects the other arithmetic the reference has: what
+// nvcc -use_fast_math makes of its GPU kernels (contracted FMAs, approximate reciprocal), bit-identical to those kernels.
 #include "nt_common.cuh"
 #include <cstdlib>
 
@@ -65,7 +66,7 @@ __device__ __forceinline__ const float4* node_ptr(const float4* nodes, int addr)
     return reinterpret_cast<const float4*>(reinterpret_cast<const char*>(nodes) + addr);
 }
 
-template <int LAYOUT, int BLOCK, int SMEM_N, bool PERSISTENT, int TRI_MODE, bool PREFETCH = false, bool WIDE = false>
+template <int LAYOUT, int BLOCK, int SMEM_N, bool PERSISTENT, bool FAST, bool WIDE>
 __global__ void __launch_bounds__(BLOCK)
 trace_kernel(int numRays, int anyHit, int fetchThreshold,
              const float4* __restrict__ rays, int4* __restrict__ results,
@@ -171,11 +172,6 @@ trace_kernel(int numRays, int anyHit, int fetchThreshold,
                     if (trav0 && trav1) {
                         if (c1min < c0min) { const int t = nodeAddr; nodeAddr = c1idx; c1idx = t; }
                         NT_PUSH(c1idx);
-                        if (PREFETCH && c1idx >= 0) {
-                            // the far child will be fetched after the near subtree: start pulling its node into L1 now
-                            const float4* far = node_ptr<LAYOUT>(nodes, c1idx);
-                            asm volatile("prefetch.global.L1 [%0];" :: "l"(far));
-                        }
                     }
                 }
 
@@ -193,20 +189,15 @@ trace_kernel(int numRays, int anyHit, int fetchThreshold,
             while (leafAddr < 0) {
                 // Woop test in exactly the operation order of Intersect::RayTriangleWoop (Util.cpp:99-127), every
                 // product and sum rounded separately (no FMA contraction) and an IEEE reciprocal, so that each
-                // accept/reject decision is bit-identical to the host reference's.
-                // TRI_MODE 0: rows 1 and 2 fetched only when needed (the reference's early-outs, least L1 traffic);
-                // TRI_MODE 1: the three rows of a triangle are requested together (one exposed latency instead of three);
-                // TRI_MODE 2: as 1, plus row 0 of the next triangle is requested before the current one is tested.
+                // accept/reject decision is bit-identical to the host reference's.  Rows 1 and 2 of a triangle are fetched
+                // only when needed (the reference's early-outs: least L1 traffic, fewest registers).
                 int triAddr = ~leafAddr;
                 float4 v00 = __ldg(woop + triAddr);
                 for (;;) {
-                    float4 v11, v22, nxt;
-                    if (TRI_MODE >= 1) { v11 = __ldg(woop + triAddr + 1); v22 = __ldg(woop + triAddr + 2); }
                     if (__float_as_int(v00.x) == (int)0x80000000) break;
-                    if (TRI_MODE == 2) nxt = __ldg(woop + triAddr + 3);
 
                     float t;
-                    if (TRI_MODE == 5) {
+                    if (FAST) {
                         // the arithmetic of the reference's GPU kernels as nvcc -use_fast_math compiles them: contracted FMAs, approximate 1/x
                         const float Oz = v00.w - origx * v00.x - origy * v00.y - origz * v00.z;
                         t = Oz * __fdividef(1.0f, dirx * v00.x + diry * v00.y + dirz * v00.z);
@@ -217,24 +208,24 @@ trace_kernel(int numRays, int anyHit, int fetchThreshold,
                     }
 
                     if (t > tmin && t < hitT) {
-                        if (TRI_MODE == 0 || TRI_MODE == 5) v11 = __ldg(woop + triAddr + 1);
+                        const float4 v11 = __ldg(woop + triAddr + 1);
                         float u;
-                        if (TRI_MODE == 5) u = (v11.w + origx * v11.x + origy * v11.y + origz * v11.z) + t * (dirx * v11.x + diry * v11.y + dirz * v11.z);
+                        if (FAST) u = (v11.w + origx * v11.x + origy * v11.y + origz * v11.z) + t * (dirx * v11.x + diry * v11.y + dirz * v11.z);
                         else {
                             const float Ou = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(v11.x, origx), __fmul_rn(v11.y, origy)), __fmul_rn(v11.z, origz)), v11.w);
                             const float Du = __fadd_rn(__fadd_rn(__fmul_rn(v11.x, dirx), __fmul_rn(v11.y, diry)), __fmul_rn(v11.z, dirz));
                             u = __fadd_rn(Ou, __fmul_rn(t, Du));
                         }
                         if (u >= 0.0f) {
-                            if (TRI_MODE == 0 || TRI_MODE == 5) v22 = __ldg(woop + triAddr + 2);
+                            const float4 v22 = __ldg(woop + triAddr + 2);
                             float v;
-                            if (TRI_MODE == 5) v = (v22.w + origx * v22.x + origy * v22.y + origz * v22.z) + t * (dirx * v22.x + diry * v22.y + dirz * v22.z);
+                            if (FAST) v = (v22.w + origx * v22.x + origy * v22.y + origz * v22.z) + t * (dirx * v22.x + diry * v22.y + dirz * v22.z);
                             else {
                                 const float Ov = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(v22.x, origx), __fmul_rn(v22.y, origy)), __fmul_rn(v22.z, origz)), v22.w);
                                 const float Dv = __fadd_rn(__fadd_rn(__fmul_rn(v22.x, dirx), __fmul_rn(v22.y, diry)), __fmul_rn(v22.z, dirz));
                                 v = __fadd_rn(Ov, __fmul_rn(t, Dv));
                             }
-                            if (v >= 0.0f && ((TRI_MODE == 5) ? (u + v) : __fadd_rn(u, v)) <= 1.0f) {
+                            if (v >= 0.0f && (FAST ? (u + v) : __fadd_rn(u, v)) <= 1.0f) {
                                 hitT = t; hitU = u; hitV = v;
                                 hitIndex = triAddr;
                                 if (anyHit) { nodeAddr = kEntrypointSentinel; break; }
@@ -242,7 +233,7 @@ trace_kernel(int numRays, int anyHit, int fetchThreshold,
                         }
                     }
                     triAddr += 3;
-                    v00 = (TRI_MODE == 2) ? nxt : __ldg(woop + triAddr);
+                    v00 = __ldg(woop + triAddr);
                 }
                 // Another leaf was postponed => process it as well.
                 leafAddr = nodeAddr;
@@ -268,27 +259,26 @@ trace_kernel(int numRays, int anyHit, int fetchThreshold,
 
 constexpr int kBlock = 128;
 
-// Tuning knobs (defaults chosen from the ncu captures in profiles/; the NT_TRACE_* environment variables exist
-// for experiments only): entries of the traversal stack kept in shared memory, and the shared-memory carveout
-// that decides how many CTAs fit next to the L1.
-struct Tuning { int smemStack; int carveout; int triMode; int fetchThreshold; };
+// Tuning knobs (defaults chosen from the ncu captures in profiles/ and the sweep in scripts/tune_trace.sh; the NT_TRACE_*
+// environment variables exist for experiments only): entries of the traversal stack kept in shared memory, the
+// shared-memory carveout that decides how many CTAs fit next to the L1, and the dynamic-fetch threshold.
+struct Tuning { int smemStack; int carveout; int fetchThreshold; };
 Tuning tuning()
 {
     static Tuning t = [] {
-        Tuning r{8, 20, 4, kDynamicFetchThreshold};      // triMode 4 = reference early-outs + 256-bit ray/node loads
+        Tuning r{8, 20, kDynamicFetchThreshold};
         if (const char* e = getenv("NT_TRACE_SMEM")) r.smemStack = atoi(e);
         if (const char* e = getenv("NT_TRACE_CARVEOUT")) r.carveout = atoi(e);
-        if (const char* e = getenv("NT_TRACE_TRI")) r.triMode = atoi(e);
         if (const char* e = getenv("NT_TRACE_FETCH")) r.fetchThreshold = atoi(e);
         return r;
     }();
     return t;
 }
 
-template <int LAYOUT, int SMEM_N, bool PERSISTENT, int TRI_MODE, bool PREFETCH = false, bool WIDE = false>
+template <int LAYOUT, int SMEM_N, bool PERSISTENT, bool FAST, bool WIDE>
 cudaError_t launch_variant(const TraceLaunch& a, int* launches)
 {
-    auto kern = trace_kernel<LAYOUT, kBlock, SMEM_N, PERSISTENT, TRI_MODE, PREFETCH, WIDE>;
+    auto kern = trace_kernel<LAYOUT, kBlock, SMEM_N, PERSISTENT, FAST, WIDE>;
     static int blocksPerSM = 0;
     if (!blocksPerSM) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, tuning().carveout);
@@ -304,33 +294,23 @@ cudaError_t launch_variant(const TraceLaunch& a, int* launches)
     return cudaGetLastError();
 }
 
-template <int LAYOUT, bool PERSISTENT, int TRI_MODE>
-cudaError_t launch_tri(const TraceLaunch& a, int* launches)
+template <int LAYOUT, bool PERSISTENT, bool FAST, bool WIDE>
+cudaError_t launch_stack(const TraceLaunch& a, int* launches)
 {
-    switch (tuning().smemStack) {
-    case 0:  return launch_variant<LAYOUT, 0, PERSISTENT, TRI_MODE>(a, launches);
-    case 4:  return launch_variant<LAYOUT, 4, PERSISTENT, TRI_MODE>(a, launches);
-    case 16: return launch_variant<LAYOUT, 16, PERSISTENT, TRI_MODE>(a, launches);
-    default: return launch_variant<LAYOUT, 8, PERSISTENT, TRI_MODE>(a, launches);
+    switch (tuning().smemStack) {            // 8 unless an experiment asks otherwise
+    case 0:  return launch_variant<LAYOUT, 0, PERSISTENT, FAST, WIDE>(a, launches);
+    case 16: return launch_variant<LAYOUT, 16, PERSISTENT, FAST, WIDE>(a, launches);
+    default: return launch_variant<LAYOUT, 8, PERSISTENT, FAST, WIDE>(a, launches);
     }
 }
 
 template <int LAYOUT, bool PERSISTENT>
 cudaError_t launch_one(const TraceLaunch& a, int* launches)
 {
-    const int triMode = a.fast ? 5 : tuning().triMode;
-    switch (triMode) {
-    case 3:  return launch_variant<LAYOUT, 8, PERSISTENT, 0, true>(a, launches);
-    case 5:  if ((reinterpret_cast<size_t>(a.rays) & 31) == 0 && (reinterpret_cast<size_t>(a.nodes) & 63) == 0)
-                 return launch_variant<LAYOUT, 8, PERSISTENT, 5, false, true>(a, launches);
-             return launch_variant<LAYOUT, 8, PERSISTENT, 5>(a, launches);
-    case 4:  if ((reinterpret_cast<size_t>(a.rays) & 31) == 0 && (reinterpret_cast<size_t>(a.nodes) & 63) == 0)
-                 return launch_variant<LAYOUT, 8, PERSISTENT, 0, false, true>(a, launches);
-             return launch_tri<LAYOUT, PERSISTENT, 0>(a, launches);
-    case 1:  return launch_tri<LAYOUT, PERSISTENT, 1>(a, launches);
-    case 2:  return launch_tri<LAYOUT, PERSISTENT, 2>(a, launches);
-    default: return launch_tri<LAYOUT, PERSISTENT, 0>(a, launches);
-    }
+    // 256-bit loads need a 32-byte aligned ray buffer and 64-byte aligned nodes (true for everything nt_mem_alloc returns)
+    const bool wide = (reinterpret_cast<size_t>(a.rays) & 31) == 0 && (reinterpret_cast<size_t>(a.nodes) & 63) == 0;
+    if (a.fast) return wide ? launch_stack<LAYOUT, PERSISTENT, true, true>(a, launches) : launch_stack<LAYOUT, PERSISTENT, true, false>(a, launches);
+    return wide ? launch_stack<LAYOUT, PERSISTENT, false, true>(a, launches) : launch_stack<LAYOUT, PERSISTENT, false, false>(a, launches);
 }
 
 } // namespace
