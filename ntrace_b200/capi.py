@@ -14,7 +14,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libntrace_b200.so")
+LIB_PATH = os.environ.get("NTRACE_B200_LIB") or os.path.join(_HERE, "libntrace_b200.so")      # override: development builds only
 
 LAYOUT_COMPACT = 4
 LAYOUT_COMPACT2 = 5

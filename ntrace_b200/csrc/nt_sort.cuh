@@ -98,18 +98,21 @@ cudaError_t exclusive_scan(const T* in, T* out, long long n, T* blockSums /* >= 
 // Stable LSD radix sort of (key, index) pairs, 8-bit digits.
 // ------------------------------------------------------------------------------------------------
 constexpr int kSortThreads = 256;
-constexpr int kSortItems = 8;                       // rounds of 32 consecutive keys per warp
+// Keys per thread (rounds of 32 consecutive keys per warp).  Measured on the 10 M-triangle builds: 8 (63 registers, 28 KB of
+// shared memory) beats 12 and 16 -- the longer runs per digit of a bigger tile do not pay for the lost occupancy.
+constexpr int kSortItems = 8;
 constexpr int kSortTile = kSortThreads * kSortItems;
 
 template <class KeyT>
 __global__ void __launch_bounds__(kSortThreads) radix_hist_kernel(const KeyT* __restrict__ keys, int n, int shift, uint* __restrict__ hist, int numBlocks)
 {
+    constexpr int ITEMS = kSortItems;
     __shared__ uint s_hist[256];
     s_hist[threadIdx.x] = 0;
     __syncthreads();
-    const int base = blockIdx.x * kSortTile;
+    const int base = blockIdx.x * (kSortThreads * ITEMS);
 #pragma unroll
-    for (int r = 0; r < kSortItems; r++) {
+    for (int r = 0; r < ITEMS; r++) {
         const int i = base + r * kSortThreads + threadIdx.x;
         if (i < n) atomicAdd(&s_hist[(uint)(keys[i] >> shift) & 255u], 1u);
     }
@@ -117,21 +120,33 @@ __global__ void __launch_bounds__(kSortThreads) radix_hist_kernel(const KeyT* __
     hist[threadIdx.x * numBlocks + blockIdx.x] = s_hist[threadIdx.x];     // digit-major: one scan gives global offsets
 }
 
+// Scatter of one pass.  Ranks: warp w owns ITEMS rounds of 32 consecutive keys; within a round MATCH.ANY groups equal digits,
+// the per-warp counters carry the running count, so the order inside a digit is the input order (stable).  The tile is then
+// put in digit order in shared memory and written out by consecutive threads, so each digit's run leaves as contiguous
+// segments instead of 32 scattered 4-byte stores per warp.
 template <class KeyT>
 __global__ void __launch_bounds__(kSortThreads) radix_scatter_kernel(const KeyT* __restrict__ keysIn, const int* __restrict__ idxIn,
                                                                      KeyT* __restrict__ keysOut, int* __restrict__ idxOut,
                                                                      int n, int shift, const uint* __restrict__ histScan, int numBlocks)
 {
+    constexpr int ITEMS = kSortItems;
+    constexpr int TILE = kSortTile;
     __shared__ uint s_cnt[kSortThreads / 32][256];
+    __shared__ uint s_digitBase[256];          // first local position of each digit
+    __shared__ uint s_outOfs[256];             // global position = s_outOfs[digit] + local position (mod 2^32)
+    __shared__ uint s_warp[kSortThreads / 32];
+    __shared__ KeyT s_key[TILE];
+    __shared__ int  s_idx[TILE];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     for (int i = threadIdx.x; i < (kSortThreads / 32) * 256; i += kSortThreads) (&s_cnt[0][0])[i] = 0;
     __syncthreads();
 
-    const int segBase = blockIdx.x * kSortTile + w * (kSortItems * 32);
-    KeyT key[kSortItems];
-    uint rank[kSortItems];
+    const int tileBase = blockIdx.x * TILE;
+    const int segBase = tileBase + w * (ITEMS * 32);
+    KeyT key[ITEMS];
+    uint rank[ITEMS];
 #pragma unroll
-    for (int r = 0; r < kSortItems; r++) {
+    for (int r = 0; r < ITEMS; r++) {
         const int i = segBase + r * 32 + lane;
         const bool valid = i < n;
         key[r] = valid ? keysIn[i] : KeyT(0);
@@ -146,20 +161,34 @@ __global__ void __launch_bounds__(kSortThreads) radix_scatter_kernel(const KeyT*
     }
     __syncthreads();
     {
-        // digit = threadIdx.x: exclusive prefix over the warps of this tile + global base of (digit, tile)
-        uint run = histScan[threadIdx.x * numBlocks + blockIdx.x];
+        // digit = threadIdx.x: exclusive prefix over the warps of this tile, then over the digits
+        const uint d = threadIdx.x;
+        uint run = 0;
 #pragma unroll
-        for (int ww = 0; ww < kSortThreads / 32; ww++) { const uint c = s_cnt[ww][threadIdx.x]; s_cnt[ww][threadIdx.x] = run; run += c; }
+        for (int ww = 0; ww < kSortThreads / 32; ww++) { const uint c = s_cnt[ww][d]; s_cnt[ww][d] = run; run += c; }
+        uint total;
+        const uint base = block_exclusive<uint>(run, s_warp, total);
+        s_digitBase[d] = base;
+        s_outOfs[d] = histScan[d * numBlocks + blockIdx.x] - base;
     }
     __syncthreads();
 #pragma unroll
-    for (int r = 0; r < kSortItems; r++) {
+    for (int r = 0; r < ITEMS; r++) {
         const int i = segBase + r * 32 + lane;
         if (i < n) {
-            const uint pos = s_cnt[w][(uint)(key[r] >> shift) & 255u] + rank[r];
-            keysOut[pos] = key[r];
-            idxOut[pos] = idxIn[i];
+            const uint d = (uint)(key[r] >> shift) & 255u;
+            const uint lp = s_digitBase[d] + s_cnt[w][d] + rank[r];
+            s_key[lp] = key[r];
+            s_idx[lp] = idxIn[i];
         }
+    }
+    __syncthreads();
+    const int count = min(TILE, n - tileBase);
+    for (int j = threadIdx.x; j < count; j += kSortThreads) {
+        const KeyT k = s_key[j];
+        const uint pos = s_outOfs[(uint)(k >> shift) & 255u] + (uint)j;
+        keysOut[pos] = k;
+        idxOut[pos] = s_idx[j];
     }
 }
 
@@ -169,7 +198,8 @@ template <class KeyT>
 cudaError_t radix_sort_pairs(KeyT* keysA, int* idxA, KeyT* keysB, int* idxB, int n, int passes,
                              uint* hist, uint* blockSums, cudaStream_t stream, int* launches)
 {
-    const int nb = (n + kSortTile - 1) / kSortTile;
+    constexpr int TILE = kSortTile;
+    const int nb = (n + TILE - 1) / TILE;
     const long long histLen = (long long)nb * 256;
     KeyT* kin = keysA; int* iin = idxA; KeyT* kout = keysB; int* iout = idxB;
     for (int pass = 0; pass < passes; pass++) {
