@@ -89,6 +89,26 @@ def test_lbvh_tiny_inputs(gpu_host, orc, n, leaf):
     _assert_same_tree(orc, (nodes, woop, idx), ref)
 
 
+@pytest.mark.parametrize("n", [2047, 2048, 2049, 4096, 6145])
+def test_lbvh_sizes_around_the_sort_tile(gpu_host, orc, n):
+    # the radix scatter stages tiles of 2048 keys in shared memory: a partly filled last tile, exactly full tiles, one key over
+    verts, tris = scenes.soup_uniform(n, seed=11, clustered=(n % 2 == 0))
+    lo, hi = scenes.bbox(verts)
+    nodes, woop, idx, keys, order, _ = _gpu_build(gpu_host, verts, tris, lo, hi, 4)
+    ref = orc.lbvh_build(verts, tris, lo, hi, hlbvh=False, leaf_size=4)
+    assert np.array_equal(keys, ref.sorted_keys) and np.array_equal(order, ref.sorted_idx)
+    _assert_same_tree(orc, (nodes, woop, idx), ref)
+
+
+def test_lbvh_full_tiles_of_one_digit(gpu_host, orc):
+    # 5000 triangles in one Morton cell: every key of two full tiles lands in the same digit bucket in all four passes
+    v, t, lo, hi = _cells_scene([(5, 6, 7), (900, 3, 512)], [5000, 300])
+    nodes, woop, idx, keys, order, _ = _gpu_build(gpu_host, v, t, lo, hi, 8)
+    ref = orc.lbvh_build(v, t, lo, hi, hlbvh=False, leaf_size=8)
+    assert np.array_equal(keys, ref.sorted_keys) and np.array_equal(order, ref.sorted_idx), "sort is not stable"
+    _assert_same_tree(orc, (nodes, woop, idx), ref)
+
+
 def test_lbvh_all_identical_keys_median_rule(gpu_host, orc):
     v, t, lo, hi = _cells_scene([(5, 6, 7)], [1000])
     nodes, woop, idx, keys, order, _ = _gpu_build(gpu_host, v, t, lo, hi, 8)
