@@ -508,6 +508,28 @@ __device__ __forceinline__ int distribute_one(const TopArgs& a, int c, int task,
     return -1;
 }
 
+// fillBins for one cluster that belongs to task t (box tb = 6 floats) of the level being prepared (emitTreeKernel.cu:735-790):
+// bin of the cluster's centre per axis, kept in clsBin for the coming distribute, and the bin's box / count updated.
+__device__ __forceinline__ void fill_bins_one(const TopArgs& a, int c, int t, const float* tb, bool inSmem, int* s_binBox, int* s_binCnt)
+{
+    const int* cb = a.clsBoxI + (size_t)c * 6;
+    const int c0 = cb[0], c1 = cb[1], c2 = cb[2], c3 = cb[3], c4 = cb[4], c5 = cb[5];
+    const float lo[3] = {i2f_ord(c0), i2f_ord(c1), i2f_ord(c2)}, hi[3] = {i2f_ord(c3), i2f_ord(c4), i2f_ord(c5)};
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const float mid = __fadd_rn(lo[k], __fdiv_rn(__fsub_rn(hi[k], lo[k]), 2.0f));
+        const float tl = tb[k], th = tb[3 + k];
+        const float step = __fdiv_rn(__fsub_rn(th, tl), 8.0f);
+        const int bid = quantise(mid, tl, step, kBins);
+        a.clsBin[c * 3 + k] = bid;
+        const int slot = (t * 3 + k) * kBins + bid;
+        int* b = inSmem ? (s_binBox + slot * 6) : (a.binBoxI + (size_t)slot * 6);
+        atomicMin(b + 0, c0); atomicMin(b + 1, c1); atomicMin(b + 2, c2);
+        atomicMax(b + 3, c3); atomicMax(b + 4, c4); atomicMax(b + 5, c5);
+        atomicAdd(inSmem ? (s_binCnt + slot) : (a.binCnt + slot), 1);
+    }
+}
+
 __global__ void __launch_bounds__(kTopThreads) hlbvh_top_kernel(TopArgs a)
 {
     namespace cg = cooperative_groups;
@@ -534,6 +556,35 @@ __global__ void __launch_bounds__(kTopThreads) hlbvh_top_kernel(TopArgs a)
     }
     grid.sync();
 
+    // Shared-memory staging of a level's bins: while a level has few tasks every cluster hammers the same handful of bins, so
+    // the block accumulates into its own copy and flushes one atomic per non-empty bin; deeper levels go straight to L2.
+    auto smemBinsInit = [&](int tasks) {
+        for (int i = threadIdx.x; i < tasks * 3 * kBins; i += kTopThreads) {
+            int* b = s_binBox + i * 6;
+            b[0] = b[1] = b[2] = f2i_ord(kF32Max); b[3] = b[4] = b[5] = f2i_ord(-kF32Max);
+            s_binCnt[i] = 0;
+        }
+        __syncthreads();
+    };
+    auto smemBinsFlush = [&](int tasks) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < tasks * 3 * kBins; i += kTopThreads) {
+            const int cnt = s_binCnt[i];
+            if (cnt == 0) continue;
+            const int* sb = s_binBox + i * 6;
+            int* b = a.binBoxI + (size_t)i * 6;
+            atomicMin(b + 0, sb[0]); atomicMin(b + 1, sb[1]); atomicMin(b + 2, sb[2]);
+            atomicMax(b + 3, sb[3]); atomicMax(b + 4, sb[4]); atomicMax(b + 5, sb[5]);
+            atomicAdd(a.binCnt + i, cnt);
+        }
+    };
+
+    // ---- fillBins of the root task (every later level is binned by the distribute phase of its parent level)
+    smemBinsInit(1);
+    for (int c = gtid; c < a.C; c += gsize) fill_bins_one(a, c, 0, a.tBox[0], true, s_binBox, s_binCnt);
+    smemBinsFlush(1);
+    grid.sync();
+
     for (;;) {
         const int T = *(volatile int*)&a.scal[0];
         if (T == 0) break;
@@ -541,51 +592,7 @@ __global__ void __launch_bounds__(kTopThreads) hlbvh_top_kernel(TopArgs a)
         const float* tBox = a.tBox[cur]; const int* tCnt = a.tCnt[cur]; const int* tId = a.tId[cur];
         const int* clsTask = a.clsTask[cur]; int* clsNext = a.clsTask[cur ^ 1];
 
-        // (bins of this level's tasks were cleared during the previous level's distribute phase / the prologue)
-
-        // ---- fillBins.  While a level has few tasks every cluster hammers the same handful of bins, so the block first
-        // accumulates into a shared-memory copy and flushes one atomic per non-empty bin; deeper levels go straight to L2.
-        const bool binsInSmem = (T <= kSmemTasks);
-        if (binsInSmem) {
-            for (int i = threadIdx.x; i < T * 3 * kBins; i += kTopThreads) {
-                int* b = s_binBox + i * 6;
-                b[0] = b[1] = b[2] = f2i_ord(kF32Max); b[3] = b[4] = b[5] = f2i_ord(-kF32Max);
-                s_binCnt[i] = 0;
-            }
-            __syncthreads();
-        }
-        for (int c = gtid; c < a.C; c += gsize) {
-            const int t = clsTask[c];
-            if (t < 0) continue;
-            const int* cb = a.clsBoxI + (size_t)c * 6;
-            float lo[3], hi[3];
-            for (int k = 0; k < 3; k++) { lo[k] = i2f_ord(cb[k]); hi[k] = i2f_ord(cb[3 + k]); }
-            for (int k = 0; k < 3; k++) {
-                const float mid = __fadd_rn(lo[k], __fdiv_rn(__fsub_rn(hi[k], lo[k]), 2.0f));
-                const float tl = tBox[t * 6 + k], th = tBox[t * 6 + 3 + k];
-                const float step = __fdiv_rn(__fsub_rn(th, tl), 8.0f);
-                const int bid = quantise(mid, tl, step, kBins);
-                a.clsBin[c * 3 + k] = bid;
-                const int slot = (t * 3 + k) * kBins + bid;
-                int* b = binsInSmem ? (s_binBox + slot * 6) : (a.binBoxI + (size_t)slot * 6);
-                atomicMin(b + 0, cb[0]); atomicMin(b + 1, cb[1]); atomicMin(b + 2, cb[2]);
-                atomicMax(b + 3, cb[3]); atomicMax(b + 4, cb[4]); atomicMax(b + 5, cb[5]);
-                atomicAdd(binsInSmem ? (s_binCnt + slot) : (a.binCnt + slot), 1);
-            }
-        }
-        if (binsInSmem) {
-            __syncthreads();
-            for (int i = threadIdx.x; i < T * 3 * kBins; i += kTopThreads) {
-                const int cnt = s_binCnt[i];
-                if (cnt == 0) continue;
-                const int* sb = s_binBox + i * 6;
-                int* b = a.binBoxI + (size_t)i * 6;
-                atomicMin(b + 0, sb[0]); atomicMin(b + 1, sb[1]); atomicMin(b + 2, sb[2]);
-                atomicMax(b + 3, sb[3]); atomicMax(b + 4, sb[4]); atomicMax(b + 5, sb[5]);
-                atomicAdd(a.binCnt + i, cnt);
-            }
-        }
-        grid.sync();
+        // (the bins of this level's tasks were filled by the previous level's distribute phase / the prologue)
 
         // ---- findSplit, phase a: per task decision + block-local offsets of the child tasks
         const int perBlock = (T + gridDim.x - 1) / gridDim.x;
@@ -684,17 +691,29 @@ __global__ void __launch_bounds__(kTopThreads) hlbvh_top_kernel(TopArgs a)
             int* w = a.topNodes + (size_t)tId[t] * 16;
             w[12] = l; w[13] = r; w[14] = a.rAxis[t]; w[15] = 0;
         }
+        // initBins for the next level's tasks: this level's bins were last read in phase a (before the barrier above); what
+        // distribute consults are the per-task results in rSplit / rAxis / rCnt* and the per-cluster bin ids in clsBin
+        for (int i = gtid; i < created * 3 * kBins; i += gsize) {
+            int* b = a.binBoxI + (size_t)i * 6;
+            b[0] = b[1] = b[2] = f2i_ord(kF32Max); b[3] = b[4] = b[5] = f2i_ord(-kF32Max);
+            a.binCnt[i] = 0;
+        }
         grid.sync();
         if (gtid == 0) { a.scal[0] = created; a.scal[1] = written + created; }      // read again only after the next grid.sync
 
-        // ---- distribute: plane splits per cluster; object-split fallback per task with clusters ranked by index
+        // ---- distribute + fillBins of the next level: plane splits per cluster; object-split fallback per task with clusters
+        // ranked by index.  A cluster that descends is binned into its child task right away (the child boxes were written in phase b).
+        const bool nextInSmem = (created <= kSmemTasks);
+        if (nextInSmem) smemBinsInit(created);
         for (int c = gtid; c < a.C; c += gsize) {
             const int t = clsTask[c];
             if (t < 0) { clsNext[c] = -1; continue; }
             const int split = a.rSplit[t];
             if (split < 0) continue;                       // handled below
             const bool goLeft = a.clsBin[c * 3 + a.rAxis[t]] <= split;
-            clsNext[c] = distribute_one(a, c, t, goLeft, a.rCntL[t], a.rCntR[t], tId[t]);
+            const int nt = distribute_one(a, c, t, goLeft, a.rCntL[t], a.rCntR[t], tId[t]);
+            clsNext[c] = nt;
+            if (nt >= 0) fill_bins_one(a, c, nt, oBox + (size_t)nt * 6, nextInSmem, s_binBox, s_binCnt);
         }
         {
             const int lane = threadIdx.x & 31;
@@ -709,19 +728,15 @@ __global__ void __launch_bounds__(kTopThreads) hlbvh_top_kernel(TopArgs a)
                     const unsigned mask = __ballot_sync(0xffffffffu, m);
                     if (m) {
                         const int rank = seen + __popc(mask & ((1u << lane) - 1u));      // arrival order == cluster index order
-                        clsNext[c] = distribute_one(a, c, t, rank <= cntL - 1, cntL, cntR, topId);
+                        const int nt = distribute_one(a, c, t, rank <= cntL - 1, cntL, cntR, topId);
+                        clsNext[c] = nt;
+                        if (nt >= 0) fill_bins_one(a, c, nt, oBox + (size_t)nt * 6, nextInSmem, s_binBox, s_binCnt);
                     }
                     seen += __popc(mask);
                 }
             }
         }
-        // ---- initBins for the next level's tasks (their bins are not read by anything in this phase: the bins consulted
-        // by distribute are per-task results copied into rSplit/rAxis/rCnt*, and clsBin holds the per-cluster bin ids)
-        for (int i = gtid; i < created * 3 * kBins; i += gsize) {
-            int* b = a.binBoxI + (size_t)i * 6;
-            b[0] = b[1] = b[2] = f2i_ord(kF32Max); b[3] = b[4] = b[5] = f2i_ord(-kF32Max);
-            a.binCnt[i] = 0;
-        }
+        if (nextInSmem) smemBinsFlush(created);
         grid.sync();
         cur ^= 1;
     }
