@@ -453,6 +453,7 @@ __global__ void __launch_bounds__(256) cluster_box_kernel(int n, const uint* __r
 constexpr int kBins = 8;            // BIN_CNT (emitTreeKernel.cuh:9)
 constexpr int kTopThreads = 256;
 constexpr int kSmemTasks = 32;      // levels with at most this many tasks bin through shared memory first
+constexpr int kTrackFirst = 64;     // tasks with at most this many clusters know their lowest cluster index (one atomicMin per member)
 
 struct TopArgs {
     int C, leafSize, linkMul;
@@ -462,6 +463,7 @@ struct TopArgs {
     int* clsParent;           // C : topNode*2 + side once the cluster terminates
     float* tBox[2];           // task boxes, 6 floats per task (lo xyz, hi xyz)
     int* tCnt[2]; int* tId[2];
+    int* tFirst[2];           // lowest cluster index of each task: where the object-split fallback starts looking for its members
     int* rSplit; int* rAxis; int* rCntL; int* rCntR; int* rLocalOfs; int* rChild; float* rBoxes;   // per task, current level
     int* binBoxI; int* binCnt;
     int* blockSum;
@@ -544,7 +546,7 @@ __global__ void __launch_bounds__(kTopThreads) hlbvh_top_kernel(TopArgs a)
 
     if (gtid == 0) {
         for (int k = 0; k < 3; k++) { a.tBox[0][k] = a.sceneLo[k]; a.tBox[0][3 + k] = a.sceneHi[k]; }
-        a.tCnt[0][0] = a.C; a.tId[0][0] = 0;
+        a.tCnt[0][0] = a.C; a.tId[0][0] = 0; a.tFirst[0][0] = 0;
         a.topParent[0] = -1;
         a.scal[0] = 1; a.scal[1] = 1;
     }
@@ -585,8 +587,20 @@ __global__ void __launch_bounds__(kTopThreads) hlbvh_top_kernel(TopArgs a)
     smemBinsFlush(1);
     grid.sync();
 
+#ifdef NT_TOP_TIMING
+    unsigned long long tA = 0, tB = 0, tD = 0, t_prev, t_now; int levels = 0, smallLevels = 0; unsigned long long tSmall = 0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_prev));
+    const unsigned long long t_start = t_prev;
+#define NT_MARK(acc) do { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_now)); acc += t_now - t_prev; t_prev = t_now; } while (0)
+#else
+#define NT_MARK(acc) do { } while (0)
+#endif
     for (;;) {
         const int T = *(volatile int*)&a.scal[0];
+#ifdef NT_TOP_TIMING
+        if (T == 0 && gtid == 0) printf("top: levels %d (T<=148: %d, %llu ns) phaseA %llu ns phaseB %llu ns distribute+fill %llu ns total %llu ns\n", levels, smallLevels, tSmall, tA, tB, tD, t_prev - t_start);
+        levels++; const unsigned long long t_lvl = t_prev;
+#endif
         if (T == 0) break;
         const int written = *(volatile int*)&a.scal[1];
         const float* tBox = a.tBox[cur]; const int* tCnt = a.tCnt[cur]; const int* tId = a.tId[cur];
@@ -653,6 +667,7 @@ __global__ void __launch_bounds__(kTopThreads) hlbvh_top_kernel(TopArgs a)
         }
         if (threadIdx.x == 0) a.blockSum[blockIdx.x] = carry;
         grid.sync();
+        NT_MARK(tA);
 
         // ---- findSplit, phase b: global offsets, child tasks, node links
         {
@@ -667,7 +682,7 @@ __global__ void __launch_bounds__(kTopThreads) hlbvh_top_kernel(TopArgs a)
             __syncthreads();
         }
         const int blockBase = s_red[0], created = s_red[1];
-        float* oBox = a.tBox[cur ^ 1]; int* oCnt = a.tCnt[cur ^ 1]; int* oId = a.tId[cur ^ 1];
+        float* oBox = a.tBox[cur ^ 1]; int* oCnt = a.tCnt[cur ^ 1]; int* oId = a.tId[cur ^ 1]; int* oFirst = a.tFirst[cur ^ 1];
         for (int t = t0 + threadIdx.x; t < t1; t += kTopThreads) {
             const int ofs = blockBase + a.rLocalOfs[t];
             const int idN = written + ofs;
@@ -677,14 +692,14 @@ __global__ void __launch_bounds__(kTopThreads) hlbvh_top_kernel(TopArgs a)
             if (cntL > 1) {
                 l = idN * a.linkMul;
                 for (int k = 0; k < 6; k++) oBox[(size_t)ofs * 6 + k] = bx[k];
-                oCnt[ofs] = cntL; oId[ofs] = idN;
+                oCnt[ofs] = cntL; oId[ofs] = idN; oFirst[ofs] = (cntL <= kTrackFirst) ? 0x7fffffff : 0;
                 a.topParent[idN] = top_parent_code(tId[t], 0);
                 val = 1;
             }
             if (cntR > 1) {
                 r = (idN + val) * a.linkMul;
                 for (int k = 0; k < 6; k++) oBox[(size_t)(ofs + val) * 6 + k] = bx[6 + k];
-                oCnt[ofs + val] = cntR; oId[ofs + val] = idN + val;
+                oCnt[ofs + val] = cntR; oId[ofs + val] = idN + val; oFirst[ofs + val] = (cntR <= kTrackFirst) ? 0x7fffffff : 0;
                 a.topParent[idN + val] = top_parent_code(tId[t], 1);
             }
             a.rChild[t] = ofs;
@@ -699,6 +714,7 @@ __global__ void __launch_bounds__(kTopThreads) hlbvh_top_kernel(TopArgs a)
             a.binCnt[i] = 0;
         }
         grid.sync();
+        NT_MARK(tB);
         if (gtid == 0) { a.scal[0] = created; a.scal[1] = written + created; }      // read again only after the next grid.sync
 
         // ---- distribute + fillBins of the next level: plane splits per cluster; object-split fallback per task with clusters
@@ -711,26 +727,36 @@ __global__ void __launch_bounds__(kTopThreads) hlbvh_top_kernel(TopArgs a)
             const int split = a.rSplit[t];
             if (split < 0) continue;                       // handled below
             const bool goLeft = a.clsBin[c * 3 + a.rAxis[t]] <= split;
-            const int nt = distribute_one(a, c, t, goLeft, a.rCntL[t], a.rCntR[t], tId[t]);
+            const int cntL = a.rCntL[t], cntR = a.rCntR[t];
+            const int nt = distribute_one(a, c, t, goLeft, cntL, cntR, tId[t]);
             clsNext[c] = nt;
-            if (nt >= 0) fill_bins_one(a, c, nt, oBox + (size_t)nt * 6, nextInSmem, s_binBox, s_binCnt);
+            if (nt >= 0) {
+                if ((goLeft ? cntL : cntR) <= kTrackFirst) atomicMin(oFirst + nt, c);
+                fill_bins_one(a, c, nt, oBox + (size_t)nt * 6, nextInSmem, s_binBox, s_binCnt);
+            }
         }
         {
             const int lane = threadIdx.x & 31;
             const int warp = gtid >> 5, nwarps = gsize >> 5;
+            const int* tFirst = a.tFirst[cur];
             for (int t = warp; t < T; t += nwarps) {
                 if (a.rSplit[t] >= 0) continue;
-                const int cntL = a.rCntL[t], cntR = a.rCntR[t], topId = tId[t];
+                // the task's clusters, in index order, lie between its lowest member and wherever the last of its tCnt members is
+                const int cntL = a.rCntL[t], cntR = a.rCntR[t], topId = tId[t], members = tCnt[t];
                 int seen = 0;
-                for (int base = 0; base < a.C; base += 32) {
+                for (int base = tFirst[t] & ~31; base < a.C && seen < members; base += 32) {
                     const int c = base + lane;
                     const bool m = (c < a.C) && (clsTask[c] == t);
                     const unsigned mask = __ballot_sync(0xffffffffu, m);
                     if (m) {
                         const int rank = seen + __popc(mask & ((1u << lane) - 1u));      // arrival order == cluster index order
-                        const int nt = distribute_one(a, c, t, rank <= cntL - 1, cntL, cntR, topId);
+                        const bool goLeft = rank <= cntL - 1;
+                        const int nt = distribute_one(a, c, t, goLeft, cntL, cntR, topId);
                         clsNext[c] = nt;
-                        if (nt >= 0) fill_bins_one(a, c, nt, oBox + (size_t)nt * 6, nextInSmem, s_binBox, s_binCnt);
+                        if (nt >= 0) {
+                            if ((goLeft ? cntL : cntR) <= kTrackFirst) atomicMin(oFirst + nt, c);
+                            fill_bins_one(a, c, nt, oBox + (size_t)nt * 6, nextInSmem, s_binBox, s_binCnt);
+                        }
                     }
                     seen += __popc(mask);
                 }
@@ -738,6 +764,10 @@ __global__ void __launch_bounds__(kTopThreads) hlbvh_top_kernel(TopArgs a)
         }
         if (nextInSmem) smemBinsFlush(created);
         grid.sync();
+        NT_MARK(tD);
+#ifdef NT_TOP_TIMING
+        if (T <= 148) { smallLevels++; tSmall += t_prev - t_lvl; }
+#endif
         cur ^= 1;
     }
 }
@@ -910,7 +940,7 @@ struct Scratch {
     DevBuf keptGap;                          // kept gaps (inner nodes) in rank order
     // HLBVH
     DevBuf clsHead, clusterOf, clsStart, clsBox, clsTask0, clsTask1, clsBin, clsParent;
-    DevBuf tBox0, tBox1, tCnt0, tCnt1, tId0, tId1, rInts, rBoxes, binBox, binCnt, blockSum, topNodes, topParent, topCounters;
+    DevBuf tBox0, tBox1, tCnt0, tCnt1, tId0, tId1, tFirst0, tFirst1, rInts, rBoxes, binBox, binCnt, blockSum, topNodes, topParent, topCounters;
 };
 Scratch g_scratch;
 
@@ -1004,6 +1034,7 @@ cudaError_t build_bvh_device(const float* dVerts, int numVerts, const int* dTris
         NT_TRY(sc.tBox0.reserve(maxTasks * 24)); NT_TRY(sc.tBox1.reserve(maxTasks * 24));
         NT_TRY(sc.tCnt0.reserve(maxTasks * 4)); NT_TRY(sc.tCnt1.reserve(maxTasks * 4));
         NT_TRY(sc.tId0.reserve(maxTasks * 4)); NT_TRY(sc.tId1.reserve(maxTasks * 4));
+        NT_TRY(sc.tFirst0.reserve(maxTasks * 4)); NT_TRY(sc.tFirst1.reserve(maxTasks * 4));
         NT_TRY(sc.rInts.reserve(maxTasks * 6 * 4)); NT_TRY(sc.rBoxes.reserve(maxTasks * 48));
         NT_TRY(sc.binBox.reserve(maxTasks * 3 * kBins * 24)); NT_TRY(sc.binCnt.reserve(maxTasks * 3 * kBins * 4));
         NT_TRY(sc.topNodes.reserve((size_t)C * 64)); NT_TRY(sc.topParent.reserve((size_t)C * 4)); NT_TRY(sc.topCounters.reserve((size_t)C * 4));
@@ -1033,6 +1064,7 @@ cudaError_t build_bvh_device(const float* dVerts, int numVerts, const int* dTris
         ta.tBox[0] = sc.tBox0.as<float>(); ta.tBox[1] = sc.tBox1.as<float>();
         ta.tCnt[0] = sc.tCnt0.as<int>(); ta.tCnt[1] = sc.tCnt1.as<int>();
         ta.tId[0] = sc.tId0.as<int>(); ta.tId[1] = sc.tId1.as<int>();
+        ta.tFirst[0] = sc.tFirst0.as<int>(); ta.tFirst[1] = sc.tFirst1.as<int>();
         int* ri = sc.rInts.as<int>();
         ta.rSplit = ri; ta.rAxis = ri + maxTasks; ta.rCntL = ri + 2 * maxTasks; ta.rCntR = ri + 3 * maxTasks;
         ta.rLocalOfs = ri + 4 * maxTasks; ta.rChild = ri + 5 * maxTasks;
