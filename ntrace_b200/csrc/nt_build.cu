@@ -525,10 +525,20 @@ __device__ __forceinline__ void fill_bins_one(const TopArgs& a, int c, int t, co
         const int bid = quantise(mid, tl, step, kBins);
         a.clsBin[c * 3 + k] = bid;
         const int slot = (t * 3 + k) * kBins + bid;
-        int* b = inSmem ? (s_binBox + slot * 6) : (a.binBoxI + (size_t)slot * 6);
-        atomicMin(b + 0, c0); atomicMin(b + 1, c1); atomicMin(b + 2, c2);
-        atomicMax(b + 3, c3); atomicMax(b + 4, c4); atomicMax(b + 5, c5);
-        atomicAdd(inSmem ? (s_binCnt + slot) : (a.binCnt + slot), 1);
+        if (inSmem) {
+            int* b = s_binBox + slot * 6;
+            atomicMin(b + 0, c0); atomicMin(b + 1, c1); atomicMin(b + 2, c2);
+            atomicMax(b + 3, c3); atomicMax(b + 4, c4); atomicMax(b + 5, c5);
+            atomicAdd(s_binCnt + slot, 1);
+        } else {
+            // a bin only ever shrinks / grows within a level, so a value read from L2 that already covers ours makes the atomic
+            // redundant (a stale read can only cost an unnecessary atomic, never skip a necessary one)
+            int* b = a.binBoxI + (size_t)slot * 6;
+            const int2 q0 = __ldcg(reinterpret_cast<const int2*>(b)), q1 = __ldcg(reinterpret_cast<const int2*>(b) + 1), q2 = __ldcg(reinterpret_cast<const int2*>(b) + 2);
+            if (c0 < q0.x) atomicMin(b + 0, c0); if (c1 < q0.y) atomicMin(b + 1, c1); if (c2 < q1.x) atomicMin(b + 2, c2);
+            if (c3 > q1.y) atomicMax(b + 3, c3); if (c4 > q2.x) atomicMax(b + 4, c4); if (c5 > q2.y) atomicMax(b + 5, c5);
+            atomicAdd(a.binCnt + slot, 1);
+        }
     }
 }
 
