@@ -613,7 +613,7 @@ __global__ void __launch_bounds__(kTopThreads) hlbvh_top_kernel(TopArgs a)
 #endif
         if (T == 0) break;
         const int written = *(volatile int*)&a.scal[1];
-        const float* tBox = a.tBox[cur]; const int* tCnt = a.tCnt[cur]; const int* tId = a.tId[cur];
+        const int* tCnt = a.tCnt[cur]; const int* tId = a.tId[cur];
         const int* clsTask = a.clsTask[cur]; int* clsNext = a.clsTask[cur ^ 1];
 
         // (the bins of this level's tasks were filled by the previous level's distribute phase / the prologue)
