@@ -107,17 +107,30 @@ template <class KeyT>
 __global__ void __launch_bounds__(kSortThreads) radix_hist_kernel(const KeyT* __restrict__ keys, int n, int shift, uint* __restrict__ hist, int numBlocks)
 {
     constexpr int ITEMS = kSortItems;
-    __shared__ uint s_hist[256];
-    s_hist[threadIdx.x] = 0;
+    // one sub-histogram per warp: the keys of a tile often share a few digits (Morton codes of neighbouring triangles), and
+    // eight warps hammering the same shared-memory counters serialise
+    __shared__ uint s_hist[kSortThreads / 32][256];
+    const int w = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < kSortThreads / 32; i++) s_hist[i][threadIdx.x] = 0;
     __syncthreads();
     const int base = blockIdx.x * (kSortThreads * ITEMS);
+    KeyT k[ITEMS];
 #pragma unroll
     for (int r = 0; r < ITEMS; r++) {
         const int i = base + r * kSortThreads + threadIdx.x;
-        if (i < n) atomicAdd(&s_hist[(uint)(keys[i] >> shift) & 255u], 1u);
+        k[r] = (i < n) ? keys[i] : KeyT(0);
+    }
+#pragma unroll
+    for (int r = 0; r < ITEMS; r++) {
+        const int i = base + r * kSortThreads + threadIdx.x;
+        if (i < n) atomicAdd(&s_hist[w][(uint)(k[r] >> shift) & 255u], 1u);
     }
     __syncthreads();
-    hist[threadIdx.x * numBlocks + blockIdx.x] = s_hist[threadIdx.x];     // digit-major: one scan gives global offsets
+    uint sum = 0;
+#pragma unroll
+    for (int i = 0; i < kSortThreads / 32; i++) sum += s_hist[i][threadIdx.x];
+    hist[threadIdx.x * numBlocks + blockIdx.x] = sum;                     // digit-major: one scan gives global offsets
 }
 
 // Scatter of one pass.  Ranks: warp w owns ITEMS rounds of 32 consecutive keys; within a round MATCH.ANY groups equal digits,
