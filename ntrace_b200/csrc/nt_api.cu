@@ -277,6 +277,8 @@ void nt_shutdown(void)
                       &g.stC, &g.stD, &g.stE, &g.counters, &g.pixelTable, &g.sceneVerts, &g.sceneTris,
                       &g.srcNodes, &g.srcWoop, &g.srcIdx, &g.layoutScratch};
     for (DevBuf* b : bufs) b->release();
+    release_build_scratch();
+    release_sort_scratch();
     for (int i = 0; i < Context::kAsyncSlots; i++) {
         g.async[i].rays.release(); g.async[i].results.release();
         cudaEventDestroy(g.async[i].evIn); cudaEventDestroy(g.async[i].evKa); cudaEventDestroy(g.async[i].evKb); cudaEventDestroy(g.async[i].evOut);

@@ -953,8 +953,16 @@ struct Scratch {
     DevBuf tBox0, tBox1, tCnt0, tCnt1, tId0, tId1, tFirst0, tFirst1, rInts, rBoxes, binBox, binCnt, blockSum, topNodes, topParent, topCounters;
 };
 Scratch g_scratch;
+static_assert(sizeof(Scratch) % sizeof(DevBuf) == 0, "Scratch holds DevBuf members only");
 
 } // namespace
+
+// nt_shutdown: the grow-only scratch belongs to the device it was allocated on
+void release_build_scratch()
+{
+    DevBuf* b = reinterpret_cast<DevBuf*>(&g_scratch);
+    for (size_t i = 0; i < sizeof(Scratch) / sizeof(DevBuf); i++) b[i].release();
+}
 
 cudaError_t build_bvh_device(const float* dVerts, int numVerts, const int* dTris, int n,
                              const BuildParams& p, BuildOutput& out, cudaStream_t stream,

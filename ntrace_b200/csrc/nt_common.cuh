@@ -97,6 +97,9 @@ struct BuildOutput {          // device buffers owned by the context
     size_t nodeBytes, woopBytes, idxBytes;
     DevBuf* sortedKeys; DevBuf* sortedIdx;   // kept for nt_bvh_build_debug
 };
+// nt_shutdown: free the grow-only scratch of the builder / the ray sorter (it belongs to the device it was allocated on)
+void release_build_scratch();
+void release_sort_scratch();
 // verts/tris are device pointers. Returns cudaSuccess and fills sizes; launches counted into *outLaunches.
 cudaError_t build_bvh_device(const float* dVerts, int numVerts, const int* dTris, int numTris,
                              const BuildParams& p, BuildOutput& out, cudaStream_t stream,

@@ -100,8 +100,15 @@ __global__ void __launch_bounds__(256) ray_reorder_kernel(int n, const int* __re
 
 struct SortScratch { DevBuf keysA, keysB, idxA, idxB, hist, blockSums, box, oldRays, oldS2I; };
 SortScratch g_ss;
+static_assert(sizeof(SortScratch) % sizeof(DevBuf) == 0, "SortScratch holds DevBuf members only");
 
 } // namespace
+
+void release_sort_scratch()
+{
+    DevBuf* b = reinterpret_cast<DevBuf*>(&g_ss);
+    for (size_t i = 0; i < sizeof(SortScratch) / sizeof(DevBuf); i++) b[i].release();
+}
 
 cudaError_t ray_sort_device(float4* rays, int* idToSlot, int* slotToID, int n, cudaStream_t stream, int numSMs, int* outLaunches)
 {
