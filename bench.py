@@ -226,9 +226,11 @@ def run_b200(args):
     counted_step = sum(counted.values())
     ray_bytes = sum(b[2] for b in batches) * 32
 
+    res_alt = [res_dev, torch.empty_like(res_dev)] if args.overlap else [res_dev, res_dev]
+
     def step():
-        for _, rays, n, closest in batches:
-            capi.trace_batch(rays, res_dev, n, closest)
+        for i, (_, rays, n, closest) in enumerate(batches):
+            capi.trace_batch(rays, res_alt[i & 1], n, closest)
 
     def barrier():
         if world > 1:
@@ -237,7 +239,7 @@ def run_b200(args):
         capi.synchronize()
 
     # ---- device-timed region: W warm-up steps, then exactly K steps between two events on the launching stream
-    capi.set_deferred(True)
+    capi.set_deferred(2 if args.overlap else 1)
     for _ in range(args.warmup):
         step()
     barrier()
@@ -348,6 +350,8 @@ def run_b200(args):
                                    "1024x768, <=1Mi rays/batch, GPU %s leaf 8%s" % ("HLBVH(hlbvhBits %d)" % args.hlbvh_bits if args.builder == "hlbvh" else "LBVH", ", SAH-guided collapse" if args.collapse else ""),
                        "rays_traced_per_step_per_gpu": int(sum(traced.values())), "rays_counted_per_step_per_gpu": int(counted_step),
                        "batches_per_step": n_launch_step, "kernel": "b200_persistent_speculative_while_while",
+                       "submission": ("nt_set_deferred(2): the step's launches are queued on two kernel streams, consecutive batches overlap at their tails"
+                                      if args.overlap else "nt_set_deferred(1): the step's launches are queued on one stream"),
                        "l2": "inputs exceed L2: %.0f MB of rays per step stream from HBM; the %.0f MB BVH is reused within a frame by design"
                              % (ray_bytes / 1e6, (node_b + woop_b + idx_b) / 1e6),
                        "parallelism": "ray batches sharded per GPU, BVH replicated by NCCL broadcast" if world > 1 else "single GPU"},
@@ -529,6 +533,8 @@ def main():
                     help="HLBVHParams.hlbvhBits for --builder hlbvh (reference Renderer default 4; 2 = finer SAH top level: better tree, +1 ms build)")
     ap.add_argument("--collapse", type=int, default=1, choices=[0, 1],
                     help="leaf formation of the GPU builder: 1 = SAH-guided collapse (north_star pipeline, maxLeaf 8), 0 = the reference's count rule")
+    ap.add_argument("--overlap", type=int, default=1, help="1 (default): the device-timed leg queues its launches on two kernel streams "
+                                                            "(nt_set_deferred(2)); 0: one stream, every batch waits for the tail of the one before")
     ap.add_argument("--profile", action="store_true", help="dev: only the device-timed region (for runs under ncu); prints no JSON")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -16,7 +16,7 @@
  *     PCIe, pageable ones are staged through the library's own device buffers;
  *   - calls are synchronous: when a call returns its outputs are complete
  *     (reference: CudaKernel::launchTimed syncs, src/framework/gpu/CudaKernel.cpp:188-221).  The two opt-in exceptions
- *     are nt_set_deferred(1) (device buffers only) and nt_trace_batch_async / nt_trace_wait;
+ *     are nt_set_deferred(1 / 2) (device buffers only) and nt_trace_batch_async / nt_trace_wait;
  *   - one device per process (reference: one CUDA context, CudaModule.hpp:92-97); multi-GPU runs
  *     use one process per GPU and replicate the BVH (nt_bvh_device_ptrs + NCCL broadcast in the host);
  *   - not re-entrant: one caller thread at a time (guarded by an internal mutex);
@@ -70,8 +70,13 @@ int nt_event_record(int slot);
 int nt_event_elapsed(int slotA, int slotB, float* outSeconds);
 /* Submission mode.  0 (default) = reference behaviour, every call returns with its outputs complete.
  * 1 = deferred: nt_trace_batch on DEVICE buffers only enqueues (outSeconds = 0) and nt_synchronize() waits;
- * calls with host buffers stay synchronous. */
-int nt_set_deferred(int enabled);
+ * calls with host buffers stay synchronous.
+ * 2 = deferred and overlapped: as 1, and consecutive launches alternate between two kernel streams, so that the CTAs of
+ * the next batch move in while the persistent CTAs of the current one run out of rays (the batches of a frame are
+ * independent once the primary results exist; the reference traces them one after the other, Renderer.cpp:405-579).
+ * A launch is ordered after everything queued before it; every other call of this API waits for the launches in flight
+ * before it enqueues or reads anything, so only the result buffers of two CONSECUTIVE nt_trace_batch calls must differ. */
+int nt_set_deferred(int mode);
 int nt_synchronize(void);
 
 /* ---- kernel selection: CudaBVHTracer::setKernel + queryConfig (CudaBVHTracer.cpp:52-84) --- */

@@ -112,8 +112,10 @@ def event_elapsed(a: int, b: int) -> float:
     return float(sec.value)
 
 
-def set_deferred(enabled: bool):
-    _check(lib().nt_set_deferred(C.c_int(1 if enabled else 0)))
+def set_deferred(enabled):
+    """False / 0: synchronous calls; True / 1: launches are queued on the main stream; 2: queued launches alternate between two
+    kernel streams so that consecutive batches overlap at their tails (batches in flight need distinct result buffers)."""
+    _check(lib().nt_set_deferred(C.c_int(int(enabled))))
 
 
 def synchronize():

@@ -54,6 +54,12 @@ struct Context {
     cudaStream_t sIn = nullptr, sOut = nullptr;
     cudaEvent_t evIn[kMaxChunks] = {}, evKa[kMaxChunks] = {}, evKb[kMaxChunks] = {};
     bool deferred = false;
+    // deferred mode 2: consecutive launches alternate between two kernel streams, so the CTAs of the next batch move in as the
+    // persistent CTAs of the current one run out of rays (the tail of one launch overlaps the head of the next)
+    bool overlap = false, overlapPending = false;
+    int overlapNext = 0;
+    cudaStream_t kStream[2] = {};
+    cudaEvent_t kDone[2] = {}, kFork = nullptr;
     int64_t launches = 0;
     // asynchronous submission (nt_trace_batch_async / nt_trace_wait): per-slot staging + events
     static constexpr int kAsyncSlots = 4;
@@ -165,10 +171,20 @@ int ensure_traversal_form()
     return 0;
 }
 
-int require_init()
+// every entry point but an overlapped deferred launch orders the main stream behind the launches still in flight on the two
+// kernel streams (deferred mode 2), so that whatever it enqueues or waits for sees their results
+int join_kernel_streams()
+{
+    if (!g.overlapPending) return 0;
+    for (int k = 0; k < 2; k++) NT_CUDA(cudaStreamWaitEvent(g.stream, g.kDone[k], 0));
+    g.overlapPending = false;
+    return 0;
+}
+
+int require_init(bool join = true)
 {
     if (!g.inited) { set_error("ntrace_b200: nt_init() has not been called (no CUDA device selected; there is no CPU fallback)"); return 1; }
-    return 0;
+    return join ? join_kernel_streams() : 0;
 }
 
 // index -> pixel table: 8x8 blocks in Morton order, Morton order inside a block, then the bottom
@@ -244,6 +260,11 @@ int nt_init(int device_ordinal)
     NT_CUDA(cudaEventCreate(&g.evA));
     NT_CUDA(cudaEventCreate(&g.evB));
     for (int i = 0; i < 8; i++) NT_CUDA(cudaEventCreate(&g.userEv[i]));
+    for (int k = 0; k < 2; k++) {
+        NT_CUDA(cudaStreamCreateWithFlags(&g.kStream[k], cudaStreamNonBlocking));
+        NT_CUDA(cudaEventCreateWithFlags(&g.kDone[k], cudaEventDisableTiming));
+    }
+    NT_CUDA(cudaEventCreateWithFlags(&g.kFork, cudaEventDisableTiming));
     NT_CUDA(cudaStreamCreateWithFlags(&g.sIn, cudaStreamNonBlocking));
     NT_CUDA(cudaStreamCreateWithFlags(&g.sOut, cudaStreamNonBlocking));
     for (int i = 0; i < Context::kMaxChunks; i++) {
@@ -273,6 +294,8 @@ void nt_shutdown(void)
     cudaStreamSynchronize(g.stream);
     cudaStreamSynchronize(g.sIn);
     cudaStreamSynchronize(g.sOut);
+    for (int k = 0; k < 2; k++) { cudaStreamSynchronize(g.kStream[k]); cudaStreamDestroy(g.kStream[k]); cudaEventDestroy(g.kDone[k]); }
+    cudaEventDestroy(g.kFork);
     DevBuf* bufs[] = {&g.nodes, &g.woop, &g.triIndex, &g.sortedKeys, &g.sortedIdx, &g.stRays, &g.stResults, &g.stA, &g.stB,
                       &g.stC, &g.stD, &g.stE, &g.counters, &g.pixelTable, &g.sceneVerts, &g.sceneTris,
                       &g.srcNodes, &g.srcWoop, &g.srcIdx, &g.layoutScratch};
@@ -372,12 +395,14 @@ int nt_event_elapsed(int slotA, int slotB, float* outSeconds)
     return 0;
 }
 
-int nt_set_deferred(int enabled)
+int nt_set_deferred(int mode)
 {
     std::lock_guard<std::mutex> lock(g_mutex);
     if (require_init()) return 1;
-    if (!enabled && g.deferred) NT_CUDA(cudaStreamSynchronize(g.stream));
-    g.deferred = enabled != 0;
+    if (mode < 0 || mode > 2) { set_error("ntrace_b200: submission mode must be 0, 1 or 2"); return 1; }
+    if (!mode && g.deferred) NT_CUDA(cudaStreamSynchronize(g.stream));         // (require_init joined the kernel streams)
+    g.deferred = mode != 0;
+    g.overlap = mode == 2;
     return 0;
 }
 
@@ -616,7 +641,8 @@ int nt_trace_batch(const float* rays, int32_t* results, int numRays, int needClo
 {
     std::lock_guard<std::mutex> lock(g_mutex);
     if (outSeconds) *outSeconds = 0.0f;
-    if (require_init()) return 1;
+    const bool overlapped = g.inited && g.deferred && g.overlap && is_device_ptr(rays) && is_device_ptr(results);
+    if (require_init(!overlapped)) return 1;
     if (numRays == 0) return 0;                                        // CudaBVHTracer.cpp:92-94
     if (numRays < 0 || !rays || !results) { set_error("ntrace_b200: invalid ray batch"); return 1; }
     if (!g.haveBVH) { set_error("CudaBVHTracer: No BVH!"); return 1; }                          // :98-99
@@ -677,6 +703,19 @@ int nt_trace_batch(const float* rays, int32_t* results, int numRays, int needClo
     }
 
     a.numRays = numRays; a.rays = (const float4*)raysDev; a.results = (int4*)resDev;
+    if (overlapped) {
+        const int k = g.overlapNext; g.overlapNext ^= 1;
+        NT_CUDA(cudaEventRecord(g.kFork, g.stream));                   // what the main stream has queued so far (ray generation) comes first
+        NT_CUDA(cudaStreamWaitEvent(g.kStream[k], g.kFork, 0));
+        a.stream = g.kStream[k];
+        a.warpCounter = g.counters.as<int>() + 4 + k;                  // one fetch counter per launch in flight
+        NT_CUDA(cudaMemsetAsync(a.warpCounter, 0, sizeof(int), a.stream));
+        NT_CUDA(launch_trace(a, &launches));
+        NT_CUDA(cudaEventRecord(g.kDone[k], a.stream));
+        g.overlapPending = true;
+        g.launches += launches;
+        return 0;
+    }
     a.warpCounter = g.counters.as<int>();
     // the counter reset is issued before the first event so the timed interval is the kernel only
     NT_CUDA(cudaMemsetAsync(a.warpCounter, 0, sizeof(int), g.stream));

@@ -244,6 +244,53 @@ def test_async_submission_matches_synchronous_calls(gpu_host, orc, small_scene):
         capi.trace_batch_async(d_in, d_out, len(d_in), True, 9)
 
 
+def test_overlapped_deferred_launches_match_synchronous_calls(gpu_host, orc, small_scene):
+    """nt_set_deferred(2): consecutive launches run on two kernel streams and overlap; results are those of synchronous calls,
+    work queued before a launch (ray generation) is seen by it, and calls made afterwards see its results."""
+    import torch
+    from ntrace_b200 import capi
+    verts, tris, cpu, (nodes, woop, idx) = small_scene
+    tracer = gpu_host.CudaBVHTracer()
+    tracer.setKernel("b200_persistent_speculative_while_while")
+    tracer.setBVH(gpu_host.CudaBVH(nodes, woop, idx))
+    cam = camera.named_camera("conference")
+    base, _, _ = orc.raygen_primary(cam.position, camera.nscreen_to_world(cam, 256, 192), 256, 192, cam.far)
+    rng = np.random.default_rng(2)
+    batches = []
+    for k in range(9):
+        n = int(rng.integers(2000, len(base)))
+        batches.append((base[rng.permutation(len(base))[:n]].copy(), k % 3 != 0))
+    d_in = [torch.from_numpy(r).cuda() for r, _ in batches]
+    sync_out = []
+    for (r, closest), d in zip(batches, d_in):
+        o = torch.zeros((len(r), 4), dtype=torch.int32, device="cuda")
+        assert capi.trace_batch(d, o, len(r), closest) > 0
+        sync_out.append(o.cpu().numpy())
+    d_out = [torch.zeros((len(r), 4), dtype=torch.int32, device="cuda") for r, _ in batches]
+    torch.cuda.synchronize()
+    capi.set_deferred(2)
+    try:
+        l0 = capi.launch_count()
+        for (r, closest), d, o in zip(batches, d_in, d_out):
+            assert capi.trace_batch(d, o, len(r), closest) == 0.0          # queued
+        assert capi.launch_count() - l0 == len(batches)
+        hits = capi.count_hits(d_out[-1], len(batches[-1][0]))             # any other call is ordered behind the launches in flight
+        # a primary batch generated on the main stream and traced right away: the launch must wait for the generator
+        rb = gpu_host.RayBuffer()
+        gpu_host.RayGen().primary(rb, cam.position, camera.nscreen_to_world(cam, 256, 192), 256, 192, cam.far)
+        o2 = torch.zeros((rb.getSize(), 4), dtype=torch.int32, device="cuda")
+        capi.trace_batch(rb.getRayBuffer(), o2, rb.getSize(), True)
+        capi.synchronize()
+    finally:
+        capi.set_deferred(0)
+    for got, want in zip(d_out, sync_out):
+        assert np.array_equal(got.cpu().numpy().view(np.uint32), want.view(np.uint32))
+    assert hits == int((sync_out[-1][:, 0] >= 0).sum())
+    _check_closest(o2.cpu().numpy(), orc.compact_trace(nodes, woop, idx, base, True))
+    with pytest.raises(capi.NtError, match="submission mode"):
+        capi.set_deferred(3)
+
+
 @pytest.mark.timeout(120)
 def test_non_finite_and_extreme_rays_terminate_and_match_the_cpu_tracer(gpu_host, orc, small_scene):
     """NaN / Inf / zero-direction / denormal / huge rays: the persistent kernel must terminate and give what the reference's
