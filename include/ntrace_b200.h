@@ -75,7 +75,9 @@ int nt_event_elapsed(int slotA, int slotB, float* outSeconds);
  * the next batch move in while the persistent CTAs of the current one run out of rays (the batches of a frame are
  * independent once the primary results exist; the reference traces them one after the other, Renderer.cpp:405-579).
  * A launch is ordered after everything queued before it; every other call of this API waits for the launches in flight
- * before it enqueues or reads anything, so only the result buffers of two CONSECUTIVE nt_trace_batch calls must differ. */
+ * before it enqueues or reads anything, so only the result buffers of two CONSECUTIVE nt_trace_batch calls must differ.
+ * Mode 2 also queues calls whose buffers are page-locked host memory (traversed in place over PCIe; results are in host
+ * memory once nt_synchronize() returns); pageable host buffers stay synchronous in every mode. */
 int nt_set_deferred(int mode);
 int nt_synchronize(void);
 

@@ -641,7 +641,8 @@ int nt_trace_batch(const float* rays, int32_t* results, int numRays, int needClo
 {
     std::lock_guard<std::mutex> lock(g_mutex);
     if (outSeconds) *outSeconds = 0.0f;
-    const bool overlapped = g.inited && g.deferred && g.overlap && is_device_ptr(rays) && is_device_ptr(results);
+    // overlapped deferred launches take device buffers and page-locked host buffers (traversed in place over PCIe)
+    const bool overlapped = g.inited && g.deferred && g.overlap && rays && results && mapped_device_ptr(rays) && mapped_device_ptr(results);
     if (require_init(!overlapped)) return 1;
     if (numRays == 0) return 0;                                        // CudaBVHTracer.cpp:92-94
     if (numRays < 0 || !rays || !results) { set_error("ntrace_b200: invalid ray batch"); return 1; }
