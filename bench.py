@@ -368,7 +368,7 @@ def run_b200(args):
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH,
                          "peak_source": peak_src,
-                         "note": "algorithmic bytes (nodes+triangles fetched per ray, oracle-counted) over avg launch time; the BVH is L2-resident, "
+                         "note": "algorithmic bytes (nodes+triangles fetched per ray, oracle-counted) over avg launch time (timed region / launches: with the overlapped submission consecutive launches share the GPU at their tails); the BVH is L2-resident, "
                                  "so DRAM traffic is far below the algorithmic bytes and frac can exceed 1 (see profiles/)",
                          "bytes_per_ray": cpu["bytes_per_ray"],
                          # what actually limits the kernel, from the committed ncu captures of this workload (static numbers,
