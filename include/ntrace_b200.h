@@ -89,7 +89,11 @@ int nt_synchronize(void);
  * those kernels recompiled for sm_100a.  Reference names accepted as aliases: "fermi_speculative_while_while" (Compact),
  * "kepler_dynamic_fetch" (Compact2), "tesla_persistent_while_while" / "tesla_persistent_speculative_while_while" /
  * "tesla_persistent_packet" (AOS_AOS, as those files ship); "b200_persistent_speculative_while_while_{aos_aos,aos_soa,
- * soa_aos,soa_soa}" select the other basic layouts.  Unknown names fail. */
+ * soa_aos,soa_soa}" select the other basic layouts.  "b200_wide4" / "b200_wide4_fastmath" (Compact) and "b200_wide4_compact2"
+ * traverse a 4-wide, 8-bit quantised node array that the library derives from the resident Compact / Compact2 BVH
+ * (csrc/nt_wide.cu): same leaves, same triangle test, so closest-hit t/u/v are bit-identical per (ray, triangle) and ids differ
+ * from the binary kernels only on exact-t ties; any-hit rays report A hit (possibly another triangle than the binary order finds).
+ * Unknown names fail. */
 int nt_set_kernel(const char* name);
 /* CudaBVHTracer::getDesiredBVHLayout -> BVHLayout of the selected kernel. */
 int nt_desired_layout(void);
@@ -130,6 +134,14 @@ int nt_bvh_set_build_layout(int layout);
  * Compact form (CudaBVH.cpp:579-664 semantics: implicit leaves, terminator-delimited Woop lists), Compact <-> Compact2
  * rescales the inner-child offsets (createCompact's nodeOffsetSizeDiv, CudaBVH.cpp:86,614). */
 int nt_bvh_convert(int layout);
+/* NEW (no reference counterpart; the reference's flattening, CudaBVH::createCompact, CudaBVH.cpp:579-664, is host code too):
+ * the 4-wide, 8-bit quantised node array ("Wide4", 64 bytes per node, format in csrc/nt_wide.cu) that the "b200_wide4*"
+ * kernels traverse, derived from a Compact (4) / Compact2 (5) node buffer.  The library does this itself when such a kernel
+ * is selected; this entry point exposes the same conversion on HOST buffers (no CUDA device needed) for tools and tests.
+ * Leaves are shared with the source BVH: a Wide4 link < 0 is the source's ~woopIndex, so woop / triIndex are used as they are.
+ * outWideNodes may be NULL to query *outWideBytes; *outMaxDepth (optional) = depth of the Wide4 tree. */
+int nt_bvh_wide4_convert_host(int layout, const void* nodes, size_t nodeBytes, size_t woopBytes,
+                              void* outWideNodes, size_t outCapacityBytes, size_t* outWideBytes, int* outMaxDepth);
 /* sizes[3] = bytes of (nodes, woop, triIndex); layout of the resident BVH in *outLayout. */
 int nt_bvh_sizes(size_t sizes[3], int* outLayout);
 /* CudaBVH::serialize source buffers (CudaBVH.cpp:105-125): copy the device BVH out (host or device dst). */

@@ -7,7 +7,7 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB = os.path.join(_HERE, "libntrace_b200.so")
-SOURCES = ["nt_api.cu", "nt_trace.cu", "nt_raygen.cu", "nt_build.cu", "nt_raysort.cu", "nt_layout.cu"]
+SOURCES = ["nt_api.cu", "nt_trace.cu", "nt_raygen.cu", "nt_build.cu", "nt_raysort.cu", "nt_layout.cu", "nt_wide.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "--threads", "0",
               "-Xcompiler", "-fPIC", "-shared"]
 

@@ -83,6 +83,11 @@ struct Context {
     DevBuf srcNodes, srcWoop, srcIdx, layoutScratch;
     size_t srcNodeBytes = 0, srcWoopBytes = 0, srcIdxBytes = 0;
     bool basic = false, converted = false;
+    // Wide4 form of the resident (Compact / Compact2) node buffer, derived on demand for the b200_wide4* kernels (nt_wide.cu)
+    DevBuf wideNodes;
+    size_t wideBytes = 0;
+    bool wideValid = false;
+    int wideDepth = 0;
     DevBuf sortedKeys, sortedIdx;
     int builtTris = 0;
     int collapseMode = 0, collapseMaxLeaf = 0;
@@ -168,6 +173,25 @@ int ensure_traversal_form()
     }
     g.nodeBytes = out.nodeBytes; g.woopBytes = out.woopBytes; g.idxBytes = out.idxBytes;
     g.converted = true;
+    return 0;
+}
+
+// derive the Wide4 node array from the resident Compact / Compact2 nodes (host conversion: nt_wide.cu); caller holds the mutex
+int ensure_wide_form()
+{
+    if (g.kernel != Kernel_Wide4Persistent || g.wideValid) return 0;
+    std::vector<int32_t> h(g.nodeBytes / 4);
+    NT_CUDA(cudaMemcpyAsync(h.data(), g.nodes.p, g.nodeBytes, cudaMemcpyDeviceToHost, g.stream));
+    NT_CUDA(cudaStreamSynchronize(g.stream));
+    std::vector<uint32_t> w;
+    std::string err;
+    const int srcLayout = g.basic ? (int)Layout_Compact : g.bvhLayout;
+    if (convert_compact_to_wide4_host(h.data(), g.nodeBytes, srcLayout, g.woopBytes / 16, w, &g.wideDepth, &err)) { set_error("ntrace_b200: " + err); return 1; }
+    NT_CUDA(g.wideNodes.reserve(w.size() * 4));
+    NT_CUDA(cudaMemcpyAsync(g.wideNodes.p, w.data(), w.size() * 4, cudaMemcpyHostToDevice, g.stream));
+    NT_CUDA(cudaStreamSynchronize(g.stream));
+    g.wideBytes = w.size() * 4;
+    g.wideValid = true;
     return 0;
 }
 
@@ -298,7 +322,7 @@ void nt_shutdown(void)
     cudaEventDestroy(g.kFork);
     DevBuf* bufs[] = {&g.nodes, &g.woop, &g.triIndex, &g.sortedKeys, &g.sortedIdx, &g.stRays, &g.stResults, &g.stA, &g.stB,
                       &g.stC, &g.stD, &g.stE, &g.counters, &g.pixelTable, &g.sceneVerts, &g.sceneTris,
-                      &g.srcNodes, &g.srcWoop, &g.srcIdx, &g.layoutScratch};
+                      &g.srcNodes, &g.srcWoop, &g.srcIdx, &g.layoutScratch, &g.wideNodes};
     for (DevBuf* b : bufs) b->release();
     release_build_scratch();
     release_sort_scratch();
@@ -427,6 +451,10 @@ int nt_set_kernel(const char* name)
         // the arithmetic nvcc -use_fast_math gives the reference's GPU kernels (contracted FMAs, approximate 1/x): bit-identical to them
         {"b200_persistent_speculative_while_while_fastmath", Kernel_PersistentSpeculative, Layout_Compact, true},
         {"b200_persistent_speculative_while_while_compact2_fastmath", Kernel_PersistentSpeculative, Layout_Compact2, true},
+        // the 4-wide quantised node array derived from the Compact / Compact2 BVH (nt_wide.cu); triangle test as above
+        {"b200_wide4", Kernel_Wide4Persistent, Layout_Compact, false},
+        {"b200_wide4_fastmath", Kernel_Wide4Persistent, Layout_Compact, true},
+        {"b200_wide4_compact2", Kernel_Wide4Persistent, Layout_Compact2, false},
         // reference kernel file names (src/rt/kernels/*.cu) accepted as aliases with their layouts AND their arithmetic, so a config
         // that names one of them gets the results that kernel produces
         {"fermi_speculative_while_while", Kernel_PlainSpeculative, Layout_Compact, true},
@@ -443,7 +471,11 @@ int nt_set_kernel(const char* name)
         {"b200_persistent_speculative_while_while_soa_soa", Kernel_PersistentSpeculative, Layout_SOA_SOA, false},
     };
     for (const Entry& e : table)
-        if (strcmp(e.name, name) == 0) { g.kernel = e.kernel; g.kernelLayout = e.layout; g.fastMath = e.fast; return 0; }
+        if (strcmp(e.name, name) == 0) {
+            if (g.kernelLayout != e.layout) g.wideValid = false;
+            g.kernel = e.kernel; g.kernelLayout = e.layout; g.fastMath = e.fast;
+            return 0;
+        }
     set_error(std::string("ntrace_b200: unknown kernel '") + name + "'");
     return 1;
 }
@@ -471,7 +503,7 @@ int nt_bvh_alloc(int layout, size_t nodeBytes, size_t woopBytes, size_t idxBytes
         NT_CUDA(g.srcIdx.reserve(idxBytes));
         g.srcNodeBytes = nodeBytes; g.srcWoopBytes = woopBytes; g.srcIdxBytes = idxBytes;
         g.bvhLayout = layout;
-        g.basic = true; g.converted = false;
+        g.basic = true; g.converted = false; g.wideValid = false;
         g.haveBVH = true;
         g.builtTris = 0;
         return 0;
@@ -481,7 +513,7 @@ int nt_bvh_alloc(int layout, size_t nodeBytes, size_t woopBytes, size_t idxBytes
         set_error("ntrace_b200: inconsistent CudaBVH buffer sizes (nodes multiple of 64 B, woop of 16 B, one index per woop float4)");
         return 1;
     }
-    g.basic = false; g.converted = false;
+    g.basic = false; g.converted = false; g.wideValid = false;
     NT_CUDA(g.nodes.reserve(nodeBytes));
     NT_CUDA(g.woop.reserve(woopBytes));
     NT_CUDA(g.triIndex.reserve(idxBytes));
@@ -528,7 +560,7 @@ int nt_bvh_build(int builder, const float* vtxPos, int numVerts, const int32_t* 
     out.sortedKeys = &g.sortedKeys; out.sortedIdx = &g.sortedIdx;
     out.nodeBytes = out.woopBytes = out.idxBytes = 0;
     g.haveBVH = false;
-    g.basic = false; g.converted = false;
+    g.basic = false; g.converted = false; g.wideValid = false;
     NT_CUDA(cudaEventRecord(g.evA, g.stream));
     int launches = 0;
     std::string err;
@@ -573,6 +605,7 @@ int nt_bvh_convert(int layout)
     if (require_init()) return 1;
     if (!g.haveBVH) { set_error("CudaBVHTracer: No BVH!"); return 1; }
     if (layout != Layout_Compact && layout != Layout_Compact2) { set_error("ntrace_b200: the resident BVH can only be converted to BVHLayout_Compact / Compact2"); return 1; }
+    g.wideValid = false;
     if (g.basic) {
         if (ensure_traversal_form()) return 1;                      // AOS/SOA -> Compact (nt_layout.cu)
         g.basic = false; g.converted = false;
@@ -584,6 +617,24 @@ int nt_bvh_convert(int layout)
     g.launches += 1;
     NT_CUDA(cudaStreamSynchronize(g.stream));
     g.bvhLayout = layout;
+    return 0;
+}
+
+int nt_bvh_wide4_convert_host(int layout, const void* nodes, size_t nodeBytes, size_t woopBytes,
+                              void* outWideNodes, size_t outCapacityBytes, size_t* outWideBytes, int* outMaxDepth)
+{
+    // pure host code: no device is touched, so this also runs where there is no GPU (it computes a data layout, it does not trace)
+    if (!nodes || !outWideBytes) { set_error("ntrace_b200: null pointer in nt_bvh_wide4_convert_host"); return 1; }
+    std::vector<uint32_t> w;
+    std::string err;
+    int depth = 0;
+    if (convert_compact_to_wide4_host((const int32_t*)nodes, nodeBytes, layout, woopBytes / 16, w, &depth, &err)) { set_error("ntrace_b200: " + err); return 1; }
+    *outWideBytes = w.size() * 4;
+    if (outMaxDepth) *outMaxDepth = depth;
+    if (outWideNodes) {
+        if (outCapacityBytes < w.size() * 4) { set_error("ntrace_b200: output buffer too small for the Wide4 node array"); return 1; }
+        memcpy(outWideNodes, w.data(), w.size() * 4);
+    }
     return 0;
 }
 
@@ -621,7 +672,8 @@ int nt_bvh_device_ptrs(void* ptrs[3])
     std::lock_guard<std::mutex> lock(g_mutex);
     if (require_init()) return 1;
     if (!g.haveBVH) { set_error("CudaBVHTracer: No BVH!"); return 1; }
-    if (g.basic) { ptrs[0] = g.srcNodes.p; ptrs[1] = g.srcWoop.p; ptrs[2] = g.srcIdx.p; g.converted = false; }   // caller may write (broadcast)
+    g.wideValid = false;                                                                                          // caller may write (broadcast)
+    if (g.basic) { ptrs[0] = g.srcNodes.p; ptrs[1] = g.srcWoop.p; ptrs[2] = g.srcIdx.p; g.converted = false; }
     else { ptrs[0] = g.nodes.p; ptrs[1] = g.woop.p; ptrs[2] = g.triIndex.p; }
     return 0;
 }
@@ -648,7 +700,7 @@ int nt_trace_batch(const float* rays, int32_t* results, int numRays, int needClo
     if (numRays < 0 || !rays || !results) { set_error("ntrace_b200: invalid ray batch"); return 1; }
     if (!g.haveBVH) { set_error("CudaBVHTracer: No BVH!"); return 1; }                          // :98-99
     if (g.bvhLayout != g.kernelLayout) { set_error("CudaBVHTracer: Incorrect BVH layout!"); return 1; }  // :100-101
-    if (ensure_traversal_form()) return 1;
+    if (ensure_traversal_form() || ensure_wide_form()) return 1;
 
     // Pinned (page-locked, UVA-mapped) host buffers are traversed in place: the kernel reads rays and writes results
     // over PCIe (zero copy), which overlaps both transfers with the traversal inside ONE launch.  Pageable host memory
@@ -660,6 +712,7 @@ int nt_trace_batch(const float* rays, int32_t* results, int numRays, int needClo
     TraceLaunch a;
     a.kernel = g.kernel; a.fast = g.fastMath ? 1 : 0; a.layout = g.basic ? (int)Layout_Compact : g.kernelLayout; a.anyHit = needClosestHit ? 0 : 1;
     a.nodes = g.nodes.as<float4>(); a.woop = g.woop.as<float4>(); a.triIndices = g.triIndex.as<int>();
+    a.wideNodes = g.wideNodes.as<float4>();
     a.numSMs = g.numSMs; a.stream = g.stream;
     int launches = 0;
 
@@ -751,7 +804,7 @@ int nt_trace_batch_async(const float* rays, int32_t* results, int numRays, int n
     if (numRays <= 0 || !rays || !results) { set_error("ntrace_b200: invalid ray batch"); return 1; }
     if (!g.haveBVH) { set_error("CudaBVHTracer: No BVH!"); return 1; }
     if (g.bvhLayout != g.kernelLayout) { set_error("CudaBVHTracer: Incorrect BVH layout!"); return 1; }
-    if (ensure_traversal_form()) return 1;
+    if (ensure_traversal_form() || ensure_wide_form()) return 1;
     const bool raysDev = is_device_ptr(rays), resDev = is_device_ptr(results);
     if ((!raysDev && !mapped_device_ptr(rays)) || (!resDev && !mapped_device_ptr(results))) {
         set_error("ntrace_b200: asynchronous submission needs device or pinned (page-locked) host buffers");
@@ -775,6 +828,7 @@ int nt_trace_batch_async(const float* rays, int32_t* results, int numRays, int n
     TraceLaunch a;
     a.kernel = g.kernel; a.fast = g.fastMath ? 1 : 0; a.layout = g.basic ? (int)Layout_Compact : g.kernelLayout; a.anyHit = needClosestHit ? 0 : 1;
     a.nodes = g.nodes.as<float4>(); a.woop = g.woop.as<float4>(); a.triIndices = g.triIndex.as<int>();
+    a.wideNodes = g.wideNodes.as<float4>();
     a.numSMs = g.numSMs; a.stream = g.stream;
     a.numRays = numRays; a.rays = dRays; a.results = dRes;
     a.warpCounter = g.counters.as<int>() + 32 + slot;

@@ -4,6 +4,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <string>
+#include <vector>
 
 namespace nt {
 
@@ -30,6 +31,7 @@ bool check_cuda(cudaError_t e, const char* what, const char* file, int line);
 enum TraceKernelId : int {
     Kernel_PersistentSpeculative = 0,   // persistent while-while, warp-level dynamic ray fetch, speculative leaf
     Kernel_PlainSpeculative = 1,        // one thread per ray, speculative while-while (fermi-style launch shape)
+    Kernel_Wide4Persistent = 2,         // persistent speculative while-while over the derived 4-wide quantised node array (nt_wide.cu)
     Kernel_Count
 };
 
@@ -42,6 +44,7 @@ struct TraceLaunch {
     const float4* rays;       // device, 2 x float4 per ray
     int4* results;            // device, 1 x int4 per ray
     const float4* nodes;      // device, 4 x float4 per node
+    const float4* wideNodes = nullptr;   // device, Wide4 node array (Kernel_Wide4Persistent only)
     const float4* woop;       // device
     const int* triIndices;    // device
     int* warpCounter;         // device, zeroed before launch (persistent kernels only)
@@ -49,6 +52,11 @@ struct TraceLaunch {
     cudaStream_t stream;
 };
 cudaError_t launch_trace(const TraceLaunch& a, int* outNumLaunches);
+// nt_wide.cu: 4-wide quantised form of a Compact / Compact2 node buffer (host side; 16 words per node) and its traversal kernel
+constexpr int kWideMaxDepth = 42;       // three pushes per level at most: 1 + 3 * depth entries fit the kernel's 128-entry stack
+int convert_compact_to_wide4_host(const int32_t* nodes, size_t nodeBytes, int layout, size_t woopRows,
+                                  std::vector<uint32_t>& out, int* outMaxDepth, std::string* err);
+cudaError_t launch_trace_wide4(const TraceLaunch& a, int* outNumLaunches);
 KernelConfig trace_kernel_config(int kernel, int layout);
 
 // ---- ray generation (nt_raygen.cu) ------------------------------------------------------------

@@ -322,7 +322,7 @@ KernelConfig trace_kernel_config(int kernel, int layout)
     c.bvhLayout = layout;
     c.blockWidth = 32;
     c.blockHeight = kBlock / 32;
-    c.usePersistentThreads = (kernel == Kernel_PersistentSpeculative) ? 1 : 0;
+    c.usePersistentThreads = (kernel == Kernel_PlainSpeculative) ? 0 : 1;
     return c;
 }
 
@@ -335,6 +335,8 @@ cudaError_t launch_trace(const TraceLaunch& a, int* launches)
         return c2 ? launch_one<Layout_Compact2, true>(a, launches) : launch_one<Layout_Compact, true>(a, launches);
     case Kernel_PlainSpeculative:
         return c2 ? launch_one<Layout_Compact2, false>(a, launches) : launch_one<Layout_Compact, false>(a, launches);
+    case Kernel_Wide4Persistent:
+        return launch_trace_wide4(a, launches);
     default:
         return cudaErrorInvalidValue;
     }

@@ -1,0 +1,421 @@
+// ntrace_b200 — 4-wide, 8-bit quantised BVH ("Wide4") derived from the resident binary CudaBVH, and its traversal kernel.
+//
+// Why (profiles/r1_summary.md): on a B200 the binary kernel (nt_trace.cu) is bound by the L1 data
+// pipe (67-75 % busy: two 32-byte sectors per node visit and lane), by dependent L1/L2 round trips (long-scoreboard stalls) and
+// by the ALU pipe (20 FMNMX per node), not by HBM.  A wide node attacks the first two: one 64-byte Wide4 node replaces a binary
+// node AND its two children (~0.55x the node visits for the same 64 bytes per visit), and knowing the ray's direction signs picks
+// the near / far plane of every child box without a min/max pair.
+//
+// The API does not change: the host still hands over / builds the reference's Compact (or Compact2) CudaBVH
+// (src/rt/cuda/CudaBVH.hpp:43-56).  The Wide4 node array is derived from it when a "b200_wide4*" kernel is selected, exactly like
+// nt_layout.cu derives the Compact form from AOS/SOA uploads.  Leaves are NOT rewritten: a Wide4 child link < 0 is the same
+// ~woopIndex as in the binary tree, so the Woop triangles, the terminators and the triIndex remap stay the reference's
+// (CudaBVH.cpp:620-638) and the triangle test is the one of nt_trace.cu — hit t/u/v are bit-identical per (ray, triangle).
+//
+// Wide4 node, 64 bytes (16 words), node i at byte i * 64:
+//   w0..2   p        float3  origin of the quantisation grid = lo corner of the union of the child boxes
+//   w3..5   s'       float3  grid step * 2^15 per axis (see decode)
+//   w6,w7   qlo.x, qlo.y      4 x uint8 each: child i in byte i
+//   w8      qlo.z    w9..11  qhi.x, qhi.y, qhi.z
+//   w12..15 link[4]  int     >= 0: Wide4 node index;  < 0: ~woopIndex of a leaf (as in the Compact layout);
+//                            an unused slot has an inverted box (qlo 255, qhi 0) and links to the last terminator of the Woop array
+// Decode: plane = p + q * s.  In the kernel a quantised plane enters the slab test as
+//   t = fma(as_float(0x3F800000 | q << 8), s' * idir, (p * idir - ood) - s' * idir)       [as_float(..) = 1 + q * 2^-15, s' = s * 2^15]
+// i.e. one PRMT and one FFMA per plane.  Boxes are quantised outwards with a margin of 1/8 grid step, which covers the rounding of
+// that expression, so a child box always contains the binary tree's box: traversal visits a superset of what the reference visits.
+#include "nt_common.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+namespace nt {
+
+// ================================================================================================================
+// host: Compact / Compact2 -> Wide4
+// ================================================================================================================
+namespace {
+
+struct Cand { float lo[3], hi[3]; int link; };
+
+inline float cand_area(const Cand& c)
+{
+    const float dx = c.hi[0] - c.lo[0], dy = c.hi[1] - c.lo[1], dz = c.hi[2] - c.lo[2];
+    return dx * dy + dy * dz + dz * dx;
+}
+
+// children of the binary node at link `addr` (Compact: byte offset, Compact2: float4 index); CudaBVH.cpp:646-651
+inline bool read_binary_children(const int32_t* nodes, size_t nodeBytes, int layout, int addr, Cand out[2])
+{
+    const size_t byteOfs = (layout == Layout_Compact2) ? (size_t)(uint32_t)addr * 16 : (size_t)(uint32_t)addr;
+    if (byteOfs % 64 || byteOfs + 64 > nodeBytes) return false;
+    const int32_t* w = nodes + byteOfs / 4;
+    const float* f = reinterpret_cast<const float*>(w);
+    out[0].lo[0] = f[0]; out[0].hi[0] = f[1]; out[0].lo[1] = f[2]; out[0].hi[1] = f[3];
+    out[1].lo[0] = f[4]; out[1].hi[0] = f[5]; out[1].lo[1] = f[6]; out[1].hi[1] = f[7];
+    out[0].lo[2] = f[8]; out[0].hi[2] = f[9]; out[1].lo[2] = f[10]; out[1].hi[2] = f[11];
+    out[0].link = w[12]; out[1].link = w[13];
+    return true;
+}
+
+// one axis of a Wide4 node: grid origin, step and the outward-rounded plane bytes of n children
+void quantise_axis(const Cand* c, int n, int axis, float& p, float& sPrime, uint8_t qlo[4], uint8_t qhi[4])
+{
+    float mn = c[0].lo[axis], mx = c[0].hi[axis];
+    for (int i = 1; i < n; i++) { mn = std::min(mn, c[i].lo[axis]); mx = std::max(mx, c[i].hi[axis]); }
+    p = mn;
+    const double ext = (double)mx - (double)mn;
+    float s = (float)(ext / 253.0);                       // 253 steps for the extent: room for the two 1/8-step margins and the rounding below
+    if (!(s > 1.0e-30f)) s = 1.0e-30f;                    // flat or degenerate axis (also NaN / negative extents)
+    while ((double)s * 253.0 < ext) s = std::nextafterf(s, INFINITY);
+    for (int i = 0; i < 4; i++) {
+        if (i >= n) { qlo[i] = 255; qhi[i] = 0; continue; }               // unused slot: inverted box
+        int a = (int)std::floor(((double)c[i].lo[axis] - (double)p) / (double)s - 0.125);
+        a = std::min(std::max(a, 0), 255);
+        while (a > 0 && (double)p + (double)a * (double)s > (double)c[i].lo[axis]) a--;
+        int b = (int)std::ceil(((double)c[i].hi[axis] - (double)p) / (double)s + 0.125);
+        b = std::min(std::max(b, 0), 255);
+        while (b < 255 && (double)p + (double)b * (double)s < (double)c[i].hi[axis]) b++;
+        qlo[i] = (uint8_t)a; qhi[i] = (uint8_t)b;
+    }
+    sPrime = s * 32768.0f;
+}
+
+} // namespace
+
+int convert_compact_to_wide4_host(const int32_t* nodes, size_t nodeBytes, int layout, size_t woopRows,
+                                  std::vector<uint32_t>& out, int* outMaxDepth, std::string* err)
+{
+    auto fail = [&](const char* m) { if (err) *err = m; return 1; };
+    if (layout != Layout_Compact && layout != Layout_Compact2) return fail("Wide4 is derived from BVHLayout_Compact / Compact2");
+    if (!nodes || nodeBytes < 64 || nodeBytes % 64 || woopRows < 1) return fail("malformed BVH: empty node or triangle buffer");
+    const size_t numBinary = nodeBytes / 64;
+    const int emptyLink = ~(int)(woopRows - 1);           // the Woop array ends with the terminator of its last leaf
+    out.clear();
+    out.reserve((numBinary / 2 + 8) * 16);
+    struct Work { int wide; int binary; int depth; };
+    std::vector<Work> work;
+    out.resize(16);
+    work.push_back({0, 0, 1});
+    size_t consumed = 0;                                  // binary nodes folded into wide nodes (cycle guard)
+    int maxDepth = 0;
+    while (!work.empty()) {
+        const Work wk = work.back();
+        work.pop_back();
+        maxDepth = std::max(maxDepth, wk.depth);
+        Cand c[4];
+        int n = 2;
+        if (!read_binary_children(nodes, nodeBytes, layout, wk.binary, c)) return fail("malformed BVH: child link outside the node buffer");
+        if (++consumed > numBinary) return fail("malformed BVH: the node links form a cycle");
+        // open the inner child with the largest surface area until four children are held (or only leaves are left)
+        while (n < 4) {
+            int best = -1;
+            float bestArea = -1.0f;
+            for (int i = 0; i < n; i++)
+                if (c[i].link >= 0) { const float a = cand_area(c[i]); if (a > bestArea || best < 0) { bestArea = a; best = i; } }
+            if (best < 0) break;
+            Cand two[2];
+            if (!read_binary_children(nodes, nodeBytes, layout, c[best].link, two)) return fail("malformed BVH: child link outside the node buffer");
+            if (++consumed > numBinary) return fail("malformed BVH: the node links form a cycle");
+            c[best] = two[0];
+            c[n++] = two[1];
+        }
+        uint32_t w[16];
+        float p[3], sp[3];
+        uint8_t qlo[3][4], qhi[3][4];
+        for (int a = 0; a < 3; a++) quantise_axis(c, n, a, p[a], sp[a], qlo[a], qhi[a]);
+        auto pack = [](const uint8_t b[4]) { return (uint32_t)b[0] | ((uint32_t)b[1] << 8) | ((uint32_t)b[2] << 16) | ((uint32_t)b[3] << 24); };
+        for (int a = 0; a < 3; a++) { std::memcpy(&w[a], &p[a], 4); std::memcpy(&w[3 + a], &sp[a], 4); }
+        w[6] = pack(qlo[0]); w[7] = pack(qlo[1]); w[8] = pack(qlo[2]);
+        w[9] = pack(qhi[0]); w[10] = pack(qhi[1]); w[11] = pack(qhi[2]);
+        for (int i = 0; i < 4; i++) {
+            int link = emptyLink;
+            if (i < n) {
+                if (c[i].link < 0) {
+                    if ((size_t)(uint32_t)~c[i].link >= woopRows) return fail("malformed BVH: leaf link outside the triangle buffer");
+                    link = c[i].link;
+                } else {
+                    const size_t idx = out.size() / 16;
+                    if (idx >= (size_t)kEntrypointSentinel) return fail("BVH too large for the Wide4 form");
+                    link = (int)idx;
+                    out.resize(out.size() + 16);
+                    work.push_back({link, c[i].link, wk.depth + 1});
+                }
+            }
+            w[12 + i] = (uint32_t)link;
+        }
+        std::memcpy(&out[(size_t)wk.wide * 16], w, 64);
+    }
+    if (outMaxDepth) *outMaxDepth = maxDepth;
+    if (maxDepth > kWideMaxDepth) return fail("BVH too deep for the Wide4 kernel's traversal stack (use a binary kernel)");
+    return 0;
+}
+
+// ================================================================================================================
+// device: traversal
+// ================================================================================================================
+namespace {
+
+constexpr int kWideStackSize = 128;            // 1 + 3 * kWideMaxDepth entries at most (three pushes per level); the conversion refuses deeper trees
+constexpr int kWideBlock = 128;
+
+__device__ __forceinline__ float wfmin3(float a, float b, float c) { float r; asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c)); return r; }
+__device__ __forceinline__ float wfmax3(float a, float b, float c) { float r; asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c)); return r; }
+__device__ __forceinline__ void wld256_nc(const float4* p, float4& a, float4& b)
+{
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(p));
+}
+__device__ __forceinline__ void wld256_cs(const float4* p, float4& a, float4& b)
+{
+    asm volatile("ld.global.cs.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(p));
+}
+// quantised plane byte I of `q` as the float 1 + q * 2^-15: bytes (0x00, q.I, 0x80, 0x3F).  `one` is 0x3F800000 passed as a kernel
+// argument: a value ptxas cannot fold, so the SELECTOR becomes the immediate operand of PRMT (it takes one immediate) instead of a
+// register that would have to be materialised for every plane
+template <int I> __device__ __forceinline__ float qplane(unsigned q, unsigned one)
+{
+    unsigned r;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(q), "r"(one), "n"(0x7604 | (I << 4)));
+    return __uint_as_float(r);
+}
+__device__ __forceinline__ void cas(int& a, int& b) { const int lo = min(a, b), hi = max(a, b); a = lo; b = hi; }
+
+template <int BLOCK, int SMEM_N, bool FAST, bool WIDE_RAYS>
+__global__ void __launch_bounds__(BLOCK)
+trace_wide4_kernel(int numRays, int anyHit, int fetchThreshold, unsigned oneBits,
+                   const float4* __restrict__ rays, int4* __restrict__ results,
+                   const float4* __restrict__ wnodes, const float4* __restrict__ woop,
+                   const int* __restrict__ triIndices, int* __restrict__ warpCounter)
+{
+    __shared__ int s_stack[(SMEM_N > 0 ? SMEM_N : 1) * BLOCK];
+    int l_stack[(kWideStackSize > SMEM_N) ? (kWideStackSize - SMEM_N) : 1];
+
+    const int tid = threadIdx.x;
+    const unsigned lane = tid & 31;
+    int* const sbase = s_stack + tid;
+
+#define NT_PUSH(v)  do { ++sp; if (sp < SMEM_N) sbase[sp * BLOCK] = (v); else l_stack[sp - SMEM_N] = (v); } while (0)
+#define NT_POP(dst) do { (dst) = (sp < SMEM_N) ? sbase[sp * BLOCK] : l_stack[sp - SMEM_N]; --sp; } while (0)
+
+    int   rayidx = -1;
+    float origx = 0, origy = 0, origz = 0, dirx = 0, diry = 0, dirz = 0, tmin = 0;
+    float idirx = 0, idiry = 0, idirz = 0, oodx = 0, oody = 0, oodz = 0;
+    int   sp = 0;
+    int   leafAddr = 0;
+    int   nodeAddr = kEntrypointSentinel;
+    int   hitIndex = -1;
+    float hitT = 0, hitU = 0, hitV = 0;
+    bool  alive = true;
+    const unsigned one = oneBits;           // 0x3F800000 as a kernel argument: see qplane()
+
+    for (;;) {
+        // ---------------- ray fetch: one atomicAdd per warp refill (as nt_trace.cu) ----------------
+        const bool need = alive && (nodeAddr == kEntrypointSentinel);
+        const unsigned needMask = __ballot_sync(0xffffffffu, need);
+        if (needMask) {
+            const int n = __popc(needMask);
+            const int rank = __popc(needMask & ((1u << lane) - 1u));
+            const int leader = __ffs(needMask) - 1;
+            int base = 0;
+            if ((int)lane == leader) base = atomicAdd(warpCounter, n);
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (need) rayidx = base + rank;
+        }
+        if (need) {
+            if (rayidx >= numRays) { alive = false; rayidx = -1; }
+            else {
+                float4 o, d;
+                if (WIDE_RAYS) wld256_cs(rays + rayidx * 2, o, d);
+                else { o = __ldcs(rays + rayidx * 2 + 0); d = __ldcs(rays + rayidx * 2 + 1); }
+                origx = o.x; origy = o.y; origz = o.z; tmin = o.w;
+                dirx = d.x; diry = d.y; dirz = d.z; hitT = d.w;
+                const float ooeps = exp2f(-80.0f);                      // fermi_speculative_while_while.cu:94-98
+                idirx = 1.0f / (fabsf(d.x) > ooeps ? d.x : copysignf(ooeps, d.x));
+                idiry = 1.0f / (fabsf(d.y) > ooeps ? d.y : copysignf(ooeps, d.y));
+                idirz = 1.0f / (fabsf(d.z) > ooeps ? d.z : copysignf(ooeps, d.z));
+                oodx = origx * idirx; oody = origy * idiry; oodz = origz * idirz;
+                sp = 0;
+                if (SMEM_N > 0) sbase[0] = kEntrypointSentinel; else l_stack[0] = kEntrypointSentinel;
+                leafAddr = 0;
+                nodeAddr = 0;
+                hitIndex = -1;
+                hitU = 0.0f; hitV = 0.0f;
+            }
+        }
+        if (!__any_sync(0xffffffffu, alive)) break;
+
+        // ---------------- traversal ----------------
+        while (nodeAddr != kEntrypointSentinel) {
+            while ((unsigned)nodeAddr < (unsigned)kEntrypointSentinel) {
+                const float4* ptr = wnodes + (size_t)nodeAddr * 4;
+                float4 A0, A1, B0, B1;
+                wld256_nc(ptr, A0, A1);            // (p.x p.y p.z s'.x) (s'.y s'.z qlo.x qlo.y)
+                wld256_nc(ptr + 2, B0, B1);        // (qlo.z qhi.x qhi.y qhi.z) (link0..3)
+
+                const float ax = A0.w * idirx, ay = A1.x * idiry, az = A1.y * idirz;
+                const float bx = fmaf(A0.x, idirx, -oodx) - ax;
+                const float by = fmaf(A0.y, idiry, -oody) - ay;
+                const float bz = fmaf(A0.z, idirz, -oodz) - az;
+                // near / far plane bytes by the sign of the ray direction
+                const bool ngx = idirx < 0.0f, ngy = idiry < 0.0f, ngz = idirz < 0.0f;
+                const unsigned qlx = __float_as_uint(A1.z), qly = __float_as_uint(A1.w), qlz = __float_as_uint(B0.x);
+                const unsigned qhx = __float_as_uint(B0.y), qhy = __float_as_uint(B0.z), qhz = __float_as_uint(B0.w);
+                const unsigned nx = ngx ? qhx : qlx, fx = ngx ? qlx : qhx;
+                const unsigned ny = ngy ? qhy : qly, fy = ngy ? qly : qhy;
+                const unsigned nz = ngz ? qhz : qlz, fz = ngz ? qlz : qhz;
+
+                int k0, k1, k2, k3;
+#define NT_CHILD(I, K)                                                                                                    \
+                {                                                                                                         \
+                    const float tn = wfmax3(fmaf(qplane<I>(nx, one), ax, bx), fmaf(qplane<I>(ny, one), ay, by),           \
+                                            fmaxf(fmaf(qplane<I>(nz, one), az, bz), tmin));                               \
+                    const float tf = wfmin3(fmaf(qplane<I>(fx, one), ax, bx), fmaf(qplane<I>(fy, one), ay, by),           \
+                                            fminf(fmaf(qplane<I>(fz, one), az, bz), hitT));                               \
+                    K = (tn <= tf) ? ((__float_as_int(tn) & ~3) | I) : 0x7fffffff;                                        \
+                }
+                NT_CHILD(0, k0) NT_CHILD(1, k1) NT_CHILD(2, k2) NT_CHILD(3, k3)
+#undef NT_CHILD
+                // children in order of entry distance (the child slot rides in the two low mantissa bits of the key)
+                cas(k0, k1); cas(k2, k3); cas(k0, k2); cas(k1, k3); cas(k1, k2);
+                const int l0 = __float_as_int(B1.x), l1 = __float_as_int(B1.y), l2 = __float_as_int(B1.z), l3 = __float_as_int(B1.w);
+#define NT_LINK(K) (((K) & 2) ? (((K) & 1) ? l3 : l2) : (((K) & 1) ? l1 : l0))
+                if (k0 == 0x7fffffff) {
+                    NT_POP(nodeAddr);
+                } else {
+                    nodeAddr = NT_LINK(k0);
+                    if (k1 != 0x7fffffff) {
+                        if (k2 != 0x7fffffff) {
+                            if (k3 != 0x7fffffff) NT_PUSH(NT_LINK(k3));
+                            NT_PUSH(NT_LINK(k2));
+                        }
+                        NT_PUSH(NT_LINK(k1));
+                    }
+                }
+#undef NT_LINK
+                // first leaf => postpone and continue traversal (speculative while-while, as nt_trace.cu)
+                if (nodeAddr < 0 && leafAddr >= 0) {
+                    leafAddr = nodeAddr;
+                    NT_POP(nodeAddr);
+                }
+                if (!__any_sync(__activemask(), leafAddr >= 0)) break;
+            }
+
+            // postponed leaves: the reference's Woop test (Util.cpp:99-127), identical to nt_trace.cu
+            while (leafAddr < 0) {
+                int triAddr = ~leafAddr;
+                float4 v00 = __ldg(woop + triAddr);
+                for (;;) {
+                    if (__float_as_int(v00.x) == (int)0x80000000) break;
+                    float t;
+                    if (FAST) {
+                        const float Oz = v00.w - origx * v00.x - origy * v00.y - origz * v00.z;
+                        t = Oz * __fdividef(1.0f, dirx * v00.x + diry * v00.y + dirz * v00.z);
+                    } else {
+                        const float Oz = __fsub_rn(__fsub_rn(__fsub_rn(v00.w, __fmul_rn(origx, v00.x)), __fmul_rn(origy, v00.y)), __fmul_rn(origz, v00.z));
+                        const float dd = __fadd_rn(__fadd_rn(__fmul_rn(dirx, v00.x), __fmul_rn(diry, v00.y)), __fmul_rn(dirz, v00.z));
+                        t = __fmul_rn(Oz, __frcp_rn(dd));
+                    }
+                    if (t > tmin && t < hitT) {
+                        const float4 v11 = __ldg(woop + triAddr + 1);
+                        float u;
+                        if (FAST) u = (v11.w + origx * v11.x + origy * v11.y + origz * v11.z) + t * (dirx * v11.x + diry * v11.y + dirz * v11.z);
+                        else {
+                            const float Ou = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(v11.x, origx), __fmul_rn(v11.y, origy)), __fmul_rn(v11.z, origz)), v11.w);
+                            const float Du = __fadd_rn(__fadd_rn(__fmul_rn(v11.x, dirx), __fmul_rn(v11.y, diry)), __fmul_rn(v11.z, dirz));
+                            u = __fadd_rn(Ou, __fmul_rn(t, Du));
+                        }
+                        if (u >= 0.0f) {
+                            const float4 v22 = __ldg(woop + triAddr + 2);
+                            float v;
+                            if (FAST) v = (v22.w + origx * v22.x + origy * v22.y + origz * v22.z) + t * (dirx * v22.x + diry * v22.y + dirz * v22.z);
+                            else {
+                                const float Ov = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(v22.x, origx), __fmul_rn(v22.y, origy)), __fmul_rn(v22.z, origz)), v22.w);
+                                const float Dv = __fadd_rn(__fadd_rn(__fmul_rn(v22.x, dirx), __fmul_rn(v22.y, diry)), __fmul_rn(v22.z, dirz));
+                                v = __fadd_rn(Ov, __fmul_rn(t, Dv));
+                            }
+                            if (v >= 0.0f && (FAST ? (u + v) : __fadd_rn(u, v)) <= 1.0f) {
+                                hitT = t; hitU = u; hitV = v;
+                                hitIndex = triAddr;
+                                if (anyHit) { nodeAddr = kEntrypointSentinel; break; }
+                            }
+                        }
+                    }
+                    triAddr += 3;
+                    v00 = __ldg(woop + triAddr);
+                }
+                leafAddr = nodeAddr;
+                if (nodeAddr < 0) NT_POP(nodeAddr);
+            }
+            if (__popc(__activemask()) < fetchThreshold) break;
+        }
+
+        // ---------------- result ----------------
+        if (rayidx >= 0 && nodeAddr == kEntrypointSentinel) {
+            int id = hitIndex;
+            if (id != -1) id = __ldg(triIndices + id);
+            __stcs(results + rayidx, make_int4(id, __float_as_int(hitT), __float_as_int(hitU), __float_as_int(hitV)));
+            rayidx = -1;
+        }
+    }
+#undef NT_PUSH
+#undef NT_POP
+}
+
+struct WideTuning { int smemStack; int carveout; int fetchThreshold; };
+WideTuning wide_tuning()
+{
+    static WideTuning t = [] {
+        WideTuning r{8, 20, 20};
+        if (const char* e = getenv("NT_WIDE_SMEM")) r.smemStack = atoi(e);
+        if (const char* e = getenv("NT_WIDE_CARVEOUT")) r.carveout = atoi(e);
+        if (const char* e = getenv("NT_WIDE_FETCH")) r.fetchThreshold = atoi(e);
+        return r;
+    }();
+    return t;
+}
+
+template <int SMEM_N, bool FAST, bool WIDE_RAYS>
+cudaError_t launch_wide_variant(const TraceLaunch& a, int* launches)
+{
+    auto kern = trace_wide4_kernel<kWideBlock, SMEM_N, FAST, WIDE_RAYS>;
+    static int blocksPerSM = 0;
+    if (!blocksPerSM) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, wide_tuning().carveout);
+        if (e != cudaSuccess) return e;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSM, kern, kWideBlock, 0);
+        if (e != cudaSuccess) return e;
+        if (blocksPerSM < 1) blocksPerSM = 1;
+    }
+    int grid = (a.numRays + kWideBlock - 1) / kWideBlock;
+    if (grid > a.numSMs * blocksPerSM) grid = a.numSMs * blocksPerSM;
+    kern<<<grid, kWideBlock, 0, a.stream>>>(a.numRays, a.anyHit, wide_tuning().fetchThreshold, 0x3F800000u, a.rays, a.results, a.wideNodes, a.woop, a.triIndices, a.warpCounter);
+    if (launches) *launches = 1;
+    return cudaGetLastError();
+}
+
+template <bool FAST, bool WIDE_RAYS>
+cudaError_t launch_wide_stack(const TraceLaunch& a, int* launches)
+{
+    switch (wide_tuning().smemStack) {
+    case 4:  return launch_wide_variant<4, FAST, WIDE_RAYS>(a, launches);
+    case 16: return launch_wide_variant<16, FAST, WIDE_RAYS>(a, launches);
+    default: return launch_wide_variant<8, FAST, WIDE_RAYS>(a, launches);
+    }
+}
+
+} // namespace
+
+cudaError_t launch_trace_wide4(const TraceLaunch& a, int* launches)
+{
+    if (a.numRays <= 0) { if (launches) *launches = 0; return cudaSuccess; }
+    if (!a.wideNodes || (reinterpret_cast<size_t>(a.wideNodes) & 63)) return cudaErrorInvalidValue;
+    const bool wideRays = (reinterpret_cast<size_t>(a.rays) & 31) == 0;
+    if (a.fast) return wideRays ? launch_wide_stack<true, true>(a, launches) : launch_wide_stack<true, false>(a, launches);
+    return wideRays ? launch_wide_stack<false, true>(a, launches) : launch_wide_stack<false, false>(a, launches);
+}
+
+} // namespace nt

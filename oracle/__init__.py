@@ -147,6 +147,30 @@ def compact_trace(nodes, woop, tri_index, rays, need_closest=True, counters=Fals
     return (res, cnt) if counters else res
 
 
+def wide4_trace(wnodes, woop, tri_index, rays, need_closest=True, counters=False, nthreads=0):
+    """CPU emulation of the product's Wide4 traversal (csrc/nt_wide.cu) on its own node array; leaves / triangle test as compact_trace."""
+    wnodes = np.ascontiguousarray(wnodes, dtype=np.uint32)
+    woop, tri_index = _i32(woop), _i32(tri_index)
+    rays = _f32(rays).reshape(-1, 8)
+    res = np.zeros((len(rays), 4), dtype=np.int32)
+    cnt = np.zeros((len(rays), 3), dtype=np.uint32) if counters else None
+    lib().orc_wide4_trace(_p(wnodes), _p(woop), _p(tri_index), _p(rays), C.c_int(len(rays)), C.c_int(1 if need_closest else 0),
+                          _p(res), _p(cnt) if counters else None, C.c_int(nthreads))
+    return (res, cnt) if counters else res
+
+
+def wide4_check(wnodes, nodes, layout=4):
+    """Structural check of a Wide4 array against its source Compact tree -> dict (raises on inconsistency)."""
+    wnodes = np.ascontiguousarray(wnodes, dtype=np.uint32)
+    nodes = _i32(nodes)
+    out = np.zeros(4, dtype=np.float64)
+    lib().orc_wide4_check.restype = C.c_int
+    rc = lib().orc_wide4_check(_p(wnodes), C.c_int64(len(wnodes) // 16), _p(nodes), C.c_int64(nodes.nbytes), C.c_int(layout), _p(out))
+    if rc != 0:
+        raise AssertionError(f"Wide4 array inconsistent with its source tree (code {rc})")
+    return dict(num_wide=int(out[0]), num_leaves=int(out[1]), max_depth=int(out[2]), worst_overhang_steps=float(out[3]))
+
+
 def brute_trace(verts, tris, rays, need_closest=True, nthreads=0):
     verts, tris = _f32(verts).reshape(-1, 3), _i32(tris).reshape(-1, 3)
     rays = _f32(rays).reshape(-1, 8)

@@ -1,6 +1,7 @@
 // ORACLE — TEST INFRASTRUCTURE ONLY (see orc_math.hpp header).  Parity status per module: see orc_math.hpp.
 // Plain-C entry points for the ctypes loader in oracle/__init__.py.
 #include "orc_bvh.hpp"
+#include "orc_wide.hpp"
 #include "orc_lbvh.hpp"
 #include "orc_raygen.hpp"
 #ifdef _OPENMP
@@ -101,6 +102,15 @@ void orc_compact_trace(const int32_t* nodes, const int32_t* woop, const int32_t*
                        const float* rays, int n, int needClosest, int32_t* results, uint32_t* counters, int nthreads)
 {
     trace_compact(nodes, woop, triIndex, (const Ray*)rays, (RayResult*)results, n, needClosest != 0, counters, nthreads);
+}
+void orc_wide4_trace(const uint32_t* wnodes, const int32_t* woop, const int32_t* triIndex,
+                     const float* rays, int n, int needClosest, int32_t* results, uint32_t* counters, int nthreads)
+{
+    trace_wide4(wnodes, woop, triIndex, (const Ray*)rays, (RayResult*)results, n, needClosest != 0, counters, nthreads);
+}
+int orc_wide4_check(const uint32_t* wnodes, int64_t numWide, const int32_t* nodes, int64_t nodeBytes, int layout, double* out4)
+{
+    return check_wide4(wnodes, (size_t)numWide, nodes, (size_t)nodeBytes, layout, out4);
 }
 void orc_brute_trace(const float* vtx, int nv, const int32_t* tri, int nt, const float* rays, int n, int needClosest, int32_t* results, int nthreads)
 {
