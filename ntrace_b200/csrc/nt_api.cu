@@ -179,7 +179,7 @@ int ensure_traversal_form()
 // derive the Wide4 node array from the resident Compact / Compact2 nodes (host conversion: nt_wide.cu); caller holds the mutex
 int ensure_wide_form()
 {
-    if (g.kernel != Kernel_Wide4Persistent || g.wideValid) return 0;
+    if ((g.kernel != Kernel_Wide4Persistent && g.kernel != Kernel_Wide4Mr) || g.wideValid) return 0;
     std::vector<int32_t> h(g.nodeBytes / 4);
     NT_CUDA(cudaMemcpyAsync(h.data(), g.nodes.p, g.nodeBytes, cudaMemcpyDeviceToHost, g.stream));
     NT_CUDA(cudaStreamSynchronize(g.stream));
@@ -455,6 +455,13 @@ int nt_set_kernel(const char* name)
         {"b200_wide4", Kernel_Wide4Persistent, Layout_Compact, false},
         {"b200_wide4_fastmath", Kernel_Wide4Persistent, Layout_Compact, true},
         {"b200_wide4_compact2", Kernel_Wide4Persistent, Layout_Compact2, false},
+        // two rays per lane, phase-scheduled (nt_wide.cu "mr"): over the binary nodes (bit-identical to the one-ray kernels) and over Wide4
+        {"b200_mr", Kernel_BinaryMr, Layout_Compact, false},
+        {"b200_mr_fastmath", Kernel_BinaryMr, Layout_Compact, true},
+        {"b200_mr_compact2", Kernel_BinaryMr, Layout_Compact2, false},
+        {"b200_wide4_mr", Kernel_Wide4Mr, Layout_Compact, false},
+        {"b200_wide4_mr_fastmath", Kernel_Wide4Mr, Layout_Compact, true},
+        {"b200_wide4_mr_compact2", Kernel_Wide4Mr, Layout_Compact2, false},
         // reference kernel file names (src/rt/kernels/*.cu) accepted as aliases with their layouts AND their arithmetic, so a config
         // that names one of them gets the results that kernel produces
         {"fermi_speculative_while_while", Kernel_PlainSpeculative, Layout_Compact, true},

@@ -32,6 +32,8 @@ enum TraceKernelId : int {
     Kernel_PersistentSpeculative = 0,   // persistent while-while, warp-level dynamic ray fetch, speculative leaf
     Kernel_PlainSpeculative = 1,        // one thread per ray, speculative while-while (fermi-style launch shape)
     Kernel_Wide4Persistent = 2,         // persistent speculative while-while over the derived 4-wide quantised node array (nt_wide.cu)
+    Kernel_BinaryMr = 3,                // two rays per lane, phase-scheduled (nt_wide.cu "mr"), binary Compact / Compact2 nodes
+    Kernel_Wide4Mr = 4,                 // the same over the Wide4 node array
     Kernel_Count
 };
 
@@ -57,6 +59,7 @@ constexpr int kWideMaxDepth = 42;       // three pushes per level at most: 1 + 3
 int convert_compact_to_wide4_host(const int32_t* nodes, size_t nodeBytes, int layout, size_t woopRows,
                                   std::vector<uint32_t>& out, int* outMaxDepth, std::string* err);
 cudaError_t launch_trace_wide4(const TraceLaunch& a, int* outNumLaunches);
+cudaError_t launch_trace_mr(const TraceLaunch& a, int* outNumLaunches);
 KernelConfig trace_kernel_config(int kernel, int layout);
 
 // ---- ray generation (nt_raygen.cu) ------------------------------------------------------------

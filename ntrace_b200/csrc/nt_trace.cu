@@ -337,6 +337,9 @@ cudaError_t launch_trace(const TraceLaunch& a, int* launches)
         return c2 ? launch_one<Layout_Compact2, false>(a, launches) : launch_one<Layout_Compact, false>(a, launches);
     case Kernel_Wide4Persistent:
         return launch_trace_wide4(a, launches);
+    case Kernel_BinaryMr:
+    case Kernel_Wide4Mr:
+        return launch_trace_mr(a, launches);
     default:
         return cudaErrorInvalidValue;
     }

@@ -365,6 +365,298 @@ trace_wide4_kernel(int numRays, int anyHit, int fetchThreshold, unsigned oneBits
 #undef NT_POP
 }
 
+// ================================================================================================================
+// Multi-ray lanes ("mr" kernels).  profiles/r2a_binding_*.json: both the binary and the Wide4 kernel execute their instructions
+// with 11-12 of 32 lanes on secondary rays — a lane whose ray waits for the other phase (holds a leaf during the node phase, sits at
+// a node during the leaf phase, or has finished) idles, and issue slots / the ALU pipe are what bind.  Here every lane owns TWO
+// rays whose state lives in shared memory (64 bytes + a short stack each); a warp step is ONE phase chosen by vote:
+//   NODE   every lane steps whichever of its two rays sits at an inner node,
+//   LEAF   every lane runs the Woop tests of the leaf whichever of its rays sits at,
+//   FETCH  every lane with a free slot takes a new ray from the global counter (one atomicAdd per warp, as before).
+// A lane idles only when neither of its rays fits the phase.  Per-ray traversal order is the depth-first order of the tree, exactly
+// as in the one-ray kernels (which only postpone leaves, never reorder them), so results are bit-identical to theirs, any-hit ids
+// included.  Ray state: f0 = (orig.xyz, tmin)  f1 = (dir.xyz, hitIndex)  f2 = (idir.xyz, hitT)  f3 = (hitU, hitV, rayidx, -).
+// ================================================================================================================
+enum : int { kFmtCompact = 0, kFmtCompact2 = 1, kFmtWide4 = 2 };
+constexpr int kMrLocal = 124;                  // stack entries beyond the shared-memory part, per ray (local memory, rarely touched)
+
+template <int BLOCK, int SMEM_N, bool FAST, int FMT>
+__global__ void __launch_bounds__(BLOCK)
+trace_mr_kernel(int numRays, int anyHit, int fetchThreshold, int leafThreshold, unsigned oneBits,
+                const float4* __restrict__ rays, int4* __restrict__ results,
+                const float4* __restrict__ nodes, const float4* __restrict__ woop,
+                const int* __restrict__ triIndices, int* __restrict__ warpCounter)
+{
+    extern __shared__ float4 s_dyn[];
+    const int tid = threadIdx.x;
+    const unsigned lane = tid & 31;
+    float4* const F = s_dyn + tid;                                              // field f of slot k: F[(f * 2 + k) * BLOCK]
+    int* const S = reinterpret_cast<int*>(s_dyn + 8 * BLOCK) + tid;             // stack entry e of slot k: S[(k * SMEM_N + e) * BLOCK]
+    int l_stack[2][kMrLocal];
+    const unsigned one = oneBits;
+
+    int cur0 = kEntrypointSentinel, cur1 = kEntrypointSentinel;                 // sentinel = free slot
+    int sp0 = 0, sp1 = 0;
+    bool more = true;                                                           // warp-uniform: the global counter still has rays
+
+#define MR_PUSH(v)  do { if (sp < SMEM_N) Sk[sp * BLOCK] = (v); else l_stack[k][sp - SMEM_N] = (v); ++sp; } while (0)
+#define MR_POP(dst) do { if (sp == 0) (dst) = kEntrypointSentinel; else { --sp; (dst) = (sp < SMEM_N) ? Sk[sp * BLOCK] : l_stack[k][sp - SMEM_N]; } } while (0)
+    // ray in slot k has finished: one int4 result store (id remapped through triIndex; a miss keeps t = tmax)
+#define MR_FINISH()                                                                                                          \
+    do {                                                                                                                     \
+        const float4 r3 = Fk[6 * BLOCK];                                                                                     \
+        const int hi = __float_as_int(Fk[2 * BLOCK].w);                                                                      \
+        const float ht = Fk[4 * BLOCK].w;                                                                                    \
+        int id = hi;                                                                                                         \
+        if (id != -1) id = __ldg(triIndices + id);                                                                           \
+        __stcs(results + __float_as_int(r3.z), make_int4(id, __float_as_int(ht), __float_as_int(r3.x), __float_as_int(r3.y))); \
+    } while (0)
+
+    for (;;) {
+        const bool e0 = cur0 == kEntrypointSentinel, e1 = cur1 == kEntrypointSentinel;
+        const bool n0 = (unsigned)cur0 < (unsigned)kEntrypointSentinel, n1 = (unsigned)cur1 < (unsigned)kEntrypointSentinel;
+        const unsigned mE = more ? __ballot_sync(0xffffffffu, e0 || e1) : 0u;
+        const unsigned mN = __ballot_sync(0xffffffffu, n0 || n1);
+        const unsigned mL = __ballot_sync(0xffffffffu, cur0 < 0 || cur1 < 0);
+        const int cN = __popc(mN), cL = __popc(mL);
+
+        if (mE && (__popc(mE) >= fetchThreshold || (mN | mL) == 0u)) {
+            // ---------------- FETCH ----------------
+            const bool need = e0 || e1;
+            const int n = __popc(mE);
+            const int rank = __popc(mE & ((1u << lane) - 1u));
+            const int leader = __ffs(mE) - 1;
+            int base = 0;
+            if ((int)lane == leader) base = atomicAdd(warpCounter, n);
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (base + n >= numRays) more = false;
+            const int rayidx = base + rank;
+            if (need && rayidx < numRays) {
+                const int k = e0 ? 0 : 1;
+                float4* const Fk = F + k * BLOCK;
+                float4 o, d;
+                wld256_cs(rays + rayidx * 2, o, d);
+                const float ooeps = exp2f(-80.0f);                      // fermi_speculative_while_while.cu:94-98
+                const float ix = 1.0f / (fabsf(d.x) > ooeps ? d.x : copysignf(ooeps, d.x));
+                const float iy = 1.0f / (fabsf(d.y) > ooeps ? d.y : copysignf(ooeps, d.y));
+                const float iz = 1.0f / (fabsf(d.z) > ooeps ? d.z : copysignf(ooeps, d.z));
+                Fk[0] = o;                                                              // (orig, tmin)
+                Fk[2 * BLOCK] = make_float4(d.x, d.y, d.z, __int_as_float(-1));         // (dir, hitIndex)
+                Fk[4 * BLOCK] = make_float4(ix, iy, iz, d.w);                           // (idir, hitT = tmax)
+                Fk[6 * BLOCK] = make_float4(0.0f, 0.0f, __int_as_float(rayidx), 0.0f);  // (hitU, hitV, rayidx, -)
+                if (k) { cur1 = 0; sp1 = 0; } else { cur0 = 0; sp0 = 0; }
+            }
+        } else if ((mN | mL) == 0u) {
+            break;
+        } else if (mL && (cN == 0 || cL >= leafThreshold || cL >= cN)) {
+            // ---------------- LEAF: Woop tests of one leaf (Util.cpp:99-127, identical to nt_trace.cu) ----------------
+            if (cur0 < 0 || cur1 < 0) {
+                const int k = (cur0 < 0) ? 0 : 1;
+                float4* const Fk = F + k * BLOCK;
+                int* const Sk = S + k * SMEM_N * BLOCK;
+                int sp = k ? sp1 : sp0;
+                int nodeAddr;
+                const float4 f0 = Fk[0], f1 = Fk[2 * BLOCK];
+                const float origx = f0.x, origy = f0.y, origz = f0.z, tmin = f0.w, dirx = f1.x, diry = f1.y, dirz = f1.z;
+                float hitT = Fk[4 * BLOCK].w, hitU = 0.0f, hitV = 0.0f;
+                int hitIndex = -1;
+                bool done = false;
+                int triAddr = ~(k ? cur1 : cur0);
+                float4 v00 = __ldg(woop + triAddr);
+                for (;;) {
+                    if (__float_as_int(v00.x) == (int)0x80000000) break;
+                    float t;
+                    if (FAST) {
+                        const float Oz = v00.w - origx * v00.x - origy * v00.y - origz * v00.z;
+                        t = Oz * __fdividef(1.0f, dirx * v00.x + diry * v00.y + dirz * v00.z);
+                    } else {
+                        const float Oz = __fsub_rn(__fsub_rn(__fsub_rn(v00.w, __fmul_rn(origx, v00.x)), __fmul_rn(origy, v00.y)), __fmul_rn(origz, v00.z));
+                        const float dd = __fadd_rn(__fadd_rn(__fmul_rn(dirx, v00.x), __fmul_rn(diry, v00.y)), __fmul_rn(dirz, v00.z));
+                        t = __fmul_rn(Oz, __frcp_rn(dd));
+                    }
+                    if (t > tmin && t < hitT) {
+                        const float4 v11 = __ldg(woop + triAddr + 1);
+                        float u;
+                        if (FAST) u = (v11.w + origx * v11.x + origy * v11.y + origz * v11.z) + t * (dirx * v11.x + diry * v11.y + dirz * v11.z);
+                        else {
+                            const float Ou = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(v11.x, origx), __fmul_rn(v11.y, origy)), __fmul_rn(v11.z, origz)), v11.w);
+                            const float Du = __fadd_rn(__fadd_rn(__fmul_rn(v11.x, dirx), __fmul_rn(v11.y, diry)), __fmul_rn(v11.z, dirz));
+                            u = __fadd_rn(Ou, __fmul_rn(t, Du));
+                        }
+                        if (u >= 0.0f) {
+                            const float4 v22 = __ldg(woop + triAddr + 2);
+                            float v;
+                            if (FAST) v = (v22.w + origx * v22.x + origy * v22.y + origz * v22.z) + t * (dirx * v22.x + diry * v22.y + dirz * v22.z);
+                            else {
+                                const float Ov = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(v22.x, origx), __fmul_rn(v22.y, origy)), __fmul_rn(v22.z, origz)), v22.w);
+                                const float Dv = __fadd_rn(__fadd_rn(__fmul_rn(v22.x, dirx), __fmul_rn(v22.y, diry)), __fmul_rn(v22.z, dirz));
+                                v = __fadd_rn(Ov, __fmul_rn(t, Dv));
+                            }
+                            if (v >= 0.0f && (FAST ? (u + v) : __fadd_rn(u, v)) <= 1.0f) {
+                                hitT = t; hitU = u; hitV = v;
+                                hitIndex = triAddr;
+                                if (anyHit) { done = true; break; }
+                            }
+                        }
+                    }
+                    triAddr += 3;
+                    v00 = __ldg(woop + triAddr);
+                }
+                if (hitIndex != -1) {                        // a closer hit in this leaf: publish it to the ray's state
+                    reinterpret_cast<float*>(Fk + 2 * BLOCK)[3] = __int_as_float(hitIndex);
+                    reinterpret_cast<float*>(Fk + 4 * BLOCK)[3] = hitT;
+                    reinterpret_cast<float2*>(Fk + 6 * BLOCK)[0] = make_float2(hitU, hitV);
+                }
+                if (done) nodeAddr = kEntrypointSentinel; else MR_POP(nodeAddr);
+                if (nodeAddr == kEntrypointSentinel) MR_FINISH();
+                if (k) { cur1 = nodeAddr; sp1 = sp; } else { cur0 = nodeAddr; sp0 = sp; }
+            }
+        } else {
+            // ---------------- NODE: one inner-node step ----------------
+            if (n0 || n1) {
+                const int k = n0 ? 0 : 1;
+                float4* const Fk = F + k * BLOCK;
+                int* const Sk = S + k * SMEM_N * BLOCK;
+                int sp = k ? sp1 : sp0;
+                int nodeAddr = k ? cur1 : cur0;
+                const float4 f0 = Fk[0], f2 = Fk[4 * BLOCK];
+                const float tmin = f0.w, hitT = f2.w;
+                const float idirx = f2.x, idiry = f2.y, idirz = f2.z;
+                const float oodx = f0.x * idirx, oody = f0.y * idiry, oodz = f0.z * idirz;
+                if (FMT == kFmtWide4) {
+                    const float4* ptr = nodes + (size_t)nodeAddr * 4;
+                    float4 A0, A1, B0, B1;
+                    wld256_nc(ptr, A0, A1);
+                    wld256_nc(ptr + 2, B0, B1);
+                    const float ax = A0.w * idirx, ay = A1.x * idiry, az = A1.y * idirz;
+                    const float bx = fmaf(A0.x, idirx, -oodx) - ax;
+                    const float by = fmaf(A0.y, idiry, -oody) - ay;
+                    const float bz = fmaf(A0.z, idirz, -oodz) - az;
+                    const bool ngx = idirx < 0.0f, ngy = idiry < 0.0f, ngz = idirz < 0.0f;
+                    const unsigned qlx = __float_as_uint(A1.z), qly = __float_as_uint(A1.w), qlz = __float_as_uint(B0.x);
+                    const unsigned qhx = __float_as_uint(B0.y), qhy = __float_as_uint(B0.z), qhz = __float_as_uint(B0.w);
+                    const unsigned nx = ngx ? qhx : qlx, fx = ngx ? qlx : qhx;
+                    const unsigned ny = ngy ? qhy : qly, fy = ngy ? qly : qhy;
+                    const unsigned nz = ngz ? qhz : qlz, fz = ngz ? qlz : qhz;
+                    int k0, k1, k2, k3;
+#define NT_CHILD(I, K)                                                                                                    \
+                    {                                                                                                     \
+                        const float tn = wfmax3(fmaf(qplane<I>(nx, one), ax, bx), fmaf(qplane<I>(ny, one), ay, by),       \
+                                                fmaxf(fmaf(qplane<I>(nz, one), az, bz), tmin));                           \
+                        const float tf = wfmin3(fmaf(qplane<I>(fx, one), ax, bx), fmaf(qplane<I>(fy, one), ay, by),       \
+                                                fminf(fmaf(qplane<I>(fz, one), az, bz), hitT));                           \
+                        K = (tn <= tf) ? ((__float_as_int(tn) & ~3) | I) : 0x7fffffff;                                    \
+                    }
+                    NT_CHILD(0, k0) NT_CHILD(1, k1) NT_CHILD(2, k2) NT_CHILD(3, k3)
+#undef NT_CHILD
+                    cas(k0, k1); cas(k2, k3); cas(k0, k2); cas(k1, k3); cas(k1, k2);
+                    const int l0 = __float_as_int(B1.x), l1 = __float_as_int(B1.y), l2 = __float_as_int(B1.z), l3 = __float_as_int(B1.w);
+#define NT_LINK(K) (((K) & 2) ? (((K) & 1) ? l3 : l2) : (((K) & 1) ? l1 : l0))
+                    if (k0 == 0x7fffffff) {
+                        MR_POP(nodeAddr);
+                    } else {
+                        nodeAddr = NT_LINK(k0);
+                        if (k1 != 0x7fffffff) {
+                            if (k2 != 0x7fffffff) {
+                                if (k3 != 0x7fffffff) MR_PUSH(NT_LINK(k3));
+                                MR_PUSH(NT_LINK(k2));
+                            }
+                            MR_PUSH(NT_LINK(k1));
+                        }
+                    }
+#undef NT_LINK
+                } else {
+                    // binary Compact / Compact2 node (CudaBVH.hpp:43-47), slab test as nt_trace.cu
+                    const float4* ptr = (FMT == kFmtCompact2) ? nodes + nodeAddr
+                                                              : reinterpret_cast<const float4*>(reinterpret_cast<const char*>(nodes) + nodeAddr);
+                    float4 n0xy, n1xy, nz, cn;
+                    wld256_nc(ptr, n0xy, n1xy);
+                    wld256_nc(ptr + 2, nz, cn);
+                    int c0idx = __float_as_int(cn.x), c1idx = __float_as_int(cn.y);
+                    const float c0lox = n0xy.x * idirx - oodx, c0hix = n0xy.y * idirx - oodx;
+                    const float c0loy = n0xy.z * idiry - oody, c0hiy = n0xy.w * idiry - oody;
+                    const float c0loz = nz.x * idirz - oodz,   c0hiz = nz.y * idirz - oodz;
+                    const float c1loz = nz.z * idirz - oodz,   c1hiz = nz.w * idirz - oodz;
+                    const float c0min = wfmax3(fminf(c0lox, c0hix), fminf(c0loy, c0hiy), fmaxf(fminf(c0loz, c0hiz), tmin));
+                    const float c0max = wfmin3(fmaxf(c0lox, c0hix), fmaxf(c0loy, c0hiy), fminf(fmaxf(c0loz, c0hiz), hitT));
+                    const float c1lox = n1xy.x * idirx - oodx, c1hix = n1xy.y * idirx - oodx;
+                    const float c1loy = n1xy.z * idiry - oody, c1hiy = n1xy.w * idiry - oody;
+                    const float c1min = wfmax3(fminf(c1lox, c1hix), fminf(c1loy, c1hiy), fmaxf(fminf(c1loz, c1hiz), tmin));
+                    const float c1max = wfmin3(fmaxf(c1lox, c1hix), fmaxf(c1loy, c1hiy), fminf(fmaxf(c1loz, c1hiz), hitT));
+                    const bool trav0 = (c0max >= c0min), trav1 = (c1max >= c1min);
+                    if (!trav0 && !trav1) {
+                        MR_POP(nodeAddr);
+                    } else {
+                        nodeAddr = trav0 ? c0idx : c1idx;
+                        if (trav0 && trav1) {
+                            if (c1min < c0min) { const int t = nodeAddr; nodeAddr = c1idx; c1idx = t; }
+                            MR_PUSH(c1idx);
+                        }
+                    }
+                }
+                if (nodeAddr == kEntrypointSentinel) MR_FINISH();
+                if (k) { cur1 = nodeAddr; sp1 = sp; } else { cur0 = nodeAddr; sp0 = sp; }
+            }
+        }
+    }
+#undef MR_PUSH
+#undef MR_POP
+#undef MR_FINISH
+}
+
+struct MrTuning { int smemStack; int ctasPerSM; int fetchThreshold; int leafThreshold; };
+MrTuning mr_tuning()
+{
+    static MrTuning t = [] {
+        MrTuning r{8, 0, 12, 16};
+        if (const char* e = getenv("NT_MR_SMEM")) r.smemStack = atoi(e);
+        if (const char* e = getenv("NT_MR_CTAS")) r.ctasPerSM = atoi(e);          // 0 = as many as fit
+        if (const char* e = getenv("NT_MR_FETCH")) r.fetchThreshold = atoi(e);
+        if (const char* e = getenv("NT_MR_LEAF")) r.leafThreshold = atoi(e);
+        return r;
+    }();
+    return t;
+}
+
+template <int SMEM_N, bool FAST, int FMT>
+cudaError_t launch_mr_variant(const TraceLaunch& a, int* launches)
+{
+    auto kern = trace_mr_kernel<kWideBlock, SMEM_N, FAST, FMT>;
+    constexpr int smemBytes = kWideBlock * (8 * 16 + 2 * SMEM_N * 4);
+    static int blocksPerSM = 0;
+    if (!blocksPerSM) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smemBytes);
+        if (e != cudaSuccess) return e;
+        int want = mr_tuning().ctasPerSM;
+        // shared memory the wanted CTAs need (+1 KB per CTA the hardware reserves); what is left of the 228 KB stays L1
+        int carve = 100;
+        if (want > 0) { carve = (want * (smemBytes + 1024) * 100 + 228 * 1024 - 1) / (228 * 1024); if (carve > 100) carve = 100; }
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+        if (e != cudaSuccess) return e;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSM, kern, kWideBlock, smemBytes);
+        if (e != cudaSuccess) return e;
+        if (want > 0 && blocksPerSM > want) blocksPerSM = want;
+        if (blocksPerSM < 1) blocksPerSM = 1;
+    }
+    int grid = (a.numRays + 2 * kWideBlock - 1) / (2 * kWideBlock);
+    if (grid > a.numSMs * blocksPerSM) grid = a.numSMs * blocksPerSM;
+    const MrTuning t = mr_tuning();
+    kern<<<grid, kWideBlock, smemBytes, a.stream>>>(a.numRays, a.anyHit, t.fetchThreshold, t.leafThreshold, 0x3F800000u, a.rays, a.results,
+                                                     FMT == kFmtWide4 ? a.wideNodes : a.nodes, a.woop, a.triIndices, a.warpCounter);
+    if (launches) *launches = 1;
+    return cudaGetLastError();
+}
+
+template <bool FAST, int FMT>
+cudaError_t launch_mr_stack(const TraceLaunch& a, int* launches)
+{
+    switch (mr_tuning().smemStack) {
+    case 4:  return launch_mr_variant<4, FAST, FMT>(a, launches);
+    case 12: return launch_mr_variant<12, FAST, FMT>(a, launches);
+    default: return launch_mr_variant<8, FAST, FMT>(a, launches);
+    }
+}
+
 struct WideTuning { int smemStack; int carveout; int fetchThreshold; };
 WideTuning wide_tuning()
 {
@@ -408,6 +700,19 @@ cudaError_t launch_wide_stack(const TraceLaunch& a, int* launches)
 }
 
 } // namespace
+
+cudaError_t launch_trace_mr(const TraceLaunch& a, int* launches)
+{
+    if (a.numRays <= 0) { if (launches) *launches = 0; return cudaSuccess; }
+    // 256-bit loads: 32-byte aligned rays, 64-byte aligned nodes (true for everything the library allocates)
+    if ((reinterpret_cast<size_t>(a.rays) & 31) || (reinterpret_cast<size_t>(a.nodes) & 63)) return cudaErrorInvalidValue;
+    if (a.kernel == Kernel_Wide4Mr) {
+        if (!a.wideNodes || (reinterpret_cast<size_t>(a.wideNodes) & 63)) return cudaErrorInvalidValue;
+        return a.fast ? launch_mr_stack<true, kFmtWide4>(a, launches) : launch_mr_stack<false, kFmtWide4>(a, launches);
+    }
+    if (a.layout == Layout_Compact2) return a.fast ? launch_mr_stack<true, kFmtCompact2>(a, launches) : launch_mr_stack<false, kFmtCompact2>(a, launches);
+    return a.fast ? launch_mr_stack<true, kFmtCompact>(a, launches) : launch_mr_stack<false, kFmtCompact>(a, launches);
+}
 
 cudaError_t launch_trace_wide4(const TraceLaunch& a, int* launches)
 {
