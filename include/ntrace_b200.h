@@ -142,6 +142,10 @@ int nt_bvh_convert(int layout);
  * outWideNodes may be NULL to query *outWideBytes; *outMaxDepth (optional) = depth of the Wide4 tree. */
 int nt_bvh_wide4_convert_host(int layout, const void* nodes, size_t nodeBytes, size_t woopBytes,
                               void* outWideNodes, size_t outCapacityBytes, size_t* outWideBytes, int* outMaxDepth);
+/* NEW: generation of the resident BVH.  The library keeps ONE resident BVH (the reference's tracer keeps one CudaAS pointer,
+ * CudaBVHTracer.hpp:46); every upload / alloc / build / convert replaces it and bumps this counter (0 = none).  A host-side handle
+ * that skips the upload because "its" BVH is resident records the value after its build and compares it before tracing. */
+int nt_bvh_generation(uint64_t* outGeneration);
 /* sizes[3] = bytes of (nodes, woop, triIndex); layout of the resident BVH in *outLayout. */
 int nt_bvh_sizes(size_t sizes[3], int* outLayout);
 /* CudaBVH::serialize source buffers (CudaBVH.cpp:105-125): copy the device BVH out (host or device dst). */

@@ -78,6 +78,7 @@ struct Context {
     size_t nodeBytes = 0, woopBytes = 0, idxBytes = 0;
     int bvhLayout = Layout_Max;
     bool haveBVH = false;
+    uint64_t generation = 0;       // bumped whenever the resident BVH is replaced or re-laid-out (nt_bvh_generation)
     // a BVH uploaded in one of the basic layouts (AOS/SOA) is kept as given in src* (what download / device_ptrs /
     // broadcast see) and rewritten on the device into nodes/woop/triIndex (Compact form) before the first trace
     DevBuf srcNodes, srcWoop, srcIdx, layoutScratch;
@@ -96,6 +97,8 @@ struct Context {
     // staging
     DevBuf stRays, stResults, stA, stB, stC, stD, stE;
     DevBuf counters;          // [0] warp counter, [1] hit counter
+    int* errHost = nullptr;   // mapped pinned word the trace kernels OR 1 into on a traversal-stack overflow (errDev: its device address)
+    int* errDev = nullptr;
     DevBuf pixelTable; int ptW = 0, ptH = 0;
     DevBuf sceneVerts, sceneTris;
 };
@@ -154,6 +157,17 @@ int copy_back(void* hostDst, const void* dev, size_t bytes)
 
 bool is_basic_layout(int layout) { return layout >= Layout_AOS_AOS && layout <= Layout_SOA_SOA; }
 
+const char* link_range_error(int layout, size_t nodeBytes, size_t woopBytes)
+{
+    if (layout == Layout_Compact && nodeBytes >= (size_t)kEntrypointSentinel)
+        return "ntrace_b200: BVHLayout_Compact stores child links as 32-bit byte offsets below 0x76543210: node buffers of 1.98 GB or more need BVHLayout_Compact2";
+    if (layout == Layout_Compact2 && nodeBytes / 16 >= (size_t)kEntrypointSentinel)
+        return "ntrace_b200: node buffer too large for 32-bit BVHLayout_Compact2 links";
+    if (woopBytes / 16 >= 0x7fffffffull)
+        return "ntrace_b200: triangle buffer too large for 32-bit leaf links";
+    return nullptr;
+}
+
 // (re)build the traversal form of a basic-layout BVH; caller holds the mutex
 int ensure_traversal_form()
 {
@@ -205,9 +219,23 @@ int join_kernel_streams()
     return 0;
 }
 
+// after a synchronisation point: did any launch since the last check overflow a ray's traversal stack?
+int check_trace_error()
+{
+    if (g.errHost && *g.errHost) {
+        *g.errHost = 0;
+        set_error("ntrace_b200: BVH too deep for the traversal stack (96 entries; the reference's STACK_SIZE is 64): results of the last launches are incomplete");
+        return 1;
+    }
+    return 0;
+}
+
 int require_init(bool join = true)
 {
     if (!g.inited) { set_error("ntrace_b200: nt_init() has not been called (no CUDA device selected; there is no CPU fallback)"); return 1; }
+    // the caller may be another host thread, or the host framework may have switched devices since nt_init
+    int cur = -1;
+    if (cudaGetDevice(&cur) != cudaSuccess || cur != g.device) NT_CUDA(cudaSetDevice(g.device));
     return join ? join_kernel_streams() : 0;
 }
 
@@ -304,6 +332,9 @@ int nt_init(int device_ordinal)
     }
     NT_CUDA(g.counters.reserve(256));
     NT_CUDA(cudaMemsetAsync(g.counters.p, 0, 256, g.stream));
+    NT_CUDA(cudaHostAlloc((void**)&g.errHost, sizeof(int), cudaHostAllocMapped));
+    *g.errHost = 0;
+    NT_CUDA(cudaHostGetDevicePointer((void**)&g.errDev, g.errHost, 0));
     NT_CUDA(cudaStreamSynchronize(g.stream));
     g.launches = 0;
     g.inited = true;
@@ -326,11 +357,13 @@ void nt_shutdown(void)
     for (DevBuf* b : bufs) b->release();
     release_build_scratch();
     release_sort_scratch();
+    reset_launch_caches();         // occupancy / carve-out decisions belong to the device they were taken on
     for (int i = 0; i < Context::kAsyncSlots; i++) {
         g.async[i].rays.release(); g.async[i].results.release();
         cudaEventDestroy(g.async[i].evIn); cudaEventDestroy(g.async[i].evKa); cudaEventDestroy(g.async[i].evKb); cudaEventDestroy(g.async[i].evOut);
     }
     cudaEventDestroy(g.evA); cudaEventDestroy(g.evB);
+    if (g.errHost) cudaFreeHost(g.errHost);
     for (int i = 0; i < 8; i++) cudaEventDestroy(g.userEv[i]);
     for (int i = 0; i < Context::kMaxChunks; i++) { cudaEventDestroy(g.evIn[i]); cudaEventDestroy(g.evKa[i]); cudaEventDestroy(g.evKb[i]); }
     cudaStreamDestroy(g.sIn); cudaStreamDestroy(g.sOut);
@@ -435,7 +468,7 @@ int nt_synchronize(void)
     std::lock_guard<std::mutex> lock(g_mutex);
     if (require_init()) return 1;
     NT_CUDA(cudaStreamSynchronize(g.stream));
-    return 0;
+    return check_trace_error();
 }
 
 int nt_set_kernel(const char* name)
@@ -505,6 +538,8 @@ int nt_bvh_alloc(int layout, size_t nodeBytes, size_t woopBytes, size_t idxBytes
             set_error("ntrace_b200: inconsistent CudaBVH buffer sizes (AOS/SOA layouts: nodes and Woop triangles in 64 B records, one S32 index per triangle)");
             return 1;
         }
+        g.haveBVH = false;             // a failed reserve must not leave the previous BVH's sizes over reallocated buffers
+        g.generation++;
         NT_CUDA(g.srcNodes.reserve(nodeBytes));
         NT_CUDA(g.srcWoop.reserve(woopBytes));
         NT_CUDA(g.srcIdx.reserve(idxBytes));
@@ -520,6 +555,11 @@ int nt_bvh_alloc(int layout, size_t nodeBytes, size_t woopBytes, size_t idxBytes
         set_error("ntrace_b200: inconsistent CudaBVH buffer sizes (nodes multiple of 64 B, woop of 16 B, one index per woop float4)");
         return 1;
     }
+    // child links are 32-bit and must stay below the EntrypointSentinel 0x76543210 that ends a traversal (a link at or above it
+    // would make the kernel spin): byte offsets for Compact, offsets / 16 for Compact2; leaf links ~woopIndex need woopIndex < 2^31
+    if (const char* why = link_range_error(layout, nodeBytes, woopBytes)) { set_error(why); return 1; }
+    g.haveBVH = false;
+    g.generation++;
     g.basic = false; g.converted = false; g.wideValid = false;
     NT_CUDA(g.nodes.reserve(nodeBytes));
     NT_CUDA(g.woop.reserve(woopBytes));
@@ -567,6 +607,7 @@ int nt_bvh_build(int builder, const float* vtxPos, int numVerts, const int32_t* 
     out.sortedKeys = &g.sortedKeys; out.sortedIdx = &g.sortedIdx;
     out.nodeBytes = out.woopBytes = out.idxBytes = 0;
     g.haveBVH = false;
+    g.generation++;
     g.basic = false; g.converted = false; g.wideValid = false;
     NT_CUDA(cudaEventRecord(g.evA, g.stream));
     int launches = 0;
@@ -617,8 +658,11 @@ int nt_bvh_convert(int layout)
         if (ensure_traversal_form()) return 1;                      // AOS/SOA -> Compact (nt_layout.cu)
         g.basic = false; g.converted = false;
         g.bvhLayout = Layout_Compact;
+        g.generation++;
     }
     if (g.bvhLayout == layout) return 0;
+    if (const char* why = link_range_error(layout, g.nodeBytes, g.woopBytes)) { set_error(why); return 1; }
+    g.generation++;
     const bool toCompact2 = (layout == Layout_Compact2);
     NT_CUDA(rescale_compact_links(g.nodes.as<int4>(), g.nodeBytes / 64, toCompact2 ? 1 : 16, toCompact2 ? 16 : 1, g.stream));
     g.launches += 1;
@@ -642,6 +686,15 @@ int nt_bvh_wide4_convert_host(int layout, const void* nodes, size_t nodeBytes, s
         if (outCapacityBytes < w.size() * 4) { set_error("ntrace_b200: output buffer too small for the Wide4 node array"); return 1; }
         memcpy(outWideNodes, w.data(), w.size() * 4);
     }
+    return 0;
+}
+
+int nt_bvh_generation(uint64_t* outGeneration)
+{
+    std::lock_guard<std::mutex> lock(g_mutex);
+    if (require_init()) return 1;
+    if (!outGeneration) { set_error("ntrace_b200: null output"); return 1; }
+    *outGeneration = g.haveBVH ? g.generation : 0;
     return 0;
 }
 
@@ -705,6 +758,7 @@ int nt_trace_batch(const float* rays, int32_t* results, int numRays, int needClo
     if (require_init(!overlapped)) return 1;
     if (numRays == 0) return 0;                                        // CudaBVHTracer.cpp:92-94
     if (numRays < 0 || !rays || !results) { set_error("ntrace_b200: invalid ray batch"); return 1; }
+    if (numRays > 0x3fffffff) { set_error("ntrace_b200: a batch holds at most 2^30 - 1 rays (32-bit ray indexing in the kernels)"); return 1; }
     if (!g.haveBVH) { set_error("CudaBVHTracer: No BVH!"); return 1; }                          // :98-99
     if (g.bvhLayout != g.kernelLayout) { set_error("CudaBVHTracer: Incorrect BVH layout!"); return 1; }  // :100-101
     if (ensure_traversal_form() || ensure_wide_form()) return 1;
@@ -720,7 +774,7 @@ int nt_trace_batch(const float* rays, int32_t* results, int numRays, int needClo
     a.kernel = g.kernel; a.fast = g.fastMath ? 1 : 0; a.layout = g.basic ? (int)Layout_Compact : g.kernelLayout; a.anyHit = needClosestHit ? 0 : 1;
     a.nodes = g.nodes.as<float4>(); a.woop = g.woop.as<float4>(); a.triIndices = g.triIndex.as<int>();
     a.wideNodes = g.wideNodes.as<float4>();
-    a.numSMs = g.numSMs; a.stream = g.stream;
+    a.numSMs = g.numSMs; a.stream = g.stream; a.errorFlag = g.errDev;
     int launches = 0;
 
     if (raysOnHost || resOnHost) {
@@ -760,7 +814,7 @@ int nt_trace_batch(const float* rays, int32_t* results, int numRays, int needClo
         float total = 0.0f;
         for (int i = 0; i < numChunks; i++) { float ms = 0.0f; NT_CUDA(cudaEventElapsedTime(&ms, g.evKa[i], g.evKb[i])); total += ms; }
         if (outSeconds) *outSeconds = total * 1.0e-3f;             // kernel time only, as the reference reports it
-        return 0;
+        return check_trace_error();
     }
 
     a.numRays = numRays; a.rays = (const float4*)raysDev; a.results = (int4*)resDev;
@@ -793,7 +847,7 @@ int nt_trace_batch(const float* rays, int32_t* results, int numRays, int needClo
     float ms = 0.0f;
     NT_CUDA(cudaEventElapsedTime(&ms, g.evA, g.evB));
     if (outSeconds) *outSeconds = ms * 1.0e-3f;
-    return 0;
+    return check_trace_error();
 }
 
 // Asynchronous form of nt_trace_batch for a host loop that keeps several independent batches in flight (the batches of a
@@ -808,7 +862,7 @@ int nt_trace_batch_async(const float* rays, int32_t* results, int numRays, int n
     if (slot < 0 || slot >= Context::kAsyncSlots) { set_error("ntrace_b200: async slot out of range"); return 1; }
     Context::AsyncSlot& s = g.async[slot];
     if (s.busy) { set_error("ntrace_b200: async slot still in flight; call nt_trace_wait first"); return 1; }
-    if (numRays <= 0 || !rays || !results) { set_error("ntrace_b200: invalid ray batch"); return 1; }
+    if (numRays <= 0 || numRays > 0x3fffffff || !rays || !results) { set_error("ntrace_b200: invalid ray batch"); return 1; }
     if (!g.haveBVH) { set_error("CudaBVHTracer: No BVH!"); return 1; }
     if (g.bvhLayout != g.kernelLayout) { set_error("CudaBVHTracer: Incorrect BVH layout!"); return 1; }
     if (ensure_traversal_form() || ensure_wide_form()) return 1;
@@ -836,7 +890,7 @@ int nt_trace_batch_async(const float* rays, int32_t* results, int numRays, int n
     a.kernel = g.kernel; a.fast = g.fastMath ? 1 : 0; a.layout = g.basic ? (int)Layout_Compact : g.kernelLayout; a.anyHit = needClosestHit ? 0 : 1;
     a.nodes = g.nodes.as<float4>(); a.woop = g.woop.as<float4>(); a.triIndices = g.triIndex.as<int>();
     a.wideNodes = g.wideNodes.as<float4>();
-    a.numSMs = g.numSMs; a.stream = g.stream;
+    a.numSMs = g.numSMs; a.stream = g.stream; a.errorFlag = g.errDev;
     a.numRays = numRays; a.rays = dRays; a.results = dRes;
     a.warpCounter = g.counters.as<int>() + 32 + slot;
     NT_CUDA(cudaMemsetAsync(a.warpCounter, 0, sizeof(int), g.stream));
@@ -870,7 +924,7 @@ int nt_trace_wait(int slot, float* outSeconds)
     float ms = 0.0f;
     NT_CUDA(cudaEventElapsedTime(&ms, s.evKa, s.evKb));
     if (outSeconds) *outSeconds = ms * 1.0e-3f;                 // kernel time only, like nt_trace_batch
-    return 0;
+    return check_trace_error();
 }
 
 int nt_raygen_primary(float* rays, int32_t* idToSlot, int32_t* slotToID, const float origin[3],

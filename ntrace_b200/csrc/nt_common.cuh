@@ -50,10 +50,14 @@ struct TraceLaunch {
     const float4* woop;       // device
     const int* triIndices;    // device
     int* warpCounter;         // device, zeroed before launch (persistent kernels only)
+    int* errorFlag = nullptr; // device-visible (mapped host) word; a kernel ORs 1 into it when a ray's traversal stack would overflow
     int numSMs;
     cudaStream_t stream;
 };
 cudaError_t launch_trace(const TraceLaunch& a, int* outNumLaunches);
+// occupancy / carve-out decisions are cached per kernel variant and per launch epoch; nt_shutdown starts a new epoch
+int launch_epoch();
+void reset_launch_caches();
 // nt_wide.cu: 4-wide quantised form of a Compact / Compact2 node buffer (host side; 16 words per node) and its traversal kernel
 constexpr int kWideMaxDepth = 42;       // three pushes per level at most: 1 + 3 * depth entries fit the kernel's 128-entry stack
 int convert_compact_to_wide4_host(const int32_t* nodes, size_t nodeBytes, int layout, size_t woopRows,

@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(BLOCK)
 trace_kernel(int numRays, int anyHit, int fetchThreshold,
              const float4* __restrict__ rays, int4* __restrict__ results,
              const float4* __restrict__ nodes, const float4* __restrict__ woop,
-             const int* __restrict__ triIndices, int* __restrict__ warpCounter)
+             const int* __restrict__ triIndices, int* __restrict__ warpCounter, int* __restrict__ errorFlag)
 {
     static_assert(SMEM_N >= 0 && SMEM_N <= kStackSize, "stack split");
     __shared__ int s_stack[(SMEM_N > 0 ? SMEM_N : 1) * BLOCK];
@@ -81,7 +81,9 @@ trace_kernel(int numRays, int anyHit, int fetchThreshold,
     const unsigned lane = tid & 31;
     int* const sbase = s_stack + tid;
 
-#define NT_PUSH(v)  do { ++sp; if (sp < SMEM_N) sbase[sp * BLOCK] = (v); else l_stack[sp - SMEM_N] = (v); } while (0)
+    // the bound check sits on the spill path only (taken on ~1e-4 of the pushes): a tree deeper than the stack drops the entry and
+    // raises the error flag instead of writing past l_stack
+#define NT_PUSH(v)  do { ++sp; if (sp < SMEM_N) sbase[sp * BLOCK] = (v); else if (sp < kStackSize) l_stack[sp - SMEM_N] = (v); else { --sp; *(volatile int*)errorFlag = 1; } } while (0)
 #define NT_POP(dst) do { (dst) = (sp < SMEM_N) ? sbase[sp * BLOCK] : l_stack[sp - SMEM_N]; --sp; } while (0)
 
     // Live state (registers).
@@ -279,8 +281,9 @@ template <int LAYOUT, int SMEM_N, bool PERSISTENT, bool FAST, bool WIDE>
 cudaError_t launch_variant(const TraceLaunch& a, int* launches)
 {
     auto kern = trace_kernel<LAYOUT, kBlock, SMEM_N, PERSISTENT, FAST, WIDE>;
-    static int blocksPerSM = 0;
-    if (!blocksPerSM) {
+    static int blocksPerSM = 0, epoch = -1;
+    if (epoch != launch_epoch()) {
+        epoch = launch_epoch();
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, tuning().carveout);
         if (e != cudaSuccess) return e;
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSM, kern, kBlock, 0);
@@ -289,7 +292,7 @@ cudaError_t launch_variant(const TraceLaunch& a, int* launches)
     }
     int grid = (a.numRays + kBlock - 1) / kBlock;
     if (PERSISTENT && grid > a.numSMs * blocksPerSM) grid = a.numSMs * blocksPerSM;   // one resident wave
-    kern<<<grid, kBlock, 0, a.stream>>>(a.numRays, a.anyHit, tuning().fetchThreshold, a.rays, a.results, a.nodes, a.woop, a.triIndices, a.warpCounter);
+    kern<<<grid, kBlock, 0, a.stream>>>(a.numRays, a.anyHit, tuning().fetchThreshold, a.rays, a.results, a.nodes, a.woop, a.triIndices, a.warpCounter, a.errorFlag);
     if (launches) *launches = 1;
     return cudaGetLastError();
 }
@@ -314,6 +317,10 @@ cudaError_t launch_one(const TraceLaunch& a, int* launches)
 }
 
 } // namespace
+
+static int g_launchEpoch = 0;
+int launch_epoch() { return g_launchEpoch; }
+void reset_launch_caches() { ++g_launchEpoch; }
 
 KernelConfig trace_kernel_config(int kernel, int layout)
 {

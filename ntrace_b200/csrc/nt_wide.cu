@@ -189,7 +189,7 @@ __global__ void __launch_bounds__(BLOCK)
 trace_wide4_kernel(int numRays, int anyHit, int fetchThreshold, unsigned oneBits,
                    const float4* __restrict__ rays, int4* __restrict__ results,
                    const float4* __restrict__ wnodes, const float4* __restrict__ woop,
-                   const int* __restrict__ triIndices, int* __restrict__ warpCounter)
+                   const int* __restrict__ triIndices, int* __restrict__ warpCounter, int* __restrict__ errorFlag)
 {
     __shared__ int s_stack[(SMEM_N > 0 ? SMEM_N : 1) * BLOCK];
     int l_stack[(kWideStackSize > SMEM_N) ? (kWideStackSize - SMEM_N) : 1];
@@ -198,7 +198,7 @@ trace_wide4_kernel(int numRays, int anyHit, int fetchThreshold, unsigned oneBits
     const unsigned lane = tid & 31;
     int* const sbase = s_stack + tid;
 
-#define NT_PUSH(v)  do { ++sp; if (sp < SMEM_N) sbase[sp * BLOCK] = (v); else l_stack[sp - SMEM_N] = (v); } while (0)
+#define NT_PUSH(v)  do { ++sp; if (sp < SMEM_N) sbase[sp * BLOCK] = (v); else if (sp < kWideStackSize) l_stack[sp - SMEM_N] = (v); else { --sp; *(volatile int*)errorFlag = 1; } } while (0)
 #define NT_POP(dst) do { (dst) = (sp < SMEM_N) ? sbase[sp * BLOCK] : l_stack[sp - SMEM_N]; --sp; } while (0)
 
     int   rayidx = -1;
@@ -385,7 +385,7 @@ __global__ void __launch_bounds__(BLOCK)
 trace_mr_kernel(int numRays, int anyHit, int fetchThreshold, int leafThreshold, unsigned oneBits,
                 const float4* __restrict__ rays, int4* __restrict__ results,
                 const float4* __restrict__ nodes, const float4* __restrict__ woop,
-                const int* __restrict__ triIndices, int* __restrict__ warpCounter)
+                const int* __restrict__ triIndices, int* __restrict__ warpCounter, int* __restrict__ errorFlag)
 {
     extern __shared__ float4 s_dyn[];
     const int tid = threadIdx.x;
@@ -399,7 +399,7 @@ trace_mr_kernel(int numRays, int anyHit, int fetchThreshold, int leafThreshold, 
     int sp0 = 0, sp1 = 0;
     bool more = true;                                                           // warp-uniform: the global counter still has rays
 
-#define MR_PUSH(v)  do { if (sp < SMEM_N) Sk[sp * BLOCK] = (v); else l_stack[k][sp - SMEM_N] = (v); ++sp; } while (0)
+#define MR_PUSH(v)  do { if (sp < SMEM_N) Sk[sp * BLOCK] = (v); else if (sp < SMEM_N + kMrLocal) l_stack[k][sp - SMEM_N] = (v); else { --sp; *(volatile int*)errorFlag = 1; } ++sp; } while (0)
 #define MR_POP(dst) do { if (sp == 0) (dst) = kEntrypointSentinel; else { --sp; (dst) = (sp < SMEM_N) ? Sk[sp * BLOCK] : l_stack[k][sp - SMEM_N]; } } while (0)
     // ray in slot k has finished: one int4 result store (id remapped through triIndex; a miss keeps t = tmax)
 #define MR_FINISH()                                                                                                          \
@@ -623,8 +623,9 @@ cudaError_t launch_mr_variant(const TraceLaunch& a, int* launches)
 {
     auto kern = trace_mr_kernel<kWideBlock, SMEM_N, FAST, FMT>;
     constexpr int smemBytes = kWideBlock * (8 * 16 + 2 * SMEM_N * 4);
-    static int blocksPerSM = 0;
-    if (!blocksPerSM) {
+    static int blocksPerSM = 0, epoch = -1;
+    if (epoch != launch_epoch()) {
+        epoch = launch_epoch();
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smemBytes);
         if (e != cudaSuccess) return e;
         int want = mr_tuning().ctasPerSM;
@@ -642,7 +643,7 @@ cudaError_t launch_mr_variant(const TraceLaunch& a, int* launches)
     if (grid > a.numSMs * blocksPerSM) grid = a.numSMs * blocksPerSM;
     const MrTuning t = mr_tuning();
     kern<<<grid, kWideBlock, smemBytes, a.stream>>>(a.numRays, a.anyHit, t.fetchThreshold, t.leafThreshold, 0x3F800000u, a.rays, a.results,
-                                                     FMT == kFmtWide4 ? a.wideNodes : a.nodes, a.woop, a.triIndices, a.warpCounter);
+                                                     FMT == kFmtWide4 ? a.wideNodes : a.nodes, a.woop, a.triIndices, a.warpCounter, a.errorFlag);
     if (launches) *launches = 1;
     return cudaGetLastError();
 }
@@ -674,8 +675,9 @@ template <int SMEM_N, bool FAST, bool WIDE_RAYS>
 cudaError_t launch_wide_variant(const TraceLaunch& a, int* launches)
 {
     auto kern = trace_wide4_kernel<kWideBlock, SMEM_N, FAST, WIDE_RAYS>;
-    static int blocksPerSM = 0;
-    if (!blocksPerSM) {
+    static int blocksPerSM = 0, epoch = -1;
+    if (epoch != launch_epoch()) {
+        epoch = launch_epoch();
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, wide_tuning().carveout);
         if (e != cudaSuccess) return e;
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSM, kern, kWideBlock, 0);
@@ -684,7 +686,7 @@ cudaError_t launch_wide_variant(const TraceLaunch& a, int* launches)
     }
     int grid = (a.numRays + kWideBlock - 1) / kWideBlock;
     if (grid > a.numSMs * blocksPerSM) grid = a.numSMs * blocksPerSM;
-    kern<<<grid, kWideBlock, 0, a.stream>>>(a.numRays, a.anyHit, wide_tuning().fetchThreshold, 0x3F800000u, a.rays, a.results, a.wideNodes, a.woop, a.triIndices, a.warpCounter);
+    kern<<<grid, kWideBlock, 0, a.stream>>>(a.numRays, a.anyHit, wide_tuning().fetchThreshold, 0x3F800000u, a.rays, a.results, a.wideNodes, a.woop, a.triIndices, a.warpCounter, a.errorFlag);
     if (launches) *launches = 1;
     return cudaGetLastError();
 }

@@ -172,6 +172,7 @@ class CudaBVH:
         self.woop = None if woop is None else np.ascontiguousarray(woop).view(np.int32).reshape(-1)
         self.tri_index = None if tri_index is None else np.ascontiguousarray(tri_index, dtype=np.int32).reshape(-1)
         self.resident = False        # True when the buffers live only in the library (GPU build)
+        self.generation = 0          # nt_bvh_generation() after the build / upload that made this handle's BVH the resident one
         self.gpu_seconds = 0.0
 
     def getLayout(self) -> int:
@@ -191,6 +192,8 @@ class CudaBVH:
 
     def _materialise(self):
         if self.nodes is None and self.resident:
+            if self.generation and capi.bvh_generation() != self.generation:
+                raise NtError("CudaBVH: this handle's BVH is no longer the resident one (a later build / upload replaced it before it was downloaded)")
             self.nodes, self.woop, self.tri_index, self.layout = capi.bvh_download()
 
     # bvhcache format: S32 layout, then 3 x (S64 size, bytes)  (CudaBVH.cpp:105-125, Buffer.cpp:349-381)
@@ -230,6 +233,8 @@ class HLBVHBuilder(CudaBVH):
         self.gpu_seconds = capi.bvh_build(capi.BUILDER_LBVH if lbvh else capi.BUILDER_HLBVH, scene.vtxPos, scene.triVtxIndex,
                                           scene.bboxMin, scene.bboxMax, params.hlbvhBits, params.leafSize, params.epsilon)
         self.resident = True
+        self.generation = capi.bvh_generation()
+        self.layout = capi.bvh_sizes()[1]                 # Compact, or Compact2 after nt_bvh_set_build_layout(5)
         self.num_tris = scene.getNumTriangles()
 
     def getGPUTime(self) -> float:
@@ -259,9 +264,20 @@ class CudaBVHTracer:
         return dict(self._config)
 
     def setBVH(self, bvh: CudaBVH):
+        """The library holds ONE resident BVH.  A handle is uploaded unless it already is that BVH (same generation); a device-built
+        handle whose BVH was replaced since is re-uploaded from its host copy if it has one, else refused."""
         self._bvh = bvh
-        if bvh is not None and not bvh.resident:
-            capi.bvh_upload(bvh.layout, bvh.nodes, bvh.woop, bvh.tri_index)
+        if bvh is None:
+            return
+        if bvh.generation and capi.bvh_generation() == bvh.generation:
+            return
+        if bvh.nodes is None:
+            if bvh.resident and not bvh.generation:          # adopt-the-resident handle (replicas after a broadcast, bench.py)
+                bvh.generation = capi.bvh_generation()
+                return
+            raise NtError("CudaBVHTracer: this BVH was built on the device and has been replaced by a later build / upload; rebuild it or keep a host copy")
+        capi.bvh_upload(bvh.layout, bvh.nodes, bvh.woop, bvh.tri_index)
+        bvh.generation = capi.bvh_generation()
 
     def traceBatch(self, rays: RayBuffer) -> float:
         """Returns the kernel time in seconds (CUDA events around the launch only)."""
@@ -272,6 +288,8 @@ class CudaBVHTracer:
             raise NtError("CudaBVHTracer: No BVH!")
         if self._bvh.getLayout() != self.getDesiredBVHLayout():
             raise NtError("CudaBVHTracer: Incorrect BVH layout!")
+        if self._bvh.generation and capi.bvh_generation() != self._bvh.generation:
+            self.setBVH(self._bvh)                           # another handle became resident in between: upload again (or refuse)
         _sync()
         return capi.trace_batch(rays.getRayBuffer(), rays.getResultBuffer(), n, rays.getNeedClosestHit())
 

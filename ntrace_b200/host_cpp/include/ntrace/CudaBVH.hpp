@@ -23,8 +23,8 @@ public:
 class CudaBVH : public CudaAS
 {
 public:
-    explicit CudaBVH(BVHLayout layout = BVHLayout_Compact) : m_layout(layout), m_resident(false) {}
-    explicit CudaBVH(std::istream& in) : m_layout(BVHLayout_Max), m_resident(false)                 // CudaBVH.cpp:105-112
+    explicit CudaBVH(BVHLayout layout = BVHLayout_Compact) : m_layout(layout), m_resident(false), m_generation(0) {}
+    explicit CudaBVH(std::istream& in) : m_layout(BVHLayout_Max), m_resident(false), m_generation(0)              // CudaBVH.cpp:105-112
     {
         S32 layout = 0;
         in.read((char*)&layout, 4);
@@ -59,13 +59,22 @@ public:
         }
     }
 
-    // true while the buffers live only inside the library (after a GPU build): setBVH then has nothing to upload
+    // true while the buffers live only inside the library (after a GPU build)
     bool isResident() const { return m_resident; }
+    // The library holds ONE resident BVH; nt_bvh_generation() changes whenever it is replaced.  A handle remembers the generation
+    // that made ITS buffers the resident ones: setBVH / traceBatch compare it and upload again (or refuse) instead of silently
+    // tracing whatever a later build left in the library.
+    uint64_t getGeneration() const { return m_generation; }
+    void setGeneration(uint64_t g) { m_generation = g; }
+    bool hasHostCopy() { return m_nodes.getSize() > 0; }
+    static uint64_t currentGeneration() { uint64_t g = 0; ntCheck(nt_bvh_generation(&g)); return g; }
 
 protected:
     void materialise()
     {
         if (!m_resident || m_nodes.getSize()) return;
+        if (m_generation && currentGeneration() != m_generation)
+            fail("CudaBVH: this handle's BVH is no longer the resident one (a later build / upload replaced it before it was downloaded)");
         size_t sz[3]; int layout = 0;
         ntCheck(nt_bvh_sizes(sz, &layout));
         m_nodes.resizeDiscard((S64)sz[0]); m_triWoop.resizeDiscard((S64)sz[1]); m_triIndex.resizeDiscard((S64)sz[2]);
@@ -74,6 +83,7 @@ protected:
 
     BVHLayout m_layout;
     bool m_resident;
+    uint64_t m_generation;
     Buffer m_nodes, m_triWoop, m_triIndex;
 };
 
@@ -96,6 +106,10 @@ public:
                              (const int32_t*)scene->getTriVtxIndexBuffer().getCudaPtr(), scene->getNumTriangles(), lo.getPtr(), hi.getPtr(),
                              params.hlbvhBits, params.leafSize, params.epsilon, &m_gpuTime));
         m_resident = true;
+        m_generation = currentGeneration();
+        size_t sz[3]; int layout = 0;
+        ntCheck(nt_bvh_sizes(sz, &layout));                       // Compact, or Compact2 after nt_bvh_set_build_layout(5)
+        m_layout = (BVHLayout)layout;
     }
     F32 getGPUTime() const { return m_gpuTime; }
 

@@ -40,11 +40,15 @@ public:
     virtual void setBVH(CudaAS* as)
     {
         m_bvh = as;
+        if (!as) return;
         CudaBVH* bvh = dynamic_cast<CudaBVH*>(as);
-        if (!as || (bvh && bvh->isResident())) return;           // GPU-built: already inside the library
+        if (bvh && bvh->getGeneration() && bvh->getGeneration() == CudaBVH::currentGeneration()) return;   // already the resident BVH
+        if (bvh && bvh->isResident() && !bvh->hasHostCopy())
+            fail("CudaBVHTracer: this BVH was built on the device and has been replaced by a later build / upload; rebuild it or keep a host copy");
         Buffer& n = as->getNodeBuffer(); Buffer& w = as->getTriWoopBuffer(); Buffer& i = as->getTriIndexBuffer();
         ntCheck(nt_bvh_upload((int)as->getLayout(), n.getPtr(), (size_t)n.getSize(), w.getPtr(), (size_t)w.getSize(),
                               (const int32_t*)i.getPtr(), (size_t)i.getSize()));
+        if (bvh) bvh->setGeneration(CudaBVH::currentGeneration());
     }
     virtual void setScene(Scene* scene) { m_scene = scene; }
 
@@ -53,6 +57,8 @@ public:
         if (!rays.getSize()) return 0.0f;                          // CudaBVHTracer.cpp:92-94
         if (!m_bvh) fail("CudaBVHTracer: No BVH!");
         if (m_bvh->getLayout() != getDesiredBVHLayout()) fail("CudaBVHTracer: Incorrect BVH layout!");
+        if (CudaBVH* bvh = dynamic_cast<CudaBVH*>(m_bvh))
+            if (bvh->getGeneration() && bvh->getGeneration() != CudaBVH::currentGeneration()) setBVH(m_bvh);   // another handle became resident in between
         float sec = 0.0f;
         ntCheck(nt_trace_batch((const float*)rays.getRayBuffer().getCudaPtr(), (int32_t*)rays.getResultBuffer().getMutableCudaPtrDiscard(),
                                rays.getSize(), rays.getNeedClosestHit() ? 1 : 0, &sec));
