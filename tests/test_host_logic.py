@@ -194,3 +194,23 @@ def test_shadow_ray_generator_properties(orc):
     # a different seed rotates the pattern
     out2, _, _ = orc.raygen_shadow(rays, res, 0, n, spp, light, radius, 78)
     assert not np.array_equal(out2.reshape(n, spp, 8)[~miss][:, :, 4:7], out[~miss][:, :, 4:7])
+
+
+def test_bench_rank_ranges_cover_every_ray_exactly_once():
+    """bench.py's multi-GPU split of a frame (both partitions): every slot of every ray type is traced by exactly one rank."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    sizes = [("primary", 1000), ("AO", 640), ("AO", 640), ("AO", 640), ("AO", 77), ("diffuse", 640), ("diffuse", 13)]
+    batches = [(t, np.arange(n * 8, dtype=np.float32).reshape(n, 8), n, t != "AO") for t, n in sizes]
+    for partition in ("deal", "slices"):
+        for world in (1, 2, 3, 4, 8):
+            seen = {t: np.zeros(sum(n for tt, n in sizes if tt == t), dtype=np.int32) for t in ("primary", "AO", "diffuse")}
+            for rank in range(world):
+                for name, rays, n, closest, off in bench.rank_ranges(batches, rank, world, partition):
+                    assert len(rays) == n and n > 0 and closest == (name != "AO")
+                    seen[name][off:off + n] += 1
+            for t in seen:
+                assert (seen[t] == 1).all(), (partition, world, t)
