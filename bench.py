@@ -174,16 +174,15 @@ DEFAULT_KERNEL = "b200_persistent_speculative_while_while"
 
 
 def lib_sha16():
-    import hashlib
-    h = hashlib.sha256()
-    with open(os.path.join(ROOT, "ntrace_b200", "libntrace_b200.so"), "rb") as f:
-        h.update(f.read())
-    return h.hexdigest()[:16]
+    """Identity of the CUDA code being timed: sha256 over the sources libntrace_b200.so is built from (csrc/*, the C header, the nvcc flags).
+    (The .so itself is not bit-reproducible across nvcc runs, so its own hash could not tie a capture to a rebuild of the same code.)"""
+    from ntrace_b200 import build as nb
+    return nb.source_sha16()
 
 
 def load_binding(kernel):
     """What binds the kernel, measured by scripts/ncu_binding.py (ncu on the GPU box) and committed under profiles/.  The capture
-    carries the sha256 of the libntrace_b200.so it profiled; `matches_timed_library` says whether that is the library timed here."""
+    carries the sha256 of the library sources it was built from; `matches_timed_library` says whether that is the library timed here."""
     path = os.path.join(ROOT, "profiles", f"r2_binding_{kernel}.json")
     if not os.path.exists(path):
         return {"available": False, "note": f"no capture at profiles/r2_binding_{kernel}.json (run scripts/ncu_binding.py under gpurun)"}

@@ -74,9 +74,12 @@ int nt_event_elapsed(int slotA, int slotB, float* outSeconds);
  * 2 = deferred and overlapped: as 1, and consecutive launches alternate between two kernel streams, so that the CTAs of
  * the next batch move in while the persistent CTAs of the current one run out of rays (the batches of a frame are
  * independent once the primary results exist; the reference traces them one after the other, Renderer.cpp:405-579).
- * A launch is ordered after everything queued before it; every other call of this API waits for the launches in flight
- * before it enqueues or reads anything, so only the result buffers of two CONSECUTIVE nt_trace_batch calls must differ.
- * Mode 2 also queues calls whose buffers are page-locked host memory (traversed in place over PCIe; results are in host
+ * A launch is ordered after everything queued before it, and after any launch still in flight that shares a ray or result buffer with
+ * it (the library remembers the buffers of the last 8 launches), so tracing the same batch twice is safe, merely not overlapped.
+ * nt_raygen_ao on device buffers is queued too in this mode (it returns at once) and waits only for the launches in flight that use
+ * ITS buffers: a host loop that alternates two secondary RayBuffers (generate B while A is traced) keeps the GPU full without any
+ * call of its own to order things.  Every other call of this API waits for all launches in flight before it enqueues or reads
+ * anything.  Mode 2 also queues calls whose buffers are page-locked host memory (traversed in place over PCIe; results are in host
  * memory once nt_synchronize() returns); pageable host buffers stay synchronous in every mode. */
 int nt_set_deferred(int mode);
 int nt_synchronize(void);

@@ -66,10 +66,15 @@ def run_benchmark(env: Environment, out=sys.stdout, device: int = 0):
         if r.lower() not in RAY_TYPE_NAMES:
             raise host.NtError(f"Unsupported ray type {r}")
     warm, meas = env.GetInt("Benchmark.warmupRepeats"), env.GetInt("Benchmark.measureRepeats")
+    # NEW knob (default off = the reference's loop): whole frames are repeated instead of single batches, the batches of a frame are
+    # queued back to back on alternating buffers (Renderer.setPipelined) and the device time of the whole batch loop is what is summed
+    pipelined = env.Has("Benchmark.pipelined") and env.GetBool("Benchmark.pipelined")
 
     print(f'Running benchmark for "{env.GetString("Benchmark.scene")}".\n', file=out)
     scene = host.Scene(verts, tris)
-    renderer = host.Renderer(host.BuildSettings(builder=builder))
+    leaf = env.GetInt("HLBVH.leafSize")
+    host.capi.bvh_set_collapse(1 if env.GetBool("HLBVH.collapse") else 0, leaf)
+    renderer = host.Renderer(host.BuildSettings(builder=builder, hlbvh=host.HLBVHParams(True, env.GetInt("HLBVH.bits"), leaf, 0.001)))
     renderer.setScene(scene)
     stats = open(env.GetString("App.stats"), "a")
     results = []
@@ -80,6 +85,19 @@ def run_benchmark(env: Environment, out=sys.stdout, device: int = 0):
                 print(f"{kernel}, {rt}, camera {ci}...", file=out)
                 renderer.setParams(host.RendererParams(kernelName=kernel, rayType=RAY_TYPE_NAMES[rt.lower()], numSamples=env.GetInt("Renderer.samples"),
                                                        aoRadius=env.GetFloat("Raygen.aoRadius"), sortSecondary=env.GetBool("Renderer.sortRays")))
+                renderer.setPipelined(pipelined)
+                if pipelined:
+                    for rep in range(warm + meas):
+                        renderer.beginFrame(cam, w, h)
+                        if rep == 0:
+                            total_rays += renderer.getTotalNumRays() * meas
+                        renderer.beginTiming()
+                        while renderer.nextBatch():
+                            renderer.traceBatch()
+                        sec = renderer.endTiming()
+                        if rep >= warm:
+                            total_time += sec
+                    continue
                 renderer.beginFrame(cam, w, h)
                 total_rays += renderer.getTotalNumRays() * meas
                 while renderer.nextBatch():

@@ -27,6 +27,20 @@ def is_stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 
+def source_sha16() -> str:
+    """sha256 (first 16 hex digits) over everything libntrace_b200.so is compiled from: csrc/*, the C header and the nvcc flags.  Ties an
+    ncu capture under profiles/ to the code bench.py times (the .so itself is not bit-reproducible across nvcc runs)."""
+    import hashlib
+    h = hashlib.sha256()
+    for f in sorted(os.listdir(CSRC)):
+        with open(os.path.join(CSRC, f), "rb") as fh:
+            h.update(f.encode() + b"\0" + fh.read())
+    with open(os.path.join(_HERE, "..", "include", "ntrace_b200.h"), "rb") as fh:
+        h.update(fh.read())
+    h.update(" ".join(NVCC_FLAGS + SOURCES).encode())
+    return h.hexdigest()[:16]
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not is_stale():
         return LIB

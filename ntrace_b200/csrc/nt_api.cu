@@ -10,6 +10,7 @@
 
 #include <cstdlib>
 #include <cstring>
+#include <initializer_list>
 #include <mutex>
 #include <vector>
 
@@ -60,6 +61,17 @@ struct Context {
     int overlapNext = 0;
     cudaStream_t kStream[2] = {};
     cudaEvent_t kDone[2] = {}, kFork = nullptr;
+    // what the overlapped launches still in flight read and write, so that a later call waits only for the launches whose buffers it
+    // touches (a ray generator filling buffer B does not wait for the trace of buffer A)
+    struct InFlight { const char* rLo = nullptr; const char* rHi = nullptr; const char* wLo = nullptr; const char* wHi = nullptr; cudaEvent_t ev = nullptr; bool live = false; };
+    static constexpr int kRing = 8;
+    InFlight ring[kRing];
+    int ringNext = 0;
+    // ray buffers written by a queued nt_raygen_ao (overlapped mode): the trace of such a buffer waits for ITS generator only, not for
+    // everything the main stream has queued since (the generator of the batch after it, which sits behind the previous trace's tail)
+    struct Producer { const char* lo = nullptr; const char* hi = nullptr; cudaEvent_t ev = nullptr; bool live = false; };
+    Producer prod[kRing];
+    int prodNext = 0;
     int64_t launches = 0;
     // asynchronous submission (nt_trace_batch_async / nt_trace_wait): per-slot staging + events
     static constexpr int kAsyncSlots = 4;
@@ -215,8 +227,41 @@ int join_kernel_streams()
 {
     if (!g.overlapPending) return 0;
     for (int k = 0; k < 2; k++) NT_CUDA(cudaStreamWaitEvent(g.stream, g.kDone[k], 0));
+    for (int i = 0; i < Context::kRing; i++) g.ring[i].live = false;
     g.overlapPending = false;
     return 0;
+}
+
+// forget the queued generators (their events stay valid): called by every entry point that synchronises the main stream
+void clear_producers() { for (int i = 0; i < Context::kRing; i++) g.prod[i].live = false; }
+
+struct Range { const void* p; size_t bytes; };
+inline bool overlaps(const char* lo, const char* hi, const Range& r)
+{
+    return r.p && r.bytes && lo && (const char*)r.p < hi && lo < (const char*)r.p + r.bytes;
+}
+// order `stream` behind exactly those overlapped launches in flight that write what the caller reads or touch what it writes
+int join_for(cudaStream_t stream, const Range* reads, int nr, const Range* writes, int nw)
+{
+    if (!g.overlapPending) return 0;
+    for (int i = 0; i < Context::kRing; i++) {
+        Context::InFlight& e = g.ring[i];
+        if (!e.live) continue;
+        bool hit = false;
+        for (int k = 0; k < nw && !hit; k++) hit = overlaps(e.rLo, e.rHi, writes[k]) || overlaps(e.wLo, e.wHi, writes[k]);
+        for (int k = 0; k < nr && !hit; k++) hit = overlaps(e.wLo, e.wHi, reads[k]);
+        if (!hit) continue;
+        NT_CUDA(cudaStreamWaitEvent(stream, e.ev, 0));
+        if (stream == g.stream) e.live = false;       // everything queued on the main stream from here on is ordered behind it
+    }
+    return 0;
+}
+// may this call skip the library-wide join?  Only overlapped mode with nothing but device memory involved
+bool fine_grained(std::initializer_list<const void*> ptrs)
+{
+    if (!(g.inited && g.deferred && g.overlap)) return false;
+    for (const void* p : ptrs) if (p && !is_device_ptr(p)) return false;
+    return true;
 }
 
 // after a synchronisation point: did any launch since the last check overflow a ray's traversal stack?
@@ -317,6 +362,8 @@ int nt_init(int device_ordinal)
         NT_CUDA(cudaEventCreateWithFlags(&g.kDone[k], cudaEventDisableTiming));
     }
     NT_CUDA(cudaEventCreateWithFlags(&g.kFork, cudaEventDisableTiming));
+    for (int i = 0; i < Context::kRing; i++) NT_CUDA(cudaEventCreateWithFlags(&g.ring[i].ev, cudaEventDisableTiming));
+    for (int i = 0; i < Context::kRing; i++) NT_CUDA(cudaEventCreateWithFlags(&g.prod[i].ev, cudaEventDisableTiming));
     NT_CUDA(cudaStreamCreateWithFlags(&g.sIn, cudaStreamNonBlocking));
     NT_CUDA(cudaStreamCreateWithFlags(&g.sOut, cudaStreamNonBlocking));
     for (int i = 0; i < Context::kMaxChunks; i++) {
@@ -351,6 +398,7 @@ void nt_shutdown(void)
     cudaStreamSynchronize(g.sOut);
     for (int k = 0; k < 2; k++) { cudaStreamSynchronize(g.kStream[k]); cudaStreamDestroy(g.kStream[k]); cudaEventDestroy(g.kDone[k]); }
     cudaEventDestroy(g.kFork);
+    for (int i = 0; i < Context::kRing; i++) { cudaEventDestroy(g.ring[i].ev); cudaEventDestroy(g.prod[i].ev); }
     DevBuf* bufs[] = {&g.nodes, &g.woop, &g.triIndex, &g.sortedKeys, &g.sortedIdx, &g.stRays, &g.stResults, &g.stA, &g.stB,
                       &g.stC, &g.stD, &g.stE, &g.counters, &g.pixelTable, &g.sceneVerts, &g.sceneTris,
                       &g.srcNodes, &g.srcWoop, &g.srcIdx, &g.layoutScratch, &g.wideNodes};
@@ -460,6 +508,7 @@ int nt_set_deferred(int mode)
     if (!mode && g.deferred) NT_CUDA(cudaStreamSynchronize(g.stream));         // (require_init joined the kernel streams)
     g.deferred = mode != 0;
     g.overlap = mode == 2;
+    clear_producers();
     return 0;
 }
 
@@ -468,6 +517,7 @@ int nt_synchronize(void)
     std::lock_guard<std::mutex> lock(g_mutex);
     if (require_init()) return 1;
     NT_CUDA(cudaStreamSynchronize(g.stream));
+    clear_producers();
     return check_trace_error();
 }
 
@@ -692,7 +742,7 @@ int nt_bvh_wide4_convert_host(int layout, const void* nodes, size_t nodeBytes, s
 int nt_bvh_generation(uint64_t* outGeneration)
 {
     std::lock_guard<std::mutex> lock(g_mutex);
-    if (require_init()) return 1;
+    if (require_init(false)) return 1;                 // touches no device memory: launches in flight are not joined
     if (!outGeneration) { set_error("ntrace_b200: null output"); return 1; }
     *outGeneration = g.haveBVH ? g.generation : 0;
     return 0;
@@ -820,13 +870,35 @@ int nt_trace_batch(const float* rays, int32_t* results, int numRays, int needClo
     a.numRays = numRays; a.rays = (const float4*)raysDev; a.results = (int4*)resDev;
     if (overlapped) {
         const int k = g.overlapNext; g.overlapNext ^= 1;
-        NT_CUDA(cudaEventRecord(g.kFork, g.stream));                   // what the main stream has queued so far (ray generation) comes first
-        NT_CUDA(cudaStreamWaitEvent(g.kStream[k], g.kFork, 0));
         a.stream = g.kStream[k];
+        // the rays' generator comes first.  When it was a queued nt_raygen_ao the launch waits for that kernel alone; otherwise for
+        // everything the main stream has queued so far
+        bool haveProducer = false;
+        for (int i = 0; i < Context::kRing; i++) {
+            Context::Producer& pr = g.prod[i];
+            if (pr.live && (const char*)raysDev < pr.hi && pr.lo < (const char*)raysDev + (size_t)numRays * 32) {
+                NT_CUDA(cudaStreamWaitEvent(a.stream, pr.ev, 0));
+                haveProducer = true;
+            }
+        }
+        if (!haveProducer) {
+            NT_CUDA(cudaEventRecord(g.kFork, g.stream));
+            NT_CUDA(cudaStreamWaitEvent(a.stream, g.kFork, 0));
+        }
+        // launches in flight on the OTHER kernel stream that share a buffer with this one (the same batch traced twice, say) come first too
+        const Range rd{raysDev, (size_t)numRays * 32}, wr{resDev, (size_t)numRays * 16};
+        if (join_for(a.stream, &rd, 1, &wr, 1)) return 1;
         a.warpCounter = g.counters.as<int>() + 4 + k;                  // one fetch counter per launch in flight
         NT_CUDA(cudaMemsetAsync(a.warpCounter, 0, sizeof(int), a.stream));
         NT_CUDA(launch_trace(a, &launches));
         NT_CUDA(cudaEventRecord(g.kDone[k], a.stream));
+        Context::InFlight& slot = g.ring[g.ringNext];
+        g.ringNext = (g.ringNext + 1) % Context::kRing;
+        if (slot.live) NT_CUDA(cudaStreamWaitEvent(g.stream, slot.ev, 0));     // the ring remembers 8 launches: the one that falls out is joined
+        slot.rLo = (const char*)raysDev; slot.rHi = slot.rLo + (size_t)numRays * 32;
+        slot.wLo = (const char*)resDev; slot.wHi = slot.wLo + (size_t)numRays * 16;
+        NT_CUDA(cudaEventRecord(slot.ev, a.stream));
+        slot.live = true;
         g.overlapPending = true;
         g.launches += launches;
         return 0;
@@ -956,11 +1028,19 @@ int nt_raygen_ao(float* outRays, int32_t* outIDToSlot, int32_t* outSlotToID, con
                  int numSamples, float maxDist, uint32_t randomSeed)
 {
     std::lock_guard<std::mutex> lock(g_mutex);
-    if (require_init()) return 1;
+    // overlapped mode, device buffers only: wait for just the launches in flight that use these buffers, and do not block the host
+    const bool fine = fine_grained({outRays, outIDToSlot, outSlotToID, inRays, inResults, triNormals});
+    if (require_init(!fine)) return 1;
     if (numInputRays == 0) return 0;
     if (numInputRays < 0 || numSamples <= 0 || firstInputSlot < 0 || !outRays || !inRays || !inResults || !triNormals) {
         set_error("ntrace_b200: invalid AO ray request");
         return 1;
+    }
+    if (fine) {
+        const size_t nO = (size_t)numInputRays * numSamples;
+        const Range rd[2] = {{inRays + (size_t)firstInputSlot * 8, (size_t)numInputRays * 32}, {inResults + (size_t)firstInputSlot * 4, (size_t)numInputRays * 16}};
+        const Range wr[3] = {{outRays, nO * 32}, {outIDToSlot, nO * 4}, {outSlotToID, nO * 4}};
+        if (join_for(g.stream, rd, 2, wr, 3)) return 1;
     }
     if (is_device_ptr(inRays) != is_device_ptr(inResults)) { set_error("ntrace_b200: inRays and inResults must live on the same side"); return 1; }
     const size_t nOut = (size_t)numInputRays * numSamples;
@@ -985,6 +1065,14 @@ int nt_raygen_ao(float* outRays, int32_t* outIDToSlot, int32_t* outSlotToID, con
     a.firstInputSlot = first; a.numInputRays = numInputRays; a.numSamples = numSamples; a.maxDist = maxDist; a.seed = randomSeed;
     NT_CUDA(launch_raygen_ao(a, g.stream));
     g.launches += 1;
+    if (fine) {                               // queued on the main stream; the trace of these rays waits for this kernel (see nt_trace_batch)
+        Context::Producer& pr = g.prod[g.prodNext];
+        g.prodNext = (g.prodNext + 1) % Context::kRing;
+        pr.lo = (const char*)dOut; pr.hi = pr.lo + nOut * 32;
+        NT_CUDA(cudaEventRecord(pr.ev, g.stream));
+        pr.live = true;
+        return 0;
+    }
     if (copy_back(hOut, dOut, nOut * 32) || copy_back(hA, dA, nOut * 4) || copy_back(hB, dB, nOut * 4)) return 1;
     NT_CUDA(cudaStreamSynchronize(g.stream));
     return 0;

@@ -25,6 +25,7 @@ OPTIONS = {
     "Benchmark.kernel": ("string", "benchmark_kernel=", None),
     "Benchmark.warmupRepeats": ("int", "benchmark_warmup=", "1"),
     "Benchmark.measureRepeats": ("int", "benchmark_measure=", "5"),
+    "Benchmark.pipelined": ("bool", "benchmark_pipelined=", "false"),      # new: queue a frame's batches back to back (Renderer.setPipelined)
     "Renderer.dataStructure": ("string", "renderer_ds=", None),
     "Renderer.builder": ("string", "renderer_builder=", None),
     "Renderer.rayType": ("string", "renderer_raytype=", None),
@@ -32,6 +33,10 @@ OPTIONS = {
     "Renderer.sortRays": ("bool", "renderer_sortrays=", "true"),
     "Renderer.cacheDataStructure": ("bool", "renderer_cache_ds=", "true"),
     "Renderer.numGpus": ("int", "renderer_numgpus=", "1"),
+    # new: HLBVHParams of Renderer::getCudaBVH (reference hard-codes {true, 4, 8, 0.001}, Renderer.cpp:201-209) and the SAH-guided collapse
+    "HLBVH.bits": ("int", "hlbvh_bits=", "4"),
+    "HLBVH.leafSize": ("int", "hlbvh_leafsize=", "8"),
+    "HLBVH.collapse": ("bool", "hlbvh_collapse=", "false"),
     "Raygen.random": ("bool", "raygen_random=", "false"),
     "Raygen.aoRadius": ("float", "raygen_aoradius=", "5.0"),
     "SBVH.alpha": ("float", "sbvh_alpha=", "1.0e-5"),

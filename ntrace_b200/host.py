@@ -58,9 +58,13 @@ def device():
     return torch().device("cuda", _device_index)
 
 
+_pipelined = False       # inside Renderer's pipelined batch loop no torch work is queued, and a device-wide sync would defeat the overlap
+
+
 def _sync():
     # the library runs on its own stream and is synchronous; torch producers must be drained before a call
-    torch().cuda.synchronize()
+    if not _pipelined:
+        torch().cuda.synchronize()
 
 
 # --------------------------------------------------------------------------------------------------
@@ -93,6 +97,12 @@ class RayBuffer:
                     new[: self._size].copy_(o[: self._size])
             self._cap = cap
         self._size = n
+
+    def reserve(self, n: int):
+        """Grow the storage to n slots without changing the size (so later resizes queue no allocation / fill)."""
+        size = self._size
+        self.resize(max(n, size))
+        self._size = size
 
     def setNeedClosestHit(self, c: bool):
         self._need_closest = bool(c)
@@ -370,6 +380,7 @@ class BuildSettings:
 
 class Renderer:
     """Frame/batch loop of the reference Renderer restricted to the tracing path."""
+    PREFETCH = 2
 
     def __init__(self, build: BuildSettings = BuildSettings()):
         self.m_raygen = RayGen(1 << 20)                               # Renderer.cpp:45
@@ -379,7 +390,17 @@ class Renderer:
         self.m_scene = None
         self.m_bvh = None
         self.m_primaryRays = RayBuffer()
-        self.m_secondaryRays = RayBuffer()
+        # Three secondary buffers.  The reference has one (Renderer.hpp: m_secondaryRays) and traces batch i before it generates
+        # batch i+1; in pipelined mode batches are generated up to PREFETCH ahead into the other buffers while batch i is traced, and
+        # consecutive launches overlap at their tails (nt_set_deferred(2); the library orders each call behind the launches / the
+        # generator that use ITS buffers only).
+        self.m_secondary = [RayBuffer(), RayBuffer(), RayBuffer()]
+        self.m_secondaryRays = self.m_secondary[0]
+        self.m_genIdx = 0
+        self.m_queue = []            # pipelined mode: batches generated ahead of the one handed out (at most PREFETCH)
+        self.m_genDone = False
+        self.m_pipelined = False
+        self.m_timing = False
         self.m_cameraFar = 0.0
         self.m_newBatch = True
         self.m_batchRays = None
@@ -392,6 +413,35 @@ class Renderer:
     def setParams(self, params: RendererParams):
         self.m_params = params
         self.m_cudaTracer.setKernel(params.kernelName)
+
+    def setPipelined(self, on: bool):
+        """NEW (no reference counterpart).  False: the reference's loop, every traceBatch() returns its kernel seconds.  True:
+        nextBatch() alternates the two secondary buffers and traceBatch() only queues (returns 0.0); bracket the batch loop with
+        beginTiming() / endTiming() to get the device seconds of everything queued in between.  Results are bit-identical."""
+        self.m_pipelined = bool(on)
+
+    def beginTiming(self):
+        global _pipelined
+        if self.m_pipelined:
+            for rb in self.m_secondary:                               # no allocation (torch fill kernels) inside the loop
+                rb.reserve(self.m_raygen.m_maxBatchSize)
+            torch().cuda.synchronize()
+            capi.set_deferred(2)
+            _pipelined = True
+        capi.event_record(6)
+        self.m_timing = True
+
+    def endTiming(self) -> float:
+        """Device seconds since beginTiming() (waits for everything queued)."""
+        global _pipelined
+        capi.event_record(7)
+        sec = capi.event_elapsed(6, 7)
+        if self.m_pipelined:
+            capi.synchronize()
+            capi.set_deferred(0)
+            _pipelined = False
+        self.m_timing = False
+        return sec
 
     def setCudaBVH(self, bvh: CudaBVH):
         """Use a prebuilt CudaBVH (e.g. a bvhcache file or a CPU-built SplitBVH flattened by the caller)."""
@@ -420,12 +470,36 @@ class Renderer:
         self.m_newBatch = True
         self.m_batchRays = None
         self.m_batchStart = 0
+        self.m_queue = []
+        self.m_genDone = False
+
+    def _nextBatchPipelined(self) -> bool:
+        """Secondary batches, pipelined: keep up to PREFETCH generated batches queued ahead of the one handed out."""
+        closest = self.m_params.rayType == RayType_Diffuse
+        dist = self.m_cameraFar if closest else self.m_params.aoRadius
+        while len(self.m_queue) < self.PREFETCH and not self.m_genDone:
+            rb = self.m_secondary[self.m_genIdx % len(self.m_secondary)]
+            ok, self.m_newBatch = self.m_raygen.ao(rb, self.m_primaryRays, self.m_scene, self.m_params.numSamples, dist, self.m_newBatch, FIXED_AO_SEED)
+            if not ok:
+                self.m_genDone = True
+                break
+            self.m_genIdx += 1
+            rb.setNeedClosestHit(closest)
+            if self.m_params.sortSecondary:
+                rb.mortonSort()
+            self.m_queue.append(rb)
+        if not self.m_queue:
+            return False
+        self.m_batchRays = self.m_secondaryRays = self.m_queue.pop(0)
+        return True
 
     def nextBatch(self) -> bool:
         if self.m_batchRays is not None:
             self.m_batchStart += self.m_batchRays.getSize()
         self.m_batchRays = None
         rt = self.m_params.rayType
+        if self.m_pipelined and rt in (RayType_AO, RayType_Diffuse):
+            return self._nextBatchPipelined()
         if rt == RayType_Primary:
             if not self.m_newBatch:
                 return False

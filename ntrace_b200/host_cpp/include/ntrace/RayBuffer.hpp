@@ -22,6 +22,7 @@ public:
             m_slotToID.resize((S64)n * sizeof(S32));
         }
     }
+    void reserve(S32 n) { const S32 s = m_size; if (n > s) { resize(n); m_size = s; } }       // grow the storage, keep the size
     void setRay(S32 slot, const Ray& ray) { setRay(slot, ray, slot); }
     void setRay(S32 slot, const Ray& ray, S32 id)            // RayBuffer.cpp:55-62
     {

@@ -58,6 +58,9 @@ public:
     }
 
 private:
+public:
+    S32 getMaxBatchSize() const { return m_maxBatchSize; }
+private:
     S32 m_maxBatchSize;
     S32 m_shadowStartIdx, m_aoStartIdx;
 };

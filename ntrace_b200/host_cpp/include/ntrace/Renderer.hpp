@@ -26,7 +26,7 @@ public:
     // check of this repo uses this constant on both sides instead
     enum { FixedSecondarySeed = 0x9E3779B9 };
 
-    Renderer() : m_raygen(1 << 20), m_scene(NULL), m_cameraFar(0.0f), m_newBatch(true), m_batchRays(NULL), m_batchStart(0)   // Renderer.cpp:45
+    Renderer() : m_raygen(1 << 20), m_scene(NULL), m_genIdx(0), m_queueHead(0), m_queueLen(0), m_genDone(false), m_pipelined(false), m_cameraFar(0.0f), m_newBatch(true), m_batchRays(NULL), m_batchStart(0)   // Renderer.cpp:45
     {
         m_cudaTracer.reset(new CudaBVHTracer());
         m_builder = "HLBVH";
@@ -40,6 +40,31 @@ public:
     const Params& getParams() const { return m_params; }
     void setHLBVHParams(const HLBVHParams& p) { m_hlbvh = p; m_accelStruct.reset(); }
     void setCudaBVH(CudaBVH* bvh) { m_accelStruct.reset(bvh); }           // takes ownership: a prebuilt / deserialised BVH
+
+    // NEW (no reference counterpart).  false: the reference's loop, every traceBatch() returns its kernel seconds.  true: nextBatch()
+    // cycles three secondary RayBuffers (the reference has one, Renderer.hpp m_secondaryRays, and traces batch i before it generates
+    // batch i+1) and generates up to Prefetch batches ahead of the one it hands out, traceBatch() only queues (returns 0) and
+    // beginTiming() / endTiming() bracket the batch loop: later batches are generated while batch i is traced and consecutive launches
+    // overlap at their tails (nt_set_deferred(2); the library orders every call behind the launches / the generator that use ITS
+    // buffers only).  Results are bit-identical to the synchronous loop.
+    enum { NumSecondary = 3, Prefetch = 2 };
+    void setPipelined(bool on) { m_pipelined = on; }
+    void beginTiming()
+    {
+        if (m_pipelined) {
+            for (int i = 0; i < NumSecondary; i++) m_secondary[i].reserve(m_raygen.getMaxBatchSize());      // no allocation inside the loop
+            ntCheck(nt_set_deferred(2));
+        }
+        ntCheck(nt_event_record(6));
+    }
+    F32 endTiming()                                                         // device seconds since beginTiming(); waits for everything queued
+    {
+        float sec = 0.0f;
+        ntCheck(nt_event_record(7));
+        ntCheck(nt_event_elapsed(6, 7, &sec));
+        if (m_pipelined) { ntCheck(nt_synchronize()); ntCheck(nt_set_deferred(0)); }
+        return sec;
+    }
     CudaBVHTracer& getCudaTracer() { return *m_cudaTracer; }
     RayBuffer& getPrimaryRays() { return m_primaryRays; }
 
@@ -77,27 +102,49 @@ public:
         m_newBatch = true;
         m_batchRays = NULL;
         m_batchStart = 0;
+        m_queueHead = m_queueLen = 0;
+        m_genDone = false;
     }
 
     bool nextBatch()                                                        // Renderer.cpp:504-566
     {
         if (m_batchRays) m_batchStart += m_batchRays->getSize();
         m_batchRays = NULL;
+        if (m_pipelined && m_params.rayType != RayType_Primary) {
+            const bool closest = (m_params.rayType == RayType_Diffuse);
+            while (m_queueLen < Prefetch && !m_genDone) {
+                RayBuffer& sec = m_secondary[m_genIdx % NumSecondary];
+                if (!m_raygen.ao(sec, m_primaryRays, *m_scene, m_params.numSamples, closest ? m_cameraFar : m_params.aoRadius, m_newBatch, FixedSecondarySeed)) { m_genDone = true; break; }
+                sec.setNeedClosestHit(closest);
+                if (m_params.sortSecondary) sec.mortonSort();
+                m_queue[(m_queueHead + m_queueLen++) % NumSecondary] = &sec;
+                m_genIdx++;
+            }
+            if (!m_queueLen) return false;
+            m_batchRays = m_queue[m_queueHead];
+            m_queueHead = (m_queueHead + 1) % NumSecondary;
+            m_queueLen--;
+            return true;
+        }
         switch (m_params.rayType) {
         case RayType_Primary:
             if (!m_newBatch) return false;
             m_newBatch = false;
             m_batchRays = &m_primaryRays;
             break;
-        case RayType_AO:
-            if (!m_raygen.ao(m_secondaryRays, m_primaryRays, *m_scene, m_params.numSamples, m_params.aoRadius, m_newBatch, FixedSecondarySeed)) return false;
-            m_batchRays = &m_secondaryRays;
+        case RayType_AO: {
+            RayBuffer& sec = m_secondary[0];
+            if (!m_raygen.ao(sec, m_primaryRays, *m_scene, m_params.numSamples, m_params.aoRadius, m_newBatch, FixedSecondarySeed)) return false;
+            m_batchRays = &sec;
             break;
-        case RayType_Diffuse:
-            if (!m_raygen.ao(m_secondaryRays, m_primaryRays, *m_scene, m_params.numSamples, m_cameraFar, m_newBatch, FixedSecondarySeed)) return false;
-            m_secondaryRays.setNeedClosestHit(true);
-            m_batchRays = &m_secondaryRays;
+        }
+        case RayType_Diffuse: {
+            RayBuffer& sec = m_secondary[0];
+            if (!m_raygen.ao(sec, m_primaryRays, *m_scene, m_params.numSamples, m_cameraFar, m_newBatch, FixedSecondarySeed)) return false;
+            sec.setNeedClosestHit(true);
+            m_batchRays = &sec;
             break;
+        }
         default:
             fail("Renderer: unsupported ray type");
         }
@@ -128,7 +175,11 @@ private:
     Params m_params;
     HLBVHParams m_hlbvh;
     String m_builder, m_cachePath, m_cacheFileOverride;
-    RayBuffer m_primaryRays, m_secondaryRays;
+    RayBuffer m_primaryRays, m_secondary[NumSecondary];
+    RayBuffer* m_queue[NumSecondary];
+    int m_genIdx, m_queueHead, m_queueLen;
+    bool m_genDone;
+    bool m_pipelined;
     F32 m_cameraFar;
     bool m_newBatch;
     RayBuffer* m_batchRays;

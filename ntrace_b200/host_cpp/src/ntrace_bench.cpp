@@ -63,6 +63,8 @@ static void runBenchmark(Environment& env)
     env.GetIntValue("Renderer.samples", samples); env.GetFloatValue("Raygen.aoRadius", aoRadius); env.GetBoolValue("Renderer.sortRays", sortRays);
     env.GetStringValue("Benchmark.kernel", kernelSpec); env.GetStringValue("Renderer.rayType", rayTypeSpec);
     env.GetStringValue("App.stats", statsFile); env.GetStringValue("Benchmark.dumpPrefix", dumpPrefix);
+    bool pipelined = false;
+    env.GetBoolValue("Benchmark.pipelined", pipelined);
     if (env.GetStringValue("Renderer.dataStructure", ds) && ds != "BVH") fail("Incorrect data structure type!  (only Renderer.dataStructure=BVH is on this path)");
     if (!env.GetStringValue("Benchmark.scene", sceneFile) || sceneFile.empty()) fail("Benchmark.scene is not set");
     if (!env.GetStringValue("Benchmark.camera", cameraSpec) || cameraSpec.empty()) fail("Benchmark.camera is empty");
@@ -101,6 +103,9 @@ static void runBenchmark(Environment& env)
     int hlbvhBits = 4, leafSize = 8;
     env.GetIntValue("HLBVH.bits", hlbvhBits); env.GetIntValue("HLBVH.leafSize", leafSize);
     renderer.setHLBVHParams(HLBVHParams(true, hlbvhBits, leafSize, 0.001f));
+    bool collapse = false;
+    env.GetBoolValue("HLBVH.collapse", collapse);
+    ntCheck(nt_bvh_set_collapse(collapse ? 1 : 0, leafSize));
 
     FILE* stats = fopen(statsFile.c_str(), "a");
     if (!stats) fail("Cannot open stats file '%s'", statsFile.c_str());
@@ -115,14 +120,28 @@ static void runBenchmark(Environment& env)
                 params.kernelName = kernels[k]; params.rayType = rayTypeIds[r]; params.numSamples = samples;
                 params.aoRadius = aoRadius; params.sortSecondary = sortRays;
                 renderer.setParams(params);
-                renderer.beginFrame(cameras[c], w, h);
-                totalRays += (long long)renderer.getTotalNumRays() * measureRepeats;
+                renderer.setPipelined(pipelined);
                 RayBuffer* last = NULL;
-                while (renderer.nextBatch()) {
-                    renderer.traceBatch();
-                    for (int i = 0; i < warmupRepeats; i++) renderer.traceBatch();
-                    for (int i = 0; i < measureRepeats; i++) totalTime += renderer.traceBatch();
-                    last = renderer.getBatchRays();
+                if (pipelined) {
+                    // NEW knob Benchmark.pipelined: whole frames are repeated instead of single batches; the batches of a frame are queued
+                    // back to back on alternating buffers and the device time of the whole batch loop is what is summed
+                    for (int rep = 0; rep < warmupRepeats + measureRepeats; rep++) {
+                        renderer.beginFrame(cameras[c], w, h);
+                        if (rep == 0) totalRays += (long long)renderer.getTotalNumRays() * measureRepeats;
+                        renderer.beginTiming();
+                        while (renderer.nextBatch()) { renderer.traceBatch(); last = renderer.getBatchRays(); }
+                        const double sec = renderer.endTiming();
+                        if (rep >= warmupRepeats) totalTime += sec;
+                    }
+                } else {
+                    renderer.beginFrame(cameras[c], w, h);
+                    totalRays += (long long)renderer.getTotalNumRays() * measureRepeats;
+                    while (renderer.nextBatch()) {
+                        renderer.traceBatch();
+                        for (int i = 0; i < warmupRepeats; i++) renderer.traceBatch();
+                        for (int i = 0; i < measureRepeats; i++) totalTime += renderer.traceBatch();
+                        last = renderer.getBatchRays();
+                    }
                 }
                 if (!dumpPrefix.empty() && c + 1 == cameras.size() && last) {
                     std::string base = dumpPrefix + "." + kernels[k] + "." + rayTypes[r];

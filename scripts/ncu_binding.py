@@ -6,13 +6,12 @@ It (1) measures an L2 bandwidth peak (torch copy of an L2-resident buffer, CUDA 
 (2) runs `ncu --metrics ...` over scripts/profile_kernel.py (one primary, one AO, one diffuse launch of the chosen kernel on the bench
 frame) and (3) stores per ray type: duration, lanes per instruction, issue-slot utilisation, ALU / FMA / LSU pipe utilisation,
 L1 data-pipe (wavefront) utilisation, L1 / L2 hit rates, L2 bytes and GB/s against the measured L2 peak, DRAM bytes and GB/s
-against the measured HBM peak, the stall breakdown, plus the sha256 of libntrace_b200.so so that bench.py can tell whether the
+against the measured HBM peak, the stall breakdown, plus the sha256 of the library's sources (ntrace_b200.build.source_sha16) so that bench.py can tell whether the
 capture describes the library it is timing.  Numbers taken under ncu are NOT bench values: durations here are cold-cache and
 serialised; bench.py uses the RATES and FRACTIONS only.
 """
 import argparse
 import csv
-import hashlib
 import json
 import os
 import subprocess
@@ -50,10 +49,8 @@ METRICS = [
 
 
 def lib_sha():
-    h = hashlib.sha256()
-    with open(os.path.join(ROOT, "ntrace_b200", "libntrace_b200.so"), "rb") as f:
-        h.update(f.read())
-    return h.hexdigest()[:16]
+    from ntrace_b200 import build as nb
+    return nb.source_sha16()
 
 
 def measure_l2_peak():
