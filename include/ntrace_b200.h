@@ -145,6 +145,10 @@ int nt_bvh_convert(int layout);
  * outWideNodes may be NULL to query *outWideBytes; *outMaxDepth (optional) = depth of the Wide4 tree. */
 int nt_bvh_wide4_convert_host(int layout, const void* nodes, size_t nodeBytes, size_t woopBytes,
                               void* outWideNodes, size_t outCapacityBytes, size_t* outWideBytes, int* outMaxDepth);
+/* FW::hashBuffer (src/framework/base/Hash.cpp:33-75): the hash Renderer::getCudaBVH builds its cache file name from
+ * ("bvhcache/<hash>_<builder>.dat", Renderer.cpp:173-178).  Pure host code (no device needed), so that both hosts above this ABI
+ * name cache files with one implementation, pinned against the reference's own Hash.cpp (tests/test_reference_pin.py). */
+int nt_hash_buffer(const void* ptr, size_t size, uint32_t* outHash);
 /* NEW: generation of the resident BVH.  The library keeps ONE resident BVH (the reference's tracer keeps one CudaAS pointer,
  * CudaBVHTracer.hpp:46); every upload / alloc / build / convert replaces it and bumps this counter (0 = none).  A host-side handle
  * that skips the upload because "its" BVH is resident records the value after its build and compares it before tracing. */
@@ -155,6 +159,20 @@ int nt_bvh_sizes(size_t sizes[3], int* outLayout);
 int nt_bvh_download(void* nodes, void* woop, int32_t* triIndex);
 /* device addresses of the three buffers, for the host's NCCL broadcast (NEW). */
 int nt_bvh_device_ptrs(void* ptrs[3]);
+/* ---- multi-GPU (NEW; SURVEY.md 8b/8e: the reference is single-context, CudaModule.hpp:92-97) ------------------------------
+ * One process per GPU.  NCCL is bound at run time (dlopen of libnccl.so.2, or the path in NTRACE_NCCL_LIB): a single-GPU host needs
+ * no NCCL.  Bootstrap: rank 0 calls nt_comm_unique_id and ships the 128 bytes to the other ranks by any means (file, socket, MPI);
+ * every rank then calls nt_comm_init (collective; the communicator lives on the device nt_init selected).
+ * nt_bvh_broadcast (collective) replicates the resident BVH of rank `root` — a header {layout, 3 sizes} and the three CudaBVH buffers,
+ * ncclBroadcast over NVLink — into every other rank's library, which allocates as nt_bvh_alloc would; outSeconds = device time of the
+ * three buffer broadcasts on this rank.  SURVEY.md sketched nt_bvh_broadcast(int numGpus); with one process per GPU the rank count
+ * belongs to the communicator, and the ray path needs no numGpus argument: each rank passes ITS slice of a RayBuffer to nt_trace_batch.
+ * nt_comm_allreduce: element-wise sum (op 0) / max (op 1) of `count` host doubles over the ranks (timing the slowest rank, counting rays). */
+int nt_comm_unique_id(void* out128);
+int nt_comm_init(int numRanks, int rank, const void* uniqueId128);
+int nt_comm_destroy(void);
+int nt_comm_allreduce(double* values, int count, int op);
+int nt_bvh_broadcast(int root, float* outSeconds);
 /* intermediate products of the last nt_bvh_build, for parity tests: sorted Morton keys and the
  * triangle order (reference buffers triMorton / triIdx, HLBVHBuilder.cpp:497-508). */
 int nt_bvh_build_debug(uint32_t* sortedKeys, int32_t* sortedIdx, int numTris);
@@ -193,8 +211,8 @@ int nt_raygen_shadow(float* outRays, int32_t* outIDToSlot, int32_t* outSlotToID,
                      const float lightPos[3], float lightRadius, uint32_t randomSeed);
 /* RayBuffer::mortonSort (src/rt/ray/RayBuffer.cpp:103-163): reorder the batch in place by the Morton key of
  * (origin, direction) and rebuild the id<->slot maps (outSlotToID[new] = inSlotToID[old], outIDToSlot[id] = new).
- * The reference sorts 192-bit keys on the CPU; here the top 64 significant key bits are radix-sorted on the GPU, ties
- * keep their original order. */
+ * The reference sorts the 192-bit keys on the CPU (compareMortonKey, hash[5] most significant); here the same full-key order is
+ * produced on the GPU by a word-wise stable LSD radix sort; rays with identical keys keep their original order. */
 int nt_ray_sort(float* rays, int32_t* idToSlot, int32_t* slotToID, int numRays);
 /* countHitsKernel (RendererKernels.cu:174-224, Renderer.cpp:693-705): results with id >= 0. */
 int nt_count_hits(const int32_t* results, int numRays, int* outHits);

@@ -7,7 +7,7 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB = os.path.join(_HERE, "libntrace_b200.so")
-SOURCES = ["nt_api.cu", "nt_trace.cu", "nt_raygen.cu", "nt_build.cu", "nt_raysort.cu", "nt_layout.cu", "nt_wide.cu"]
+SOURCES = ["nt_api.cu", "nt_trace.cu", "nt_raygen.cu", "nt_build.cu", "nt_raysort.cu", "nt_layout.cu", "nt_wide.cu", "nt_comm.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "--threads", "0",
               "-Xcompiler", "-fPIC", "-shared"]
 
@@ -44,7 +44,7 @@ def source_sha16() -> str:
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not is_stale():
         return LIB
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES] + ["-lcudart"]
+    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES] + ["-lcudart", "-ldl"]
     env = dict(os.environ)
     # the image exports CXX=/opt/gcc/bin/g++ (a wrapper); let nvcc use the system host compiler
     r = subprocess.run(cmd, capture_output=True, text=True, env=env)

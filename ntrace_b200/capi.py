@@ -28,7 +28,7 @@ EXPORTS = [
     "nt_event_record", "nt_event_elapsed", "nt_set_deferred", "nt_synchronize",
     "nt_set_kernel", "nt_desired_layout", "nt_kernel_config",
     "nt_bvh_upload", "nt_bvh_alloc", "nt_bvh_build", "nt_bvh_set_collapse", "nt_bvh_set_build_layout", "nt_bvh_convert", "nt_bvh_sizes", "nt_bvh_download",
-    "nt_bvh_device_ptrs", "nt_bvh_build_debug", "nt_bvh_wide4_convert_host", "nt_bvh_generation",
+    "nt_bvh_device_ptrs", "nt_bvh_build_debug", "nt_bvh_wide4_convert_host", "nt_bvh_generation", "nt_hash_buffer", "nt_comm_unique_id", "nt_comm_init", "nt_comm_destroy", "nt_comm_allreduce", "nt_bvh_broadcast",
     "nt_trace_batch", "nt_trace_batch_async", "nt_trace_wait", "nt_raygen_primary", "nt_raygen_ao", "nt_raygen_shadow", "nt_ray_sort", "nt_count_hits", "nt_tri_normals",
 ]
 
@@ -171,6 +171,43 @@ def bvh_convert(layout: int):
 
 def bvh_set_collapse(mode: int, max_leaf: int = 0):
     _check(lib().nt_bvh_set_collapse(C.c_int(mode), C.c_int(max_leaf)))
+
+
+def hash_buffer(data) -> int:
+    """FW::hashBuffer (Hash.cpp:33-75) of a bytes-like object / numpy array; host-only."""
+    if isinstance(data, (bytes, bytearray)):
+        data = np.frombuffer(bytes(data), dtype=np.uint8)
+    data = np.ascontiguousarray(data)
+    out = C.c_uint32(0)
+    _check(lib().nt_hash_buffer(C.c_void_p(data.ctypes.data) if data.nbytes else None, C.c_size_t(data.nbytes), C.byref(out)))
+    return int(out.value)
+
+
+def comm_unique_id() -> bytes:
+    buf = (C.c_char * 128)()
+    _check(lib().nt_comm_unique_id(buf))
+    return bytes(buf)
+
+
+def comm_init(num_ranks: int, rank: int, unique_id: bytes):
+    _check(lib().nt_comm_init(C.c_int(num_ranks), C.c_int(rank), C.c_char_p(unique_id)))
+
+
+def comm_destroy():
+    _check(lib().nt_comm_destroy())
+
+
+def comm_allreduce(values, op: str = "max"):
+    a = np.ascontiguousarray(values, dtype=np.float64).copy()
+    _check(lib().nt_comm_allreduce(ptr(a), C.c_int(len(a)), C.c_int(0 if op == "sum" else 1)))
+    return a
+
+
+def bvh_broadcast(root: int = 0) -> float:
+    """Replicate rank `root`'s resident BVH into every rank's library (NCCL, inside the C ABI) -> seconds of the three broadcasts."""
+    sec = C.c_float(0.0)
+    _check(lib().nt_bvh_broadcast(C.c_int(root), C.byref(sec)))
+    return float(sec.value)
 
 
 def bvh_generation() -> int:

@@ -405,6 +405,7 @@ void nt_shutdown(void)
     for (DevBuf* b : bufs) b->release();
     release_build_scratch();
     release_sort_scratch();
+    comm_destroy();
     reset_launch_caches();         // occupancy / carve-out decisions belong to the device they were taken on
     for (int i = 0; i < Context::kAsyncSlots; i++) {
         g.async[i].rays.release(); g.async[i].results.release();
@@ -736,6 +737,124 @@ int nt_bvh_wide4_convert_host(int layout, const void* nodes, size_t nodeBytes, s
         if (outCapacityBytes < w.size() * 4) { set_error("ntrace_b200: output buffer too small for the Wide4 node array"); return 1; }
         memcpy(outWideNodes, w.data(), w.size() * 4);
     }
+    return 0;
+}
+
+// ---- multi-GPU: communicator + BVH replication (nt_comm.cu) ---------------------------------------------------------------------
+int nt_comm_unique_id(void* out128) { std::lock_guard<std::mutex> lock(g_mutex); return comm_unique_id(out128); }
+
+int nt_comm_init(int numRanks, int rank, const void* uniqueId128)
+{
+    std::lock_guard<std::mutex> lock(g_mutex);
+    if (require_init()) return 1;                     // the communicator lives on the device nt_init selected
+    return comm_init(numRanks, rank, uniqueId128);
+}
+
+int nt_comm_destroy(void)
+{
+    std::lock_guard<std::mutex> lock(g_mutex);
+    if (g.inited) { cudaSetDevice(g.device); cudaStreamSynchronize(g.stream); }
+    return comm_destroy();
+}
+
+int nt_comm_allreduce(double* values, int count, int op)
+{
+    std::lock_guard<std::mutex> lock(g_mutex);
+    if (require_init()) return 1;
+    return comm_allreduce_f64(values, count, op, g.stream);
+}
+
+int nt_bvh_broadcast(int root, float* outSeconds)
+{
+    std::lock_guard<std::mutex> lock(g_mutex);
+    if (outSeconds) *outSeconds = 0.0f;
+    if (require_init()) return 1;
+    if (!comm_ready()) { set_error("ntrace_b200: no communicator (nt_comm_init)"); return 1; }
+    if (root < 0 || root >= comm_size()) { set_error("ntrace_b200: broadcast root out of range"); return 1; }
+    const bool isRoot = comm_rank() == root;
+    if (isRoot && !g.haveBVH) { set_error("CudaBVHTracer: No BVH!"); return 1; }
+    // header: layout + the three sizes ("+ a 16-byte header {layout, sizes}"; sizes are 64-bit here)
+    long long meta[4] = {0, 0, 0, 0};
+    if (isRoot) {
+        meta[0] = g.bvhLayout;
+        meta[1] = (long long)(g.basic ? g.srcNodeBytes : g.nodeBytes);
+        meta[2] = (long long)(g.basic ? g.srcWoopBytes : g.woopBytes);
+        meta[3] = (long long)(g.basic ? g.srcIdxBytes : g.idxBytes);
+    }
+    void* dMeta = g.counters.as<char>() + 128;
+    NT_CUDA(cudaMemcpyAsync(dMeta, meta, sizeof(meta), cudaMemcpyHostToDevice, g.stream));
+    if (comm_broadcast_bytes(dMeta, sizeof(meta), root, g.stream)) return 1;
+    NT_CUDA(cudaMemcpyAsync(meta, dMeta, sizeof(meta), cudaMemcpyDeviceToHost, g.stream));
+    NT_CUDA(cudaStreamSynchronize(g.stream));
+    const int layout = (int)meta[0];
+    const size_t nb = (size_t)meta[1], wb = (size_t)meta[2], ib = (size_t)meta[3];
+    if (!isRoot) {
+        // replica: make room exactly as nt_bvh_alloc does (the old BVH is gone from here on)
+        g.haveBVH = false;
+        g.generation++;
+        g.wideValid = false; g.converted = false;
+        g.basic = is_basic_layout(layout);
+        if (!g.basic && layout != Layout_Compact && layout != Layout_Compact2) { set_error("ntrace_b200: broadcast header carries an unknown layout"); return 1; }
+        NT_CUDA((g.basic ? g.srcNodes : g.nodes).reserve(nb));
+        NT_CUDA((g.basic ? g.srcWoop : g.woop).reserve(wb));
+        NT_CUDA((g.basic ? g.srcIdx : g.triIndex).reserve(ib));
+        if (g.basic) { g.srcNodeBytes = nb; g.srcWoopBytes = wb; g.srcIdxBytes = ib; }
+        else { g.nodeBytes = nb; g.woopBytes = wb; g.idxBytes = ib; }
+        g.bvhLayout = layout;
+        g.builtTris = 0;
+    }
+    NT_CUDA(cudaEventRecord(g.evA, g.stream));
+    if (comm_broadcast_bytes((g.basic ? g.srcNodes : g.nodes).p, nb, root, g.stream)) return 1;
+    if (comm_broadcast_bytes((g.basic ? g.srcWoop : g.woop).p, wb, root, g.stream)) return 1;
+    if (comm_broadcast_bytes((g.basic ? g.srcIdx : g.triIndex).p, ib, root, g.stream)) return 1;
+    NT_CUDA(cudaEventRecord(g.evB, g.stream));
+    NT_CUDA(cudaStreamSynchronize(g.stream));
+    float ms = 0.0f;
+    NT_CUDA(cudaEventElapsedTime(&ms, g.evA, g.evB));
+    if (outSeconds) *outSeconds = ms * 1.0e-3f;
+    if (!isRoot) {
+        g.haveBVH = true;
+        if (g.basic && ensure_traversal_form()) { g.haveBVH = false; return 1; }
+    }
+    return 0;
+}
+
+int nt_hash_buffer(const void* ptr, size_t size, uint32_t* outHash)
+{
+    // FW::hashBuffer (src/framework/base/Hash.cpp:33-75; Bob Jenkins' 1996 mix, Hash.hpp:169-181): pure host code
+    if (!outHash || (!ptr && size) || size > 0x7fffffffull) { set_error("ntrace_b200: bad arguments to nt_hash_buffer"); return 1; }
+#define NT_JENKINS_MIX(a, b, c) \
+    a -= b; a -= c; a ^= (c >> 13); b -= c; b -= a; b ^= (a << 8);  c -= a; c -= b; c ^= (b >> 13); \
+    a -= b; a -= c; a ^= (c >> 12); b -= c; b -= a; b ^= (a << 16); c -= a; c -= b; c ^= (b >> 5);  \
+    a -= b; a -= c; a ^= (c >> 3);  b -= c; b -= a; b ^= (a << 10); c -= a; c -= b; c ^= (b >> 15);
+    const uint8_t* src = (const uint8_t*)ptr;
+    uint32_t a = 0x9e3779b9u, b = 0x9e3779b9u, c = 0x9e3779b9u;
+    size_t left = size;
+    while (left >= 12) {
+        a += (uint32_t)src[0] + ((uint32_t)src[1] << 8) + ((uint32_t)src[2] << 16) + ((uint32_t)src[3] << 24);
+        b += (uint32_t)src[4] + ((uint32_t)src[5] << 8) + ((uint32_t)src[6] << 16) + ((uint32_t)src[7] << 24);
+        c += (uint32_t)src[8] + ((uint32_t)src[9] << 8) + ((uint32_t)src[10] << 16) + ((uint32_t)src[11] << 24);
+        NT_JENKINS_MIX(a, b, c);
+        src += 12; left -= 12;
+    }
+    switch (left) {
+    case 11: c += (uint32_t)src[10] << 16;   // fall through
+    case 10: c += (uint32_t)src[9] << 8;     // fall through
+    case 9:  c += (uint32_t)src[8];          // fall through
+    case 8:  b += (uint32_t)src[7] << 24;    // fall through
+    case 7:  b += (uint32_t)src[6] << 16;    // fall through
+    case 6:  b += (uint32_t)src[5] << 8;     // fall through
+    case 5:  b += (uint32_t)src[4];          // fall through
+    case 4:  a += (uint32_t)src[3] << 24;    // fall through
+    case 3:  a += (uint32_t)src[2] << 16;    // fall through
+    case 2:  a += (uint32_t)src[1] << 8;     // fall through
+    case 1:  a += (uint32_t)src[0];          // fall through
+    default: break;
+    }
+    c += (uint32_t)left;
+    NT_JENKINS_MIX(a, b, c);
+#undef NT_JENKINS_MIX
+    *outHash = c;
     return 0;
 }
 

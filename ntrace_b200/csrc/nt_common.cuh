@@ -126,4 +126,14 @@ cudaError_t convert_basic_layout(int layout, const void* dNodes, size_t nodeByte
                                  const int* dTriIndex, size_t idxBytes, int targetLayout, BuildOutput& out, DevBuf& scratch,
                                  cudaStream_t stream, int* outLaunches, std::string* err);
 
+// ---- multi-GPU (nt_comm.cu): NCCL bound at run time
+int comm_unique_id(void* out128);
+int comm_init(int numRanks, int rank, const void* uniqueId128);
+int comm_destroy();
+bool comm_ready();
+int comm_rank();
+int comm_size();
+int comm_broadcast_bytes(void* devPtr, size_t bytes, int root, cudaStream_t stream);
+int comm_allreduce_f64(double* hostValues, int count, int op, cudaStream_t stream);
+
 } // namespace nt

@@ -3,10 +3,11 @@
 // Replaces src/rt/ray/RayBuffer.cpp:103-163 + src/rt/ray/RayBufferKernels.cu:70-196: the reference finds the AABB of the
 // rays on the GPU, builds a 192-bit key per ray (origin and direction, 32 bits per component, bit i of component k at
 // key bit k + 6 i), **sorts the keys on the CPU** (multicore quicksort, RayBuffer.cpp:149) and gathers the rays on the GPU.
-// Here everything stays on the device: the sort is the same hand-written stable LSD radix sort the BVH builder uses, on
-// the top 64 significant bits of the reference key (bits 83..146: 10-11 bits per origin axis, 7 per direction axis).
-// Rays whose keys agree on those 64 bits keep their original relative order; in the reference they would be ordered by
-// the remaining low bits — such rays are coherent to 2^-10 of the batch extent, so tracing is unaffected.
+// Here everything stays on the device: the sort is the same hand-written stable LSD radix sort the BVH builder uses, over the
+// FULL key in the comparator's order (compareMortonKey, RayBuffer.cpp:88-99: hash[5] most significant): the 192 bits are held
+// as three 64-bit words and sorted least-significant word first — 8 passes on bits 0..63, 8 on bits 64..127 and 4 on bits
+// 128..159 (bits 150..191 are always zero: the origin components have 25 significant bits, the direction components 22).
+// Rays with identical keys keep their original relative order (the reference's quicksort leaves that case unspecified).
 #include "nt_common.cuh"
 #include "nt_sort.cuh"
 
@@ -48,9 +49,9 @@ __global__ void __launch_bounds__(256) ray_aabb_kernel(const float4* __restrict_
 // (U32)float as the reference's device code converts: saturating, NaN and negatives -> 0
 __device__ __forceinline__ unsigned f2u_sat(float f) { return __float2uint_rz(f); }
 
-// genMortonKeysKernel, truncated to key bits [83, 147)
+// genMortonKeysKernel: key bit (k + 6 i) = bit i of component k (collectBits, RayBufferKernels.cu:120-136), as three 64-bit words
 __global__ void __launch_bounds__(256) ray_keys_kernel(const float4* __restrict__ rays, int n, const int* __restrict__ box,
-                                                        u64* __restrict__ keys, int* __restrict__ idx)
+                                                        u64* __restrict__ w0, u64* __restrict__ w1, u64* __restrict__ w2, int* __restrict__ idx)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -70,17 +71,23 @@ __global__ void __launch_bounds__(256) ray_keys_kernel(const float4* __restrict_
         comp[k] = f2u_sat(__fmul_rn(__fmul_rn(a, 256.0f), 65536.0f));
         comp[3 + k] = f2u_sat(__fmul_rn(__fmul_rn(b, 32.0f), 65536.0f));
     }
-    // key bit (k + 6 i) = bit i of component k; keep key bits 83..146 -> output bit (k + 6 i - 83)
-    u64 key = 0;
+    u64 w[3] = {0, 0, 0};
 #pragma unroll
-    for (int bit = 13; bit <= 24; bit++)
+    for (int bit = 0; bit < 32; bit++)
 #pragma unroll
         for (int k = 0; k < 6; k++) {
-            const int pos = k + 6 * bit - 83;
-            if (pos >= 0 && pos < 64) key |= (u64)((comp[k] >> bit) & 1u) << pos;
+            const int pos = k + 6 * bit;
+            w[pos >> 6] |= (u64)((comp[k] >> bit) & 1u) << (pos & 63);
         }
-    keys[i] = key;
+    w0[i] = w[0]; w1[i] = w[1]; w2[i] = w[2];
     idx[i] = i;
+}
+
+// next round of the word-wise LSD sort: the key word of the rays in their current order
+__global__ void __launch_bounds__(256) ray_key_gather_kernel(int n, const int* __restrict__ order, const u64* __restrict__ word, u64* __restrict__ out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = __ldg(word + __ldg(order + i));
 }
 
 // reorderRaysKernel
@@ -98,7 +105,7 @@ __global__ void __launch_bounds__(256) ray_reorder_kernel(int n, const int* __re
     outSlotToID[i] = id;
 }
 
-struct SortScratch { DevBuf keysA, keysB, idxA, idxB, hist, blockSums, box, oldRays, oldS2I; };
+struct SortScratch { DevBuf keysA, keysB, idxA, idxB, hist, blockSums, box, oldRays, oldS2I, word1, word2; };
 SortScratch g_ss;
 static_assert(sizeof(SortScratch) % sizeof(DevBuf) == 0, "SortScratch holds DevBuf members only");
 
@@ -121,16 +128,27 @@ cudaError_t ray_sort_device(float4* rays, int* idToSlot, int* slotToID, int n, c
     NT_TRY(s.hist.reserve(radix_hist_bytes(n)));
     NT_TRY(s.blockSums.reserve(scan_block_sums_bytes((long long)radix_hist_bytes(n) / 4)));
     NT_TRY(s.box.reserve(64)); NT_TRY(s.oldRays.reserve((size_t)n * 32)); NT_TRY(s.oldS2I.reserve((size_t)n * 4));
+    NT_TRY(s.word1.reserve((size_t)n * 8)); NT_TRY(s.word2.reserve((size_t)n * 8));
 
     ray_aabb_init_kernel<<<1, 32, 0, stream>>>(s.box.as<int>());
     int grid = (n + 255) / 256;
     if (grid > numSMs * 8) grid = numSMs * 8;
     ray_aabb_kernel<<<grid, 256, 0, stream>>>(rays, n, s.box.as<int>());
-    ray_keys_kernel<<<(n + 255) / 256, 256, 0, stream>>>(rays, n, s.box.as<int>(), s.keysA.as<u64>(), s.idxA.as<int>());
+    ray_keys_kernel<<<(n + 255) / 256, 256, 0, stream>>>(rays, n, s.box.as<int>(), s.keysA.as<u64>(), s.word1.as<u64>(), s.word2.as<u64>(), s.idxA.as<int>());
     launches += 3;
     NT_TRY(cudaGetLastError());
+    // least significant word first; every round is stable, so after the last one the order is that of the whole 192-bit key
     NT_TRY(radix_sort_pairs<u64>(s.keysA.as<u64>(), s.idxA.as<int>(), s.keysB.as<u64>(), s.idxB.as<int>(), n, 8,
                                  s.hist.as<uint>(), s.blockSums.as<uint>(), stream, &launches));
+    const u64* words[2] = {s.word1.as<u64>(), s.word2.as<u64>()};
+    const int passes[2] = {8, 4};
+    for (int r = 0; r < 2; r++) {
+        ray_key_gather_kernel<<<(n + 255) / 256, 256, 0, stream>>>(n, s.idxA.as<int>(), words[r], s.keysA.as<u64>());
+        launches++;
+        NT_TRY(cudaGetLastError());
+        NT_TRY(radix_sort_pairs<u64>(s.keysA.as<u64>(), s.idxA.as<int>(), s.keysB.as<u64>(), s.idxB.as<int>(), n, passes[r],
+                                     s.hist.as<uint>(), s.blockSums.as<uint>(), stream, &launches));
+    }
     NT_TRY(cudaMemcpyAsync(s.oldRays.p, rays, (size_t)n * 32, cudaMemcpyDeviceToDevice, stream));
     NT_TRY(cudaMemcpyAsync(s.oldS2I.p, slotToID, (size_t)n * 4, cudaMemcpyDeviceToDevice, stream));
     ray_reorder_kernel<<<(n + 255) / 256, 256, 0, stream>>>(n, s.idxA.as<int>(), s.oldRays.as<float4>(), s.oldS2I.as<int>(), rays, idToSlot, slotToID);

@@ -25,6 +25,7 @@ OPTIONS = {
     "Benchmark.kernel": ("string", "benchmark_kernel=", None),
     "Benchmark.warmupRepeats": ("int", "benchmark_warmup=", "1"),
     "Benchmark.measureRepeats": ("int", "benchmark_measure=", "5"),
+    "Benchmark.cachePath": ("string", "benchmark_cachepath=", None),        # new: directory of the bvhcache files (reference: "bvhcache")
     "Benchmark.pipelined": ("bool", "benchmark_pipelined=", "false"),      # new: queue a frame's batches back to back (Renderer.setPipelined)
     "Renderer.dataStructure": ("string", "renderer_ds=", None),
     "Renderer.builder": ("string", "renderer_builder=", None),

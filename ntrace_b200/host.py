@@ -162,6 +162,16 @@ class Scene:
         self.bboxMin = self.verts_host.min(0).astype(np.float32)
         self.bboxMax = self.verts_host.max(0).astype(np.float32)
 
+    # host views of the three buffers Scene::hash covers here (Scene.cpp:171-179)
+    def triVtxIndex_host(self):
+        return self.tris_host
+
+    def vtxPos_host(self):
+        return self.verts_host
+
+    def triNormal_host(self):
+        return self.triNormal.cpu().numpy()
+
     def getNumTriangles(self) -> int:
         return len(self.tris_host)
 
@@ -376,6 +386,59 @@ class RendererParams:
 class BuildSettings:
     builder: str = "HLBVH"            # Renderer.builder: HLBVH | LBVH (GPU); prebuilt CudaBVH via setCudaBVH
     hlbvh: HLBVHParams = field(default_factory=HLBVHParams)
+    cachePath: str = None             # Renderer.cacheDataStructure: directory of the bvhcache files (reference: "bvhcache"); None = no cache
+    dataStructure: str = "BVH"        # Renderer.dataStructure (part of the cache file name)
+
+
+# ---- bvhcache file names: Renderer::getCudaBVH (Renderer.cpp:173-178) ------------------------------------------------
+_MAGIC = 0x9e3779b9
+
+
+def _jenkins_mix(a, b, c):
+    """FW_JENKINS_MIX (Hash.hpp:172-181), 32-bit wrap-around arithmetic."""
+    M = 0xffffffff
+    a = (a - b - c) & M; a ^= c >> 13
+    b = (b - c - a) & M; b ^= (a << 8) & M
+    c = (c - a - b) & M; c ^= b >> 13
+    a = (a - b - c) & M; a ^= c >> 12
+    b = (b - c - a) & M; b ^= (a << 16) & M
+    c = (c - a - b) & M; c ^= b >> 5
+    a = (a - b - c) & M; a ^= c >> 3
+    b = (b - c - a) & M; b ^= (a << 10) & M
+    c = (c - a - b) & M; c ^= b >> 15
+    return a, b, c
+
+
+def hash_bits(a, b=None, c=None, d=None, e=0, f=0):
+    """FW::hashBits, both overloads (Hash.hpp:183-184): (a[, b[, c]]) and (a, b, c, d[, e[, f]])."""
+    M = 0xffffffff
+    if d is None:
+        b = _MAGIC if b is None else b
+        c = 0 if c is None else c
+        a, b, c = _jenkins_mix(a & M, b & M, (c + _MAGIC) & M)
+        return c
+    a, b, c = _jenkins_mix(a & M, b & M, (c + _MAGIC) & M)
+    a, b, c = _jenkins_mix((a + d) & M, (b + e) & M, (c + f) & M)
+    return c
+
+
+def _f2b(x: float) -> int:
+    return int(np.float32(x).view(np.uint32))
+
+
+def cache_file_name(scene: "Scene", builder: str, layout: int, cachePath: str = "bvhcache", dataStructure: str = "BVH",
+                    minLeaf: int = 1, maxLeaf: int = 1, splitAlpha: float = 1.0e-5) -> str:
+    """"<cachePath>/<hash>_<builder>.dat" exactly as Renderer::getCudaBVH forms it (Renderer.cpp:173-178): hashBits(scene hash,
+    Platform("GPU") hash with the renderer's leaf preferences (1, 1) (Renderer.cpp:88-89), BuildParams hash (splitAlpha), layout,
+    hash of Renderer.dataStructure).  Scene::hash (Scene.cpp:171-179) covers five buffers; this path carries no material colours,
+    so those two enter as empty buffers — for a scene WITH materials the reference's name differs, the file format does not."""
+    hb = capi.hash_buffer
+    empty = hb(b"")
+    scene_hash = hash_bits(hb(scene.triVtxIndex_host()), hb(scene.triNormal_host()), empty, empty, hb(scene.vtxPos_host()))
+    platform = hash_bits(hb(b"GPU"), _f2b(1.0), _f2b(1.0), hash_bits(1, 1, minLeaf, maxLeaf))              # Platform.hpp:162
+    params = hash_bits(_f2b(splitAlpha))                                                                       # BVH.hpp:141-144
+    h = hash_bits(scene_hash, platform, params, layout, hb(dataStructure.encode()))
+    return "%s/%08x_%s.dat" % (cachePath, h, builder)
 
 
 class Renderer:
@@ -451,6 +514,14 @@ class Renderer:
         if self.m_bvh is not None:
             return self.m_bvh
         b = self.m_build.builder
+        cache = None
+        if self.m_build.cachePath is not None:                       # Renderer.cpp:173-191: a cache file that exists is imported
+            import os
+            cache = cache_file_name(self.m_scene, b, self.m_cudaTracer.getDesiredBVHLayout(), self.m_build.cachePath, self.m_build.dataStructure)
+            if os.path.exists(cache):
+                with open(cache, "rb") as f:
+                    self.m_bvh = CudaBVH.deserialize(f)
+                return self.m_bvh
         if b == "HLBVH":
             self.m_bvh = HLBVHBuilder(self.m_scene, self.m_build.hlbvh)     # Renderer.cpp:201-209
         elif b == "LBVH":
@@ -458,6 +529,11 @@ class Renderer:
             self.m_bvh = HLBVHBuilder(self.m_scene, p)
         else:
             raise NtError(f"Unsupported BVH builder {b}")
+        if cache is not None:                                         # Renderer.cpp:293-299
+            import os
+            os.makedirs(os.path.dirname(cache) or ".", exist_ok=True)
+            with open(cache, "wb") as f:
+                self.m_bvh.serialize(f)
         return self.m_bvh
 
     def beginFrame(self, cam: "_camera.Camera", w: int, h: int):

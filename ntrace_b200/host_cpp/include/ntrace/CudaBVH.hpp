@@ -68,6 +68,16 @@ public:
     void setGeneration(uint64_t g) { m_generation = g; }
     bool hasHostCopy() { return m_nodes.getSize() > 0; }
     static uint64_t currentGeneration() { uint64_t g = 0; ntCheck(nt_bvh_generation(&g)); return g; }
+    // a handle for the BVH that is resident in the library right now (a replica after nt_bvh_broadcast)
+    static CudaBVH* adoptResident()
+    {
+        size_t sz[3]; int layout = 0;
+        ntCheck(nt_bvh_sizes(sz, &layout));
+        CudaBVH* b = new CudaBVH((BVHLayout)layout);
+        b->m_resident = true;
+        b->m_generation = currentGeneration();
+        return b;
+    }
 
 protected:
     void materialise()

@@ -19,6 +19,13 @@ public:
                                   (int32_t*)orays.getSlotToIDBuffer().getMutableCudaPtrDiscard(), origin.getPtr(), nscreenToWorld.getPtr(), w, h, maxDist, randomSeed));
     }
 
+    // advance the batching of ao() by one batch without generating it (multi-GPU: the batch belongs to another rank); false at the end
+    bool skipAo(RayBuffer& irays, int numSamples, bool& newBatch)
+    {
+        S32 lo, hi;
+        return batching(irays.getSize(), numSamples, m_aoStartIdx, newBatch, lo, hi);
+    }
+
     // true while the batch continues (reference signature: newBatch is in/out)
     bool ao(RayBuffer& orays, RayBuffer& irays, Scene& scene, int numSamples, float maxDist, bool& newBatch, U32 randomSeed = 0)
     {

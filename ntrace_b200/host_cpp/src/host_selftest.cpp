@@ -11,6 +11,8 @@
 
 // Scene.hpp constructs device buffers; the loaders are static and GPU-free, so only they are pulled in here
 #include "ntrace/Scene.hpp"
+#include "ntrace/Renderer.hpp"
+#include <iterator>
 
 using namespace FW;
 
@@ -24,6 +26,26 @@ static void printMat(const char* name, const Mat4f& m)
 int main(int argc, char** argv)
 {
     try {
+        // host_selftest --cache <in.dat> <out.dat>: the bvhcache stream through CudaBVH(std::istream&) and serialize() (no GPU needed)
+        if (argc == 4 && std::string(argv[1]) == "--cache") {
+            std::ifstream in(argv[2], std::ios::binary);
+            if (!in) fail("cannot open %s", argv[2]);
+            CudaBVH bvh(in);
+            std::ofstream out(argv[3], std::ios::binary);
+            bvh.serialize(out);
+            printf("{\"layout\": %d, \"nodeBytes\": %lld, \"woopBytes\": %lld, \"idxBytes\": %lld}\n", (int)bvh.getLayout(),
+                   (long long)bvh.getNodeBuffer().getSize(), (long long)bvh.getTriWoopBuffer().getSize(), (long long)bvh.getTriIndexBuffer().getSize());
+            return 0;
+        }
+        // host_selftest --hash <file>: FW::hashBuffer of a file and the hashBits overloads on fixed arguments (cache file naming)
+        if (argc == 3 && std::string(argv[1]) == "--hash") {
+            std::ifstream in(argv[2], std::ios::binary);
+            std::vector<char> d((std::istreambuf_iterator<char>(in)), std::istreambuf_iterator<char>());
+            printf("{\"hashBuffer\": %u, \"hashBits1\": %u, \"hashBits3\": %u, \"hashBits4\": %u, \"hashBits6\": %u}\n",
+                   Renderer::hashBuffer(d.data(), d.size()), Renderer::hashBits(12345u), Renderer::hashBits(1u, 2u, 3u),
+                   Renderer::hashBits(1u, 2u, 3u, 4u), Renderer::hashBits(0xdeadbeefu, 7u, 0x80000000u, 4u, 5u, 6u));
+            return 0;
+        }
         if (argc < 3) fail("usage: host_selftest <config.conf> <mesh.obj> [-D...]");
         Environment env;
         std::vector<char*> args;

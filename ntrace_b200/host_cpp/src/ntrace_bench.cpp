@@ -15,6 +15,7 @@
 #include "ntrace/NTrace.hpp"
 #include <algorithm>
 #include <cstdlib>
+#include <unistd.h>
 
 using namespace FW;
 
@@ -69,7 +70,38 @@ static void runBenchmark(Environment& env)
     if (!env.GetStringValue("Benchmark.scene", sceneFile) || sceneFile.empty()) fail("Benchmark.scene is not set");
     if (!env.GetStringValue("Benchmark.camera", cameraSpec) || cameraSpec.empty()) fail("Benchmark.camera is empty");
 
+    // Renderer.numGpus (new): one process per GPU.  Rank and world size come from the launcher's environment (RANK / WORLD_SIZE /
+    // LOCAL_RANK, as torchrun and most MPI wrappers export them) or from -DBenchmark.rank / -DRenderer.numGpus; the NCCL unique id
+    // travels through the file Benchmark.commFile (rank 0 writes it, the others wait for it)
+    int numGpus = 1, rank = 0;
+    env.GetIntValue("Renderer.numGpus", numGpus);
+    if (getenv("WORLD_SIZE")) numGpus = atoi(getenv("WORLD_SIZE"));
+    if (getenv("RANK")) rank = atoi(getenv("RANK"));
+    env.GetIntValue("Benchmark.rank", rank);
+    if (numGpus > 1) { device = getenv("LOCAL_RANK") ? atoi(getenv("LOCAL_RANK")) : rank; }
     ntCheck(nt_init(device));
+    if (numGpus > 1) {
+        std::string commFile;
+        if (!env.GetStringValue("Benchmark.commFile", commFile) || commFile.empty()) fail("Renderer.numGpus > 1 needs Benchmark.commFile (a path every rank can reach)");
+        char id[128];
+        if (rank == 0) {
+            ntCheck(nt_comm_unique_id(id));
+            const std::string tmp = commFile + ".tmp";
+            FILE* f = fopen(tmp.c_str(), "wb");
+            if (!f || fwrite(id, 1, 128, f) != 128) fail("Cannot write '%s'", tmp.c_str());
+            fclose(f);
+            if (rename(tmp.c_str(), commFile.c_str()) != 0) fail("Cannot publish '%s'", commFile.c_str());
+        } else {
+            bool got = false;
+            for (int i = 0; i < 1200 && !got; i++) {
+                FILE* f = fopen(commFile.c_str(), "rb");
+                if (f) { got = fread(id, 1, 128, f) == 128; fclose(f); }
+                if (!got) usleep(100000);
+            }
+            if (!got) fail("rank %d: no NCCL unique id at '%s'", rank, commFile.c_str());
+        }
+        ntCheck(nt_comm_init(numGpus, rank, id));
+    }
     std::vector<CameraControls> cameras;
     std::vector<std::string> camTokens = splitList(cameraSpec, ";");
     for (size_t i = 0; i < camTokens.size(); i++) {
@@ -98,8 +130,11 @@ static void runBenchmark(Environment& env)
     std::unique_ptr<Scene> scene(Scene::importMesh(sceneFile));
     Renderer renderer;
     renderer.setScene(scene.get());
+    if (numGpus > 1) renderer.setMultiGpu(rank, numGpus);
     std::string cacheFile;
     if (env.GetStringValue("Benchmark.cacheFile", cacheFile)) renderer.setCacheFile(cacheFile);
+    std::string cachePath;
+    if (env.GetStringValue("Benchmark.cachePath", cachePath) && !cachePath.empty()) renderer.setCachePath(cachePath);     // files named <hash>_<builder>.dat
     int hlbvhBits = 4, leafSize = 8;
     env.GetIntValue("HLBVH.bits", hlbvhBits); env.GetIntValue("HLBVH.leafSize", leafSize);
     renderer.setHLBVHParams(HLBVHParams(true, hlbvhBits, leafSize, 0.001f));
@@ -149,11 +184,17 @@ static void runBenchmark(Environment& env)
                     dumpBuffer(base + ".results", last->getResultBuffer(), (S64)last->getSize() * 16);
                 }
             }
+            if (numGpus > 1) ntCheck(nt_comm_allreduce(&totalTime, 1, 1));                           // the slowest rank's time; the rays are the frame's
             double krays = totalTime > 0.0 ? (double)totalRays / totalTime * 1.0e-3 : 0.0;
             results.push_back(krays);
-            fprintf(stats, "#SUM_RENDER_TIME\n%g\n#SUM_RENDER_KRAYS\n%g\n", totalTime, krays);      // pushStat (Defs.hpp:166-172)
+            if (rank == 0) fprintf(stats, "#SUM_RENDER_TIME\n%g\n#SUM_RENDER_KRAYS\n%g\n", totalTime, krays);      // pushStat (Defs.hpp:166-172)
         }
     fclose(stats);
+    if (numGpus > 1) {
+        if (rank == 0) printf("%d GPUs: BVH broadcast %.3f ms\n", numGpus, renderer.getBroadcastTime() * 1e3);
+        ntCheck(nt_comm_destroy());
+        if (rank != 0) return;
+    }
 
     printf("Done.\n\n%-42s", "Kernel");
     for (size_t r = 0; r < rayTypes.size(); r++) printf("%-14s", rayTypes[r].c_str());

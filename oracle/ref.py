@@ -112,6 +112,16 @@ class RefBVH:
         lib().ref_layout_copy(self._h, C.c_int(layout), _p(nodes), _p(woop), _p(idx))
         return nodes, woop, idx
 
+    def serialize(self, layout: int = 4) -> bytes:
+        """CudaBVH(bvh, layout).serialize() through the reference's own stream operators -> the bvhcache byte stream."""
+        lib().ref_serialize.restype = C.c_longlong
+        n = lib().ref_serialize(self._h, C.c_int(layout), None, C.c_longlong(0))
+        if n < 0:
+            raise ValueError("bad layout")
+        buf = np.zeros(n, dtype=np.uint8)
+        lib().ref_serialize(self._h, C.c_int(layout), _p(buf), C.c_longlong(n))
+        return buf.tobytes()
+
     def layout_trace(self, layout: int, rays, need_closest=True) -> np.ndarray:
         """CudaBVH::trace on the AOS_AOS (0) or Compact (4) buffers."""
         rays = _f32(rays).reshape(-1, 8)
@@ -129,6 +139,19 @@ class RefBVH:
         else:
             lib().ref_compact_trace_mt(self._h, _p(rays), C.c_int(len(rays)), C.c_int(1 if need_closest else 0), _p(res), C.c_int(nthreads))
         return res
+
+
+def deserialize(data: bytes):
+    """CudaBVH(InputStream&) of the reference on a byte stream -> (layout, nodes, woop, triIndex)."""
+    raw = np.frombuffer(data, dtype=np.uint8).copy()
+    sizes = np.zeros(4, dtype=np.int64)
+    if lib().ref_deserialize(_p(raw), C.c_longlong(len(raw)), _p(sizes), None, None, None):
+        raise ValueError("the reference's reader rejected the stream")
+    nodes = np.zeros(sizes[1] // 4, dtype=np.int32)
+    woop = np.zeros(sizes[2] // 4, dtype=np.int32)
+    idx = np.zeros(sizes[3] // 4, dtype=np.int32)
+    lib().ref_deserialize(_p(raw), C.c_longlong(len(raw)), _p(sizes), _p(nodes), _p(woop), _p(idx))
+    return int(sizes[0]), nodes, woop, idx
 
 
 def ray_box(lo, hi, ray):

@@ -28,7 +28,7 @@ void fail(const char* fmt, ...)
     abort();
 }
 
-static bool s_hasError = false;
+static bool s_hasError = false;       // (FW:: namespace scope below)
 void setError(const char* fmt, ...)
 {
     char buf[1024]; va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof(buf), fmt, ap); va_end(ap);
@@ -229,6 +229,49 @@ void ref_invert4(const float* in16, float* out16)
     for (int i = 0; i < 4; i++) for (int j = 0; j < 4; j++) m(i, j) = in16[i * 4 + j];
     Mat4f r = invert(m);
     for (int i = 0; i < 4; i++) for (int j = 0; j < 4; j++) out16[i * 4 + j] = r(i, j);
+}
+
+// FW::hashBuffer / the cache-name formula of Renderer::getCudaBVH (Renderer.cpp:173-178) evaluated by the reference's own Hash.cpp
+unsigned ref_hash_buffer(const void* p, int size) { return hashBuffer(p, size); }
+unsigned ref_cache_name_hash(unsigned sceneHash, int minLeaf, int maxLeaf, float splitAlpha, int layout, const char* ds)
+{
+    Platform platform("GPU");
+    platform.setLeafPreferences(minLeaf, maxLeaf);
+    BVH::BuildParams params;
+    params.splitAlpha = splitAlpha;
+    return hashBits(sceneHash, platform.computeHash(), params.computeHash(), (U32)layout, hash<String>(String(ds)));
+}
+unsigned ref_scene_hash(unsigned triVtxIndex, unsigned triNormal, unsigned triMaterialColor, unsigned triShadedColor, unsigned vtxPos)
+{
+    return hashBits(triVtxIndex, triNormal, triMaterialColor, triShadedColor, vtxPos);      // Scene.cpp:171-179
+}
+
+// CudaBVH::serialize (CudaBVH.cpp:116-125) through the reference's own OutputStream operators (io/Stream.cpp) into memory: the byte
+// stream Renderer::getCudaBVH writes to bvhcache/<hash>_<builder>.dat (Renderer.cpp:293-299).  Returns the stream length; copies
+// at most cap bytes.  (Buffer's "S64 size, then the bytes" is the shim's statement of Buffer.cpp:349-381: the real Buffer.cpp needs
+// the CUDA driver API.)
+long long ref_serialize(void* p, int layout, void* out, long long cap)
+{
+    RefHandle* h = (RefHandle*)p;
+    if (layout < 0 || layout >= BVHLayout_Max) return -1;
+    if (!h->byLayout[layout]) h->byLayout[layout] = new CudaBVH(*h->bvh, (BVHLayout)layout);
+    MemoryOutputStream ms;
+    h->byLayout[layout]->serialize(ms);
+    const Array<U8>& d = ms.getData();
+    if (out && cap > 0) memcpy(out, d.getPtr(), (size_t)(d.getSize() < cap ? d.getSize() : cap));
+    return d.getSize();
+}
+// CudaBVH(InputStream&) (CudaBVH.cpp:105-108): read a stream back with the reference's reader.  sizes = [layout, nodeBytes, woopBytes, idxBytes]
+int ref_deserialize(const void* bytes, long long n, long long* sizes, void* nodes, void* woop, void* idx)
+{
+    MemoryInputStream in(bytes, (int)n);
+    CudaBVH bvh(in);
+    if (hasError()) { s_hasError = false; return 1; }
+    sizes[0] = (long long)bvh.getLayout(); sizes[1] = bvh.getNodeBuffer().getSize(); sizes[2] = bvh.getTriWoopBuffer().getSize(); sizes[3] = bvh.getTriIndexBuffer().getSize();
+    if (nodes) memcpy(nodes, bvh.getNodeBuffer().getPtr(), (size_t)sizes[1]);
+    if (woop) memcpy(woop, bvh.getTriWoopBuffer().getPtr(), (size_t)sizes[2]);
+    if (idx) memcpy(idx, bvh.getTriIndexBuffer().getPtr(), (size_t)sizes[3]);
+    return 0;
 }
 
 } // extern "C"

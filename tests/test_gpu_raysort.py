@@ -40,12 +40,14 @@ def test_sort_matches_reference_order(gpu_host, orc):
     assert sorted(s2i.tolist()) == list(range(n))
     assert np.array_equal(i2s[s2i], np.arange(n))
     assert np.array_equal(after.view(np.uint32), before[s2i].view(np.uint32))
-    # same order as the restated reference sort on the truncated key; the full-key order differs only inside ties
-    order_t, k64 = orc.ray_morton_order(before, truncated=True)
-    assert np.array_equal(s2i, order_t)
-    assert (np.diff(k64[s2i].astype(np.float64)) >= 0).all()
-    order_f, _ = orc.ray_morton_order(before, truncated=False)
-    assert np.array_equal(k64[order_f], k64[order_t])                 # same multiset position by position (ties permuted only)
+    # exactly the order of the restated reference sort on the FULL 192-bit key (compareMortonKey, RayBuffer.cpp:88-99; rays with
+    # identical keys in their original order)
+    order_f, k64 = orc.ray_morton_order(before, truncated=False)
+    assert np.array_equal(s2i, order_f)
+    keys, _, _ = orc.ray_morton_keys(before)
+    ks = keys[s2i].astype(np.uint64)
+    big = [tuple(int(x) for x in row[::-1]) for row in ks[:: max(1, n // 4096)]]
+    assert big == sorted(big)                                          # hash[5] most significant
     # tracing the sorted batch returns the same result for every ray id
     tracer.traceBatch(sec)
     res_after = sec.results_host()
@@ -59,8 +61,8 @@ def test_sort_primary_and_edge_sizes(gpu_host, orc):
     ids_before = prim.getSlotToIDBuffer().cpu().numpy().copy()          # pixel ids
     prim.mortonSort()
     s2i = prim.getSlotToIDBuffer().cpu().numpy()
-    order_t, _ = orc.ray_morton_order(before, truncated=True)
-    assert np.array_equal(s2i, ids_before[order_t])                      # outSlotToID[new] = inSlotToID[old]
+    order_f, _ = orc.ray_morton_order(before, truncated=False)
+    assert np.array_equal(s2i, ids_before[order_f])                      # outSlotToID[new] = inSlotToID[old]
     assert np.array_equal(prim.getIDToSlotBuffer().cpu().numpy()[s2i], np.arange(len(s2i)))
     for n in (0, 1, 2, 33):
         rb = gpu_host.RayBuffer()
@@ -68,13 +70,13 @@ def test_sort_primary_and_edge_sizes(gpu_host, orc):
         rb.mortonSort()
         assert rb.getSize() == n
         if n:
-            o, _ = orc.ray_morton_order(before[:n], truncated=True)
+            o, _ = orc.ray_morton_order(before[:n], truncated=False)
             assert np.array_equal(rb.getSlotToIDBuffer().cpu().numpy(), o)
     # host pointers through the C ABI
     from ntrace_b200 import capi
     rays = before[:1000].copy(); a = np.zeros(1000, np.int32); b = np.arange(1000, dtype=np.int32)
     capi.ray_sort(rays, a, b, 1000)
-    o, _ = orc.ray_morton_order(before[:1000], truncated=True)
+    o, _ = orc.ray_morton_order(before[:1000], truncated=False)
     assert np.array_equal(b, o) and np.array_equal(rays.view(np.uint32), before[:1000][o].view(np.uint32))
 
 

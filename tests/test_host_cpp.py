@@ -183,3 +183,91 @@ def test_cpp_benchmark_driver_end_to_end(built, orc, tmp_path):
     a = np.fromfile(f"{prefix}.{k}.primary.results", dtype=np.int32).reshape(-1, 4)
     b = np.fromfile(f"{prefix}2.{k}.primary.results", dtype=np.int32).reshape(-1, 4)
     assert np.array_equal(a[:, :2], b[:, :2])
+
+
+@pytest.mark.gpu
+def test_named_cache_file_is_shared_by_both_hosts_and_pipelined_driver_runs(built, gpu_host, tmp_path):
+    """Renderer::getCudaBVH's cache: "<cachePath>/<hash>_<builder>.dat" (Renderer.cpp:173-178).  The C++ driver writes it, the Python
+    Renderer computes the same name for the same scene, imports the file instead of building, and traces the same results; the C++
+    driver run a second time (pipelined loop) imports it too."""
+    import re
+    from ntrace_b200 import host
+    verts, tris = scenes.room(12_000, seed=21, wall_frac=0.3)
+    mesh = str(tmp_path / "scene.ntmesh")
+    mesh_io.save_ntmesh(mesh, verts, tris)
+    conf = tmp_path / "config.conf"
+    conf.write_text(CONFIG % dict(stats=str(tmp_path / "stats.log"), scene=mesh, camera=camera.SIGNATURES["conference"]))
+    cache_dir = str(tmp_path / "bvhcache")
+    os.makedirs(cache_dir)
+    args = [os.path.join(built, "ntrace_bench"), str(conf), f"-DBenchmark.cachePath={cache_dir}", "-DRenderer.cacheDataStructure=true"]
+    r = subprocess.run(args, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    files = os.listdir(cache_dir)
+    assert len(files) == 1 and re.fullmatch(r"[0-9a-f]{8}_HLBVH\.dat", files[0]), files
+    scene = host.Scene(verts, tris)
+    name = host.cache_file_name(scene, "HLBVH", host.BVHLayout_Compact, cache_dir)
+    assert os.path.basename(name) == files[0]                      # one naming rule, two hosts
+    # the Python Renderer imports the C++ host's file (no build: the handle has a host copy and no GPU build time) ...
+    rnd = host.Renderer(host.BuildSettings(builder="HLBVH", cachePath=cache_dir))
+    rnd.setScene(scene)
+    bvh = rnd.getCudaBVH()
+    assert not bvh.resident and bvh.gpu_seconds == 0.0 and bvh.nodes is not None
+    # ... and traces what a freshly built tree of the same parameters traces
+    cam = camera.named_camera("conference")
+    rnd.setParams(host.RendererParams(rayType=host.RayType_Primary))
+    rnd.beginFrame(cam, 320, 240)
+    assert rnd.nextBatch()
+    rnd.traceBatch()
+    cached = rnd.m_batchRays.results_host().copy()
+    fresh = host.Renderer(host.BuildSettings(builder="HLBVH"))
+    fresh.setScene(scene)
+    fresh.setParams(host.RendererParams(rayType=host.RayType_Primary))
+    fresh.beginFrame(cam, 320, 240)
+    assert fresh.nextBatch()
+    fresh.traceBatch()
+    assert np.array_equal(cached, fresh.m_batchRays.results_host())
+    # second C++ run: imports the cache, pipelined batch loop
+    mtime = os.path.getmtime(os.path.join(cache_dir, files[0]))
+    r2 = subprocess.run(args + ["-DBenchmark.pipelined=true"], capture_output=True, text=True, timeout=300)
+    assert r2.returncode == 0, r2.stderr
+    assert os.listdir(cache_dir) == files and os.path.getmtime(os.path.join(cache_dir, files[0])) == mtime
+    t1 = [l for l in r.stdout.splitlines() if l.startswith("b200_persistent_speculative_while_while ")][-1].split()[1:]
+    t2 = [l for l in r2.stdout.splitlines() if l.startswith("b200_persistent_speculative_while_while ")][-1].split()[1:]
+    assert len(t1) == len(t2) == 3 and all(float(x) > 50.0 for x in t2)
+
+
+@pytest.mark.gpu
+def test_cpp_driver_on_two_gpus_matches_one_gpu(built, tmp_path):
+    """Renderer.numGpus in the C++ host: two processes, NCCL unique id through a file, rank 0 builds, nt_bvh_broadcast replicates, the
+    secondary batches are dealt round-robin.  The frame's ray count is the single-GPU run's; throughput is reported by rank 0 only."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (run with gpurun --gpus 2)")
+    verts, tris = scenes.room(30_000, seed=13, wall_frac=0.3)
+    mesh = str(tmp_path / "scene.ntmesh")
+    mesh_io.save_ntmesh(mesh, verts, tris)
+    conf = tmp_path / "config.conf"
+    conf.write_text(CONFIG % dict(stats=str(tmp_path / "stats1.log"), scene=mesh, camera=camera.SIGNATURES["conference"]))
+    exe = os.path.join(built, "ntrace_bench")
+    r1 = subprocess.run([exe, str(conf), "-DRenderer.samples=16", "-DBenchmark.pipelined=true"], capture_output=True, text=True, timeout=300)
+    assert r1.returncode == 0, r1.stderr
+    comm = str(tmp_path / "nccl_id")
+    procs = []
+    for rank in range(2):
+        env = dict(os.environ, RANK=str(rank), WORLD_SIZE="2", LOCAL_RANK=str(rank))
+        procs.append(subprocess.Popen([exe, str(conf), "-DRenderer.samples=16", "-DBenchmark.pipelined=true", f"-DBenchmark.commFile={comm}",
+                                       f"-DApp.stats={tmp_path / 'stats2.log'}"], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
+    outs = [p.communicate(timeout=300) for p in procs]
+    for p, (o, e) in zip(procs, outs):
+        assert p.returncode == 0, o + e
+    assert "2 GPUs: BVH broadcast" in outs[0][0] and "[Mrays/s]" in outs[0][0] and "[Mrays/s]" not in outs[1][0]
+
+    def records(path):
+        s = open(path).read().split()
+        return [float(s[i + 1]) for i, x in enumerate(s) if x == "#SUM_RENDER_KRAYS"], [float(s[i + 1]) for i, x in enumerate(s) if x == "#SUM_RENDER_TIME"]
+    k1, t1 = records(tmp_path / "stats1.log")
+    k2, t2 = records(tmp_path / "stats2.log")
+    assert len(k1) == len(k2) == 3
+    # same frame, same ray accounting: rays = krays * time must agree between the runs for every ray type
+    for a, b, c, d in zip(k1, t1, k2, t2):
+        assert abs(a * b - c * d) <= 1e-3 * a * b

@@ -196,3 +196,82 @@ def test_gpu_kernel_reproduces_frozen_reference_trace(orc, gpu_host, name, cfg):
     tracer.traceBatch(rb)
     any_got = rb.results_host()[:, 0] >= 0
     assert np.array_equal(any_got, np.load(os.path.join(HERE, f"ref_{name}.npz"))[f"{cfg}.flat_any"][:, 0] >= 0)
+
+
+# ---- bvhcache: the stream format and the file naming, pinned against the reference's own serializer / Hash.cpp -------------------------
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def test_bvhcache_stream_written_by_the_reference_is_read_and_rewritten_byte_for_byte():
+    """tests/golden/ref_map_compact.dat was written by the reference's CudaBVH::serialize (scripts/make_ref_cache_golden.py).  The Python
+    reader must recover the three buffers and write the identical stream back; so must the C++ host's stream constructor."""
+    import io
+    import json
+    import subprocess
+    from ntrace_b200 import host
+    data = open(os.path.join(GOLDEN_DIR, "ref_map_compact.dat"), "rb").read()
+    kat = json.load(open(os.path.join(GOLDEN_DIR, "ref_cache_golden.json")))
+    import hashlib
+    assert hashlib.sha256(data).hexdigest() == kat["dat_sha256"]
+    b = host.CudaBVH.deserialize(io.BytesIO(data))
+    assert b.layout == 4 and b.nodes.nbytes % 64 == 0 and b.woop.nbytes == 4 * b.tri_index.nbytes
+    assert 4 + 3 * 8 + b.nodes.nbytes + b.woop.nbytes + b.tri_index.nbytes == len(data)
+    # it is the Map.obj SplitBVH: every one of the 488 triangles is referenced (triIndex holds [id, 0, 0] per triangle, 0 per terminator)
+    assert set(b.tri_index.tolist()) == set(range(488))
+    out = io.BytesIO()
+    b.serialize(out)
+    assert out.getvalue() == data
+    exe = os.path.join(os.path.dirname(GOLDEN_DIR), "..", "ntrace_b200", "host_cpp", "host_selftest")
+    if os.path.exists(exe):
+        import tempfile
+        with tempfile.TemporaryDirectory() as tmp:
+            dst = os.path.join(tmp, "out.dat")
+            r = subprocess.run([exe, "--cache", os.path.join(GOLDEN_DIR, "ref_map_compact.dat"), dst], capture_output=True, text=True)
+            assert r.returncode == 0, r.stderr
+            assert json.loads(r.stdout) == {"layout": 4, "nodeBytes": b.nodes.nbytes, "woopBytes": b.woop.nbytes, "idxBytes": b.tri_index.nbytes}
+            assert open(dst, "rb").read() == data
+
+
+def test_cache_file_name_hashes_match_the_reference_known_answers():
+    """FW::hashBuffer (the library's nt_hash_buffer), hashBits and the cache-name formula against values computed by the reference's Hash.cpp."""
+    import json
+    import subprocess
+    from ntrace_b200 import capi, host
+    kat = json.load(open(os.path.join(GOLDEN_DIR, "ref_cache_golden.json")))
+    data = open(os.path.join(GOLDEN_DIR, "ref_map_compact.dat"), "rb").read()
+    for n, v in kat["hash_buffer"].items():
+        assert capi.hash_buffer(data[: int(n)]) == v, n
+    for n, v in kat["hash_buffer_unaligned"].items():
+        assert capi.hash_buffer(data[1: 1 + int(n)]) == v, n
+    assert host.hash_bits(*kat["scene_hash"]["args"]) == kat["scene_hash"]["value"]
+    for row in kat["cache_name_hash"]:
+        platform = host.hash_bits(capi.hash_buffer(b"GPU"), host._f2b(1.0), host._f2b(1.0), host.hash_bits(1, 1, row["minLeaf"], row["maxLeaf"]))
+        params = host.hash_bits(host._f2b(row["splitAlpha"]))
+        assert host.hash_bits(row["sceneHash"], platform, params, row["layout"], capi.hash_buffer(row["ds"].encode())) == row["value"]
+    exe = os.path.join(os.path.dirname(GOLDEN_DIR), "..", "ntrace_b200", "host_cpp", "host_selftest")
+    if os.path.exists(exe):
+        r = subprocess.run([exe, "--hash", os.path.join(GOLDEN_DIR, "ref_map_compact.dat")], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        got = json.loads(r.stdout)
+        assert got["hashBuffer"] == kat["hash_buffer"][str(len(data))]
+        assert got == {"hashBuffer": got["hashBuffer"], "hashBits1": host.hash_bits(12345), "hashBits3": host.hash_bits(1, 2, 3),
+                       "hashBits4": host.hash_bits(1, 2, 3, 4), "hashBits6": host.hash_bits(0xdeadbeef, 7, 0x80000000, 4, 5, 6)}
+
+
+def test_live_reference_serializer_round_trip(ref):
+    """With /root/reference present: a stream freshly written by the reference is read by the Python host, and the Python host's
+    stream is accepted by the reference's own reader (CudaBVH(InputStream&), CudaBVH.cpp:105-108)."""
+    import io
+    from ntrace_b200 import host, scenes
+    verts, tris = scenes.room(3000, seed=5)
+    r = ref.RefBVH(verts, tris, split=False, min_leaf=1, max_leaf=4)
+    for layout in (4, 5, 0):
+        data = r.serialize(layout)
+        n, w, i = r.layout(layout)
+        b = host.CudaBVH.deserialize(io.BytesIO(data))
+        assert b.layout == layout and np.array_equal(b.nodes, n) and np.array_equal(b.woop, w) and np.array_equal(b.tri_index, i)
+        out = io.BytesIO()
+        b.serialize(out)
+        assert out.getvalue() == data
+        L, nn, ww, ii = ref.deserialize(out.getvalue())
+        assert L == layout and np.array_equal(nn, n) and np.array_equal(ww, w) and np.array_equal(ii, i)
