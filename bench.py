@@ -272,6 +272,7 @@ def run_b200(args):
     if world > 1:
         bcast_ms = multigpu.broadcast_bvh(src=0) * 1e3
     (node_b, woop_b, idx_b), bvh_layout = capi.bvh_sizes()
+    timed_tree = capi.bvh_sah()                       # SAH of the tree that is timed (nt_bvh_sah: the reference's BVH::Stats formula, on the device)
     bvh = host.CudaBVH(layout=bvh_layout)
     bvh.resident = True
     tracer = host.CudaBVHTracer()
@@ -522,7 +523,9 @@ def run_b200(args):
             "detail": {"primary_mrays": counted["primary"] / type_sec["primary"] * 1e-6, "ao_mrays": counted["AO"] / type_sec["AO"] * 1e-6,
                        "diffuse_mrays": counted["diffuse"] / type_sec["diffuse"] * 1e-6,
                        "build_ms": float(np.mean(build_s[1:]) * 1e3), "build_mtris": len(tris) / float(np.mean(build_s[1:])) * 1e-6,
-                       "bvh_broadcast_ms": bcast_ms, "primary_hits": int(hits),
+                       "timed_tree": timed_tree,
+                       "bvh_broadcast_ms": bcast_ms, "bvh_broadcast_via": "nt_bvh_broadcast (C ABI, NCCL bound by dlopen)" if multigpu._comm_ready else ("torch.distributed" if world > 1 else None),
+                       "primary_hits": int(hits),
                        "one_stream_value": counted_step * args.steps / sec_serial * 1e-6,
                        "overlap_gain": sec_serial / sec},
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": int(ray_bytes), "d2h_bytes_per_step": int(ray_bytes // 2),
@@ -557,6 +560,8 @@ def run_b200(args):
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.barrier()
+        if multigpu._comm_ready:
+            capi.comm_destroy()
         dist.destroy_process_group()
     if out is not None and not (out["parity"]["ok"] and sharded_ok and gathered_ok is not False):
         print("bench.py: PARITY FAILURE — the line above must not be used", file=sys.stderr)

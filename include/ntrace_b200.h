@@ -145,6 +145,11 @@ int nt_bvh_convert(int layout);
  * outWideNodes may be NULL to query *outWideBytes; *outMaxDepth (optional) = depth of the Wide4 tree. */
 int nt_bvh_wide4_convert_host(int layout, const void* nodes, size_t nodeBytes, size_t woopBytes,
                               void* outWideNodes, size_t outCapacityBytes, size_t* outWideBytes, int* outMaxDepth);
+/* SAH cost of the resident BVH as the reference reports it in BVH::Stats (BVH.cpp:67-70: BVHNode::computeSubtreeProbabilities,
+ * BVHNode.cpp:79-94, Platform costs 1 / 1: an inner node costs 2, a leaf its triangle count, each weighted by area / root area), computed
+ * on the device in one parallel pass (the reference's GPU twin, calcSAH, is a single-thread recursion with inner cost 1,
+ * emitTreeKernel.cu:1361-1400).  Also returns the inner-node, leaf and triangle-reference counts (any of the three may be NULL). */
+int nt_bvh_sah(double* outSah, int64_t* outNumInner, int64_t* outNumLeaves, int64_t* outNumTris);
 /* FW::hashBuffer (src/framework/base/Hash.cpp:33-75): the hash Renderer::getCudaBVH builds its cache file name from
  * ("bvhcache/<hash>_<builder>.dat", Renderer.cpp:173-178).  Pure host code (no device needed), so that both hosts above this ABI
  * name cache files with one implementation, pinned against the reference's own Hash.cpp (tests/test_reference_pin.py). */

@@ -28,7 +28,7 @@ EXPORTS = [
     "nt_event_record", "nt_event_elapsed", "nt_set_deferred", "nt_synchronize",
     "nt_set_kernel", "nt_desired_layout", "nt_kernel_config",
     "nt_bvh_upload", "nt_bvh_alloc", "nt_bvh_build", "nt_bvh_set_collapse", "nt_bvh_set_build_layout", "nt_bvh_convert", "nt_bvh_sizes", "nt_bvh_download",
-    "nt_bvh_device_ptrs", "nt_bvh_build_debug", "nt_bvh_wide4_convert_host", "nt_bvh_generation", "nt_hash_buffer", "nt_comm_unique_id", "nt_comm_init", "nt_comm_destroy", "nt_comm_allreduce", "nt_bvh_broadcast",
+    "nt_bvh_device_ptrs", "nt_bvh_build_debug", "nt_bvh_wide4_convert_host", "nt_bvh_generation", "nt_bvh_sah", "nt_hash_buffer", "nt_comm_unique_id", "nt_comm_init", "nt_comm_destroy", "nt_comm_allreduce", "nt_bvh_broadcast",
     "nt_trace_batch", "nt_trace_batch_async", "nt_trace_wait", "nt_raygen_primary", "nt_raygen_ao", "nt_raygen_shadow", "nt_ray_sort", "nt_count_hits", "nt_tri_normals",
 ]
 
@@ -171,6 +171,14 @@ def bvh_convert(layout: int):
 
 def bvh_set_collapse(mode: int, max_leaf: int = 0):
     _check(lib().nt_bvh_set_collapse(C.c_int(mode), C.c_int(max_leaf)))
+
+
+def bvh_sah() -> dict:
+    """SAH (BVHNode.cpp:79-94 formula) and node / leaf / triangle counts of the resident BVH, computed on the device."""
+    sah = C.c_double(0.0)
+    a, b, c = C.c_int64(0), C.c_int64(0), C.c_int64(0)
+    _check(lib().nt_bvh_sah(C.byref(sah), C.byref(a), C.byref(b), C.byref(c)))
+    return dict(sah=float(sah.value), num_inner=int(a.value), num_leaf=int(b.value), num_tris=int(c.value))
 
 
 def hash_buffer(data) -> int:

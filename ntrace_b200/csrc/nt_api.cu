@@ -858,6 +858,27 @@ int nt_hash_buffer(const void* ptr, size_t size, uint32_t* outHash)
     return 0;
 }
 
+int nt_bvh_sah(double* outSah, int64_t* outNumInner, int64_t* outNumLeaves, int64_t* outNumTris)
+{
+    std::lock_guard<std::mutex> lock(g_mutex);
+    if (require_init()) return 1;
+    if (!outSah) { set_error("ntrace_b200: null output"); return 1; }
+    if (!g.haveBVH) { set_error("CudaBVHTracer: No BVH!"); return 1; }
+    if (ensure_traversal_form()) return 1;                 // AOS / SOA uploads are measured through their Compact form (same tree)
+    struct { double terms, rootArea; unsigned long long leaves, tris; } h;
+    void* d = g.counters.as<char>() + 192;
+    NT_CUDA(cudaMemsetAsync(d, 0, 32, g.stream));
+    NT_CUDA(launch_sah(g.nodes.as<float4>(), g.nodeBytes / 64, g.woop.as<float4>(), g.woopBytes / 16, d, g.stream));
+    g.launches += 1;
+    NT_CUDA(cudaMemcpyAsync(&h, d, 32, cudaMemcpyDeviceToHost, g.stream));
+    NT_CUDA(cudaStreamSynchronize(g.stream));
+    *outSah = 2.0 + (h.rootArea > 0.0 ? h.terms / h.rootArea : 0.0);       // the root's own 2 * Cn at P = 1
+    if (outNumInner) *outNumInner = (int64_t)(g.nodeBytes / 64);
+    if (outNumLeaves) *outNumLeaves = (int64_t)h.leaves;
+    if (outNumTris) *outNumTris = (int64_t)h.tris;
+    return 0;
+}
+
 int nt_bvh_generation(uint64_t* outGeneration)
 {
     std::lock_guard<std::mutex> lock(g_mutex);

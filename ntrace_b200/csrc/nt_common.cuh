@@ -122,6 +122,7 @@ cudaError_t build_bvh_device(const float* dVerts, int numVerts, const int* dTris
 
 // ---- basic CudaBVH layouts (nt_layout.cu): AOS/SOA buffers on the device -> Compact / Compact2 form in `out`
 cudaError_t rescale_compact_links(int4* dNodes, size_t numNodes, int mulNum, int mulDen, cudaStream_t stream);
+cudaError_t launch_sah(const float4* dNodes, size_t numNodes, const float4* dWoop, size_t woopRows, void* out4, cudaStream_t stream);
 cudaError_t convert_basic_layout(int layout, const void* dNodes, size_t nodeBytes, const void* dWoop, size_t woopBytes,
                                  const int* dTriIndex, size_t idxBytes, int targetLayout, BuildOutput& out, DevBuf& scratch,
                                  cudaStream_t stream, int* outLaunches, std::string* err);

@@ -129,7 +129,60 @@ __global__ void rescale_links_kernel(int4* nodes, size_t numNodes, int num, int 
     nodes[i * 4 + 3] = link;
 }
 
+// SAH of a flat Compact / Compact2 tree with the formula the reference reports (BVHNode::computeSubtreeProbabilities, BVHNode.cpp:79-94
+// through BVH.cpp:67-70; Platform costs Cn = Ct = 1): sum over nodes of P(n) * (Cn * #children + Ct * #triangles) with
+// P(child) = P(parent) * A(child) / A(parent), P(root) = 1.  The product telescopes to A(n) / A(root), so the sum is parallel: one thread
+// per inner node adds, for each of its two child boxes, 2 * A (inner child) or #triangles * A (leaf child, triangles counted up to the
+// terminator); the root contributes 2.  Replaces the reference's single-thread calcSAH kernel (emitTreeKernel.cu:1361-1400), which uses
+// inner cost 1 (do not mix the two).  acc = {sum of child terms, A(root), leaves, triangles} in double / u64.
+__global__ void __launch_bounds__(256) sah_kernel(const float4* __restrict__ nodes, size_t numNodes, const float4* __restrict__ woop, size_t woopRows,
+                                                   double* __restrict__ acc, unsigned long long* __restrict__ counts)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    double sum = 0.0;
+    unsigned leaves = 0, tris = 0;
+    if (i < numNodes) {
+        const float4 n0 = __ldg(nodes + i * 4), n1 = __ldg(nodes + i * 4 + 1), nz = __ldg(nodes + i * 4 + 2), cn = __ldg(nodes + i * 4 + 3);
+        const float dx[2] = {n0.y - n0.x, n1.y - n1.x}, dy[2] = {n0.w - n0.z, n1.w - n1.z}, dz[2] = {nz.y - nz.x, nz.w - nz.z};
+        const int link[2] = {__float_as_int(cn.x), __float_as_int(cn.y)};
+        for (int c = 0; c < 2; c++) {
+            const double area = 2.0 * ((double)dx[c] * dy[c] + (double)dy[c] * dz[c] + (double)dz[c] * dx[c]);     // AABB::area (Util.hpp:45)
+            if (link[c] >= 0) sum += 2.0 * area;
+            else {
+                unsigned n = 0;
+                for (size_t a = (size_t)(unsigned)~link[c]; a < woopRows && __float_as_uint(__ldg(woop + a).x) != 0x80000000u; a += 3) n++;
+                sum += (double)n * area;
+                leaves++; tris += n;
+            }
+        }
+        if (i == 0) {
+            const float lo[3] = {fminf(n0.x, n1.x), fminf(n0.z, n1.z), fminf(nz.x, nz.z)}, hi[3] = {fmaxf(n0.y, n1.y), fmaxf(n0.w, n1.w), fmaxf(nz.y, nz.w)};
+            const double ex = hi[0] - lo[0], ey = hi[1] - lo[1], ez = hi[2] - lo[2];
+            acc[1] = 2.0 * (ex * ey + ey * ez + ez * ex);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        leaves += __shfl_xor_sync(0xffffffffu, leaves, o);
+        tris += __shfl_xor_sync(0xffffffffu, tris, o);
+    }
+    if ((threadIdx.x & 31) == 0 && (sum != 0.0 || leaves)) {
+        atomicAdd(acc, sum);
+        atomicAdd(counts, (unsigned long long)leaves);
+        atomicAdd(counts + 1, (unsigned long long)tris);
+    }
+}
+
 } // namespace
+
+// out4 (device, 32 bytes, zeroed by the caller): {double childTerms, double rootArea, u64 leaves, u64 triangles}
+cudaError_t launch_sah(const float4* dNodes, size_t numNodes, const float4* dWoop, size_t woopRows, void* out4, cudaStream_t stream)
+{
+    if (numNodes == 0) return cudaErrorInvalidValue;
+    sah_kernel<<<(unsigned)((numNodes + 255) / 256), 256, 0, stream>>>(dNodes, numNodes, dWoop, woopRows, (double*)out4, (unsigned long long*)out4 + 2);
+    return cudaGetLastError();
+}
 
 cudaError_t rescale_compact_links(int4* dNodes, size_t numNodes, int mulNum, int mulDen, cudaStream_t stream)
 {

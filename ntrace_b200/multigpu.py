@@ -47,11 +47,47 @@ def broadcast_meta(meta, src: int):
     return [int(x) for x in meta.tolist()]
 
 
-def broadcast_bvh(src: int = 0) -> float:
-    """Replicate the BVH resident on rank `src` to every rank (NCCL over NVLink).  Returns seconds (device time
-    of the three broadcasts on this rank)."""
+_comm_ready = False
+
+
+def init_comm() -> bool:
+    """Create the library's own NCCL communicator (nt_comm_init, C ABI) for the ranks of the default torch.distributed group: rank 0
+    asks the library for the unique id, torch.distributed only carries those 128 bytes to the other ranks.  False when NCCL cannot
+    be bound (the callers then fall back to torch's collectives)."""
+    global _comm_ready
+    if _comm_ready:
+        return True
     import torch
     import torch.distributed as dist
+    rank, world = dist.get_rank(), dist.get_world_size()
+    ok = torch.ones(1, dtype=torch.int32, device="cuda")
+    uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        try:
+            uid.copy_(torch.frombuffer(bytearray(capi.comm_unique_id()), dtype=torch.uint8))
+        except capi.NtError:
+            ok.zero_()
+    dist.broadcast(ok, 0)
+    if int(ok.item()) == 0:
+        return False
+    dist.broadcast(uid, 0)
+    try:
+        capi.comm_init(world, rank, bytes(uid.cpu().numpy().tobytes()))
+    except capi.NtError:
+        ok.zero_()
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    _comm_ready = int(ok.item()) == 1
+    return _comm_ready
+
+
+def broadcast_bvh(src: int = 0, use_capi: bool = True) -> float:
+    """Replicate the BVH resident on rank `src` to every rank (NCCL over NVLink).  Returns seconds (device time
+    of the three broadcasts on this rank).  With use_capi the library's own nt_bvh_broadcast does it (the communicator of
+    init_comm()); otherwise, or when NCCL could not be bound inside the library, torch.distributed broadcasts the three buffers."""
+    import torch
+    import torch.distributed as dist
+    if use_capi and init_comm():
+        return capi.bvh_broadcast(src)
     rank = dist.get_rank()
     meta = torch.zeros(4, dtype=torch.int64, device="cuda")
     if rank == src:

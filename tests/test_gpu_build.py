@@ -348,3 +348,27 @@ def test_builder_emits_compact2_on_request(gpu_host, orc):
         assert np.array_equal(np.where(n4[:, 12:14] >= 0, n4[:, 12:14] // 16, n4[:, 12:14]), n5[:, 12:14])
     with pytest.raises(capi.NtError, match="Compact"):
         capi.bvh_set_build_layout(0)
+
+
+@pytest.mark.parametrize("bits,collapse", [(10, 0), (4, 0), (2, 1)])
+def test_device_sah_metric_matches_the_reference_formula(gpu_host, orc, bits, collapse):
+    """nt_bvh_sah (one parallel pass on the device) against the restated BVHNode::computeSubtreeProbabilities walk of the same tree."""
+    verts, tris = scenes.room(40_000, seed=17, wall_frac=0.3)
+    lo, hi = scenes.bbox(verts)
+    capi.bvh_set_collapse(collapse, 8)
+    try:
+        capi.bvh_build(capi.BUILDER_HLBVH, np.ascontiguousarray(verts, np.float32), np.ascontiguousarray(tris, np.int32), lo, hi, bits, 8, 0.001)
+    finally:
+        capi.bvh_set_collapse(0, 0)
+    got = capi.bvh_sah()
+    nodes, woop, idx, _ = capi.bvh_download()
+    ref = orc.compact_sah(nodes, woop)
+    assert got["num_inner"] == ref["num_inner"] and got["num_leaf"] == ref["num_leaf"] and got["num_tris"] == ref["num_tris"] == len(tris)
+    assert abs(got["sah"] - ref["sah"]) <= 2e-4 * ref["sah"], (got["sah"], ref["sah"])     # fp32 probability products there, fp64 areas here
+    # an uploaded CPU-built SplitBVH too (different leaf shape: one triangle per leaf, duplicated references)
+    v2, t2 = scenes.room(9_000, seed=3, wall_frac=0.3)
+    cpu = orc.CpuBVH(v2, t2, orc.BUILDER_SPLIT, 1, 1)
+    n2, w2, i2 = cpu.compact()
+    capi.bvh_upload(capi.LAYOUT_COMPACT, n2, w2, i2)
+    got2, ref2 = capi.bvh_sah(), orc.compact_sah(n2, w2)
+    assert got2["num_leaf"] == ref2["num_leaf"] and abs(got2["sah"] - ref2["sah"]) <= 2e-4 * ref2["sah"]
