@@ -170,7 +170,7 @@ def bytes_per_ray(cnt, hit_frac):
 
 
 # --------------------------------------------------------------------------------------------------
-DEFAULT_KERNEL = "b200_persistent_speculative_while_while"
+DEFAULT_KERNEL = "b200_auto"
 
 
 def lib_sha16():

@@ -205,7 +205,7 @@ int ensure_traversal_form()
 // derive the Wide4 node array from the resident Compact / Compact2 nodes (host conversion: nt_wide.cu); caller holds the mutex
 int ensure_wide_form()
 {
-    if ((g.kernel != Kernel_Wide4Persistent && g.kernel != Kernel_Wide4Mr) || g.wideValid) return 0;
+    if ((g.kernel != Kernel_Wide4Persistent && g.kernel != Kernel_Wide4Mr && g.kernel != Kernel_Auto) || g.wideValid) return 0;
     std::vector<int32_t> h(g.nodeBytes / 4);
     NT_CUDA(cudaMemcpyAsync(h.data(), g.nodes.p, g.nodeBytes, cudaMemcpyDeviceToHost, g.stream));
     NT_CUDA(cudaStreamSynchronize(g.stream));
@@ -543,6 +543,10 @@ int nt_set_kernel(const char* name)
         {"b200_mr", Kernel_BinaryMr, Layout_Compact, false},
         {"b200_mr_fastmath", Kernel_BinaryMr, Layout_Compact, true},
         {"b200_mr_compact2", Kernel_BinaryMr, Layout_Compact2, false},
+        // per batch the faster of the two on a B200: any-hit batches through the binary kernel (the reference's visiting order, so the reported
+        // any-hit triangle is the reference's too), closest-hit batches through Wide4 (their result does not depend on the visiting order)
+        {"b200_auto", Kernel_Auto, Layout_Compact, false},
+        {"b200_auto_compact2", Kernel_Auto, Layout_Compact2, false},
         {"b200_wide4_mr", Kernel_Wide4Mr, Layout_Compact, false},
         {"b200_wide4_mr_fastmath", Kernel_Wide4Mr, Layout_Compact, true},
         {"b200_wide4_mr_compact2", Kernel_Wide4Mr, Layout_Compact2, false},
@@ -961,7 +965,8 @@ int nt_trace_batch(const float* rays, int32_t* results, int numRays, int needClo
     const bool raysOnHost = (raysDev == nullptr), resOnHost = (resDev == nullptr);
 
     TraceLaunch a;
-    a.kernel = g.kernel; a.fast = g.fastMath ? 1 : 0; a.layout = g.basic ? (int)Layout_Compact : g.kernelLayout; a.anyHit = needClosestHit ? 0 : 1;
+    a.kernel = (g.kernel == Kernel_Auto) ? (needClosestHit ? (int)Kernel_Wide4Persistent : (int)Kernel_PersistentSpeculative) : g.kernel;
+    a.fast = g.fastMath ? 1 : 0; a.layout = g.basic ? (int)Layout_Compact : g.kernelLayout; a.anyHit = needClosestHit ? 0 : 1;
     a.nodes = g.nodes.as<float4>(); a.woop = g.woop.as<float4>(); a.triIndices = g.triIndex.as<int>();
     a.wideNodes = g.wideNodes.as<float4>();
     a.numSMs = g.numSMs; a.stream = g.stream; a.errorFlag = g.errDev;
@@ -1099,7 +1104,8 @@ int nt_trace_batch_async(const float* rays, int32_t* results, int numRays, int n
         else { NT_CUDA(s.results.reserve((size_t)numRays * 16)); dRes = s.results.as<int4>(); s.copyOut = true; }
     }
     TraceLaunch a;
-    a.kernel = g.kernel; a.fast = g.fastMath ? 1 : 0; a.layout = g.basic ? (int)Layout_Compact : g.kernelLayout; a.anyHit = needClosestHit ? 0 : 1;
+    a.kernel = (g.kernel == Kernel_Auto) ? (needClosestHit ? (int)Kernel_Wide4Persistent : (int)Kernel_PersistentSpeculative) : g.kernel;
+    a.fast = g.fastMath ? 1 : 0; a.layout = g.basic ? (int)Layout_Compact : g.kernelLayout; a.anyHit = needClosestHit ? 0 : 1;
     a.nodes = g.nodes.as<float4>(); a.woop = g.woop.as<float4>(); a.triIndices = g.triIndex.as<int>();
     a.wideNodes = g.wideNodes.as<float4>();
     a.numSMs = g.numSMs; a.stream = g.stream; a.errorFlag = g.errDev;

@@ -34,6 +34,7 @@ enum TraceKernelId : int {
     Kernel_Wide4Persistent = 2,         // persistent speculative while-while over the derived 4-wide quantised node array (nt_wide.cu)
     Kernel_BinaryMr = 3,                // two rays per lane, phase-scheduled (nt_wide.cu "mr"), binary Compact / Compact2 nodes
     Kernel_Wide4Mr = 4,                 // the same over the Wide4 node array
+    Kernel_Auto = 5,                    // per batch: any-hit -> Kernel_PersistentSpeculative, closest-hit -> Kernel_Wide4Persistent (API level only)
     Kernel_Count
 };
 

@@ -329,7 +329,7 @@ KernelConfig trace_kernel_config(int kernel, int layout)
     c.bvhLayout = layout;
     c.blockWidth = 32;
     c.blockHeight = kBlock / 32;
-    c.usePersistentThreads = (kernel == Kernel_PlainSpeculative) ? 0 : 1;
+    c.usePersistentThreads = (kernel == Kernel_PlainSpeculative) ? 0 : 1;        // Kernel_Auto: both of its kernels are persistent
     return c;
 }
 

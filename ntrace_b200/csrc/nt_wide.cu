@@ -186,7 +186,7 @@ __device__ __forceinline__ void cas(int& a, int& b) { const int lo = min(a, b), 
 
 template <int BLOCK, int SMEM_N, bool FAST, bool WIDE_RAYS>
 __global__ void __launch_bounds__(BLOCK)
-trace_wide4_kernel(int numRays, int anyHit, int fetchThreshold, unsigned oneBits,
+trace_wide4_kernel(int numRays, int anyHit, int fetchThreshold, int nodeExit, unsigned oneBits,
                    const float4* __restrict__ rays, int4* __restrict__ results,
                    const float4* __restrict__ wnodes, const float4* __restrict__ woop,
                    const int* __restrict__ triIndices, int* __restrict__ warpCounter, int* __restrict__ errorFlag)
@@ -301,7 +301,13 @@ trace_wide4_kernel(int numRays, int anyHit, int fetchThreshold, unsigned oneBits
                     leafAddr = nodeAddr;
                     NT_POP(nodeAddr);
                 }
-                if (!__any_sync(__activemask(), leafAddr >= 0)) break;
+                // all lanes hold a leaf => process them.  Also when fewer than nodeExit lanes are left in this loop: a Wide4 node step costs
+                // ~150 instructions, too many to issue for a handful of lanes; the ones still searching sit out the leaf phase and come back
+                // (measured on the bench frame, profiles/r2_summary.md: nodeExit 8 = +10 % AO, +6 % diffuse over 0)
+                {
+                    const unsigned am = __activemask();
+                    if (!__any_sync(am, leafAddr >= 0) || __popc(am) < nodeExit) break;
+                }
             }
 
             // postponed leaves: the reference's Woop test (Util.cpp:99-127), identical to nt_trace.cu
@@ -658,11 +664,12 @@ cudaError_t launch_mr_stack(const TraceLaunch& a, int* launches)
     }
 }
 
-struct WideTuning { int smemStack; int carveout; int fetchThreshold; };
+struct WideTuning { int smemStack; int carveout; int fetchThreshold; int nodeExit; };
 WideTuning wide_tuning()
 {
     static WideTuning t = [] {
-        WideTuning r{8, 20, 20};
+        WideTuning r{8, 20, 20, 8};
+        if (const char* e = getenv("NT_WIDE_NODE_EXIT")) r.nodeExit = atoi(e);
         if (const char* e = getenv("NT_WIDE_SMEM")) r.smemStack = atoi(e);
         if (const char* e = getenv("NT_WIDE_CARVEOUT")) r.carveout = atoi(e);
         if (const char* e = getenv("NT_WIDE_FETCH")) r.fetchThreshold = atoi(e);
@@ -686,7 +693,7 @@ cudaError_t launch_wide_variant(const TraceLaunch& a, int* launches)
     }
     int grid = (a.numRays + kWideBlock - 1) / kWideBlock;
     if (grid > a.numSMs * blocksPerSM) grid = a.numSMs * blocksPerSM;
-    kern<<<grid, kWideBlock, 0, a.stream>>>(a.numRays, a.anyHit, wide_tuning().fetchThreshold, 0x3F800000u, a.rays, a.results, a.wideNodes, a.woop, a.triIndices, a.warpCounter, a.errorFlag);
+    kern<<<grid, kWideBlock, 0, a.stream>>>(a.numRays, a.anyHit, wide_tuning().fetchThreshold, wide_tuning().nodeExit, 0x3F800000u, a.rays, a.results, a.wideNodes, a.woop, a.triIndices, a.warpCounter, a.errorFlag);
     if (launches) *launches = 1;
     return cudaGetLastError();
 }
