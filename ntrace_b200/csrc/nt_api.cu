@@ -667,14 +667,13 @@ int nt_bvh_build(int builder, const float* vtxPos, int numVerts, const int32_t* 
     NT_CUDA(cudaEventRecord(g.evA, g.stream));
     int launches = 0;
     std::string err;
-    cudaError_t e = build_bvh_device((const float*)dV, numVerts, (const int*)dT, numTris, p, out, g.stream, g.numSMs, &launches, &err);
+    cudaError_t e = build_bvh_device((const float*)dV, numVerts, (const int*)dT, numTris, p, out, g.stream, g.numSMs, &launches, &err, g.evB);
     g.launches += launches;
     if (e != cudaSuccess) {
         if (!err.empty()) { set_error("ntrace_b200: " + err); cudaGetLastError(); return 1; }
         NT_CUDA(e);
     }
-    NT_CUDA(cudaEventRecord(g.evB, g.stream));
-    NT_CUDA(cudaEventSynchronize(g.evB));
+    NT_CUDA(cudaEventSynchronize(g.evB));        // recorded by the builder behind its last kernel, before the size readback
     float ms = 0.0f;
     NT_CUDA(cudaEventElapsedTime(&ms, g.evA, g.evB));
     if (outGpuSeconds) *outGpuSeconds = ms * 1.0e-3f;

@@ -26,6 +26,7 @@
 #include "nt_common.cuh"
 #include "nt_sort.cuh"
 #include <cooperative_groups.h>
+#include <cstdlib>
 #include <cstring>
 
 namespace nt {
@@ -60,10 +61,12 @@ __device__ __forceinline__ F3 max3v(F3 a, F3 b) { F3 r; r.x = fmaxf(a.x, b.x); r
 
 __global__ void __launch_bounds__(256) morton_kernel(const float* __restrict__ verts, const int* __restrict__ tris, int n,
                                                       float lox, float loy, float loz, float sx, float sy, float sz,
-                                                      uint* __restrict__ keys, int* __restrict__ idx)
+                                                      uint* __restrict__ keys, int* __restrict__ idx,
+                                                      u64* __restrict__ zeroPack, int* __restrict__ zeroCounters)
 {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n) return;
+    zeroPack[t] = 0; zeroCounters[t] = 0;        // scan input and refit arrival counters of this position (saves two memsets)
     const F3 a = ld3(verts, __ldg(tris + 3 * t)), b = ld3(verts, __ldg(tris + 3 * t + 1)), c = ld3(verts, __ldg(tris + 3 * t + 2));
     const F3 lo = min3v(a, min3v(b, c)), hi = max3v(a, max3v(b, c));
     const float mx = __fadd_rn(lo.x, __fdiv_rn(__fsub_rn(hi.x, lo.x), 2.0f));
@@ -307,15 +310,18 @@ __device__ __forceinline__ void climb(const ClimbCtx& c, int curId, int parCode)
 
 // One thread per KEPT gap (= inner node), taken from the rank-ordered list leaf_emit_kernel leaves behind: with leafSize 8
 // only ~18 % of the gaps survive, and a thread per gap ran this latency-bound kernel with 6 of 32 lanes alive.
-__global__ void __launch_bounds__(256) emit_kernel(int numKept, const int* __restrict__ keptGap, const int* __restrict__ nodeS,
+// The number of kept gaps and of top-level nodes is read from the device scalars (no host readback before the launch: the grid
+// covers every gap and the surplus threads leave).
+__global__ void __launch_bounds__(256) emit_kernel(const int* __restrict__ keptGap, const int* __restrict__ nodeS,
                                                     const int* __restrict__ nodeE, const uint* __restrict__ flags,
                                                     const int* __restrict__ scalars, const float* __restrict__ triBox, float eps, ClimbCtx c)
 {
     const int rank = blockIdx.x * blockDim.x + threadIdx.x;
-    if (rank >= numKept) return;
+    if (rank >= scalars[2]) return;              // low word of the scan total = kept gaps
     const int g = __ldg(keptGap + rank);
     const uint f = flags[g];
     c.nb.rootGap = scalars[0];
+    c.nb.numTop = c.topParent ? scalars[5] : 0;
     c.nb.rootRank = (c.nb.numTop > 0) ? 0u : (uint)c.ex[c.nb.rootGap];
     const int id = gap_node_id(c.nb, g, (uint)rank);
     const int s = nodeS[g], e = nodeE[g], split = g + 1;
@@ -357,13 +363,14 @@ __global__ void __launch_bounds__(256) emit_kernel(int numKept, const int* __res
 // HLBVH: clusters with <= leafSize triangles hang directly under a top-level node as leaves
 // (distribute, emitTreeKernel.cu:990-996): link, leaf box, then join the refit.
 __global__ void __launch_bounds__(256) cluster_leaf_emit_kernel(int numClusters, int leafSize, const int* __restrict__ clsStart,
-                                                                 const int* __restrict__ clsParent,
+                                                                 const int* __restrict__ clsParent, const int* __restrict__ scalars,
                                                                  const float* __restrict__ triBox, float eps, ClimbCtx c)
 {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= numClusters) return;
     const int cs = clsStart[k], ce = clsStart[k + 1];
     if (ce - cs > leafSize) return;
+    c.nb.numTop = scalars[5];
     const int code = clsParent[k];
     const int pid = code >> 1, side = code & 1;
     c.nodes[(size_t)pid * 16 + 12 + side] = ~(3 * cs + (int)(c.ex[cs] >> 32));
@@ -943,11 +950,14 @@ __global__ void single_triangle_kernel(const float* __restrict__ verts, const in
     nodes[12] = ~0; nodes[13] = ~1; nodes[14] = -1; nodes[15] = 0;
 }
 
+constexpr int kOneSweepMaxKeys = 2400000;
+
 struct Scratch {
-    DevBuf keysB, idxB, hist, blockSums, nodeS, nodeE, parent, flags, pack, ex, counters, scalars;
+    DevBuf keysB, idxB, hist, blockSums, nodeS, nodeE, parent, flags, pack, ex, counters;
     DevBuf childBox, childCost, flags2;      // SAH collapse
     DevBuf triBox;                           // 6 floats per sorted position
     DevBuf keptGap;                          // kept gaps (inner nodes) in rank order
+    DevBuf zero;                             // scalars + scan descriptors + the one-sweep radix sort's zone: cleared by one memset per build
     // HLBVH
     DevBuf clsHead, clusterOf, clsStart, clsBox, clsTask0, clsTask1, clsBin, clsParent;
     DevBuf tBox0, tBox1, tCnt0, tCnt1, tId0, tId1, tFirst0, tFirst1, rInts, rBoxes, binBox, binCnt, blockSum, topNodes, topParent, topCounters;
@@ -966,7 +976,7 @@ void release_build_scratch()
 
 cudaError_t build_bvh_device(const float* dVerts, int numVerts, const int* dTris, int n,
                              const BuildParams& p, BuildOutput& out, cudaStream_t stream,
-                             int numSMs, int* outLaunches, std::string* err)
+                             int numSMs, int* outLaunches, std::string* err, cudaEvent_t doneEvent)
 {
     (void)numVerts;
     int launches = 0;
@@ -990,9 +1000,31 @@ cudaError_t build_bvh_device(const float* dVerts, int numVerts, const int* dTris
     uint* keysA = out.sortedKeys->as<uint>();
     int* idxA = out.sortedIdx->as<int>();
 
+    // ---- everything the pipeline needs zeroed, in ONE allocation cleared by ONE memset: the scalars, the descriptors / tickets of
+    // the two single-pass scans and the radix sort's zone (digit histograms, tickets, tile descriptors of the four passes)
+    // One-sweep sort while all of a pass's tiles are resident at once (<= ~1200 tiles of 2048 keys): fewer launches, 0.19 -> 0.15 ms
+    // at 283 K triangles.  Beyond that the serial per-digit look-back over thousands of tiles costs more than the histogram + scan
+    // launches it replaces (10 M soup: 1.81 vs 1.74 ms), so large inputs keep the four-pass form.  NT_SORT_ONESWEEP=0/1 forces either.
+    static const int oneSweepMode = [] { const char* e = getenv("NT_SORT_ONESWEEP"); return e ? (atoi(e) != 0 ? 1 : 0) : -1; }();
+    const bool oneSweep = oneSweepMode < 0 ? (n <= kOneSweepMaxKeys) : (oneSweepMode != 0);
+    static const bool chainedScan = [] { const char* e = getenv("NT_SCAN_CHAINED"); return !e || atoi(e) != 0; }();
+    const size_t zScalars = 0, zDescU = 64, zDescP = zDescU + ((scan_desc_bytes(n) + 15) & ~(size_t)15),
+                 zSort = zDescP + ((scan_desc_bytes(n) + 15) & ~(size_t)15), zBytes = zSort + (oneSweep ? onesweep_zone_bytes(n, 4) : 0);
+    NT_TRY(sc.zero.reserve(zBytes));
+    NT_TRY(cudaMemsetAsync(sc.zero.p, 0, zBytes, stream));
+    char* zone = sc.zero.as<char>();
+    int* scalars = reinterpret_cast<int*>(zone + zScalars);
+    int* rootGap = scalars;                              // int [0]
+    u64* totals = reinterpret_cast<u64*>(scalars) + 1;   // bytes 8..15: (leaves << 32 | inner gap nodes)
+    int* topScal = scalars + 4;                          // ints [4] numTasks, [5] top-level nodes written
+    uint* clusterCount = reinterpret_cast<uint*>(scalars) + 6;   // int [6]
+    uint* scanTickets = reinterpret_cast<uint*>(scalars) + 8;    // ints [8], [9]
+
     // ---- Morton codes (HLBVHBuilder.cpp:67-83: step = (hi - lo) / 1024 on the host, in fp32)
+    NT_TRY(sc.pack.reserve((size_t)n * 8)); NT_TRY(sc.counters.reserve((size_t)n * 4));
     const float sx = (p.hi[0] - p.lo[0]) / 1024.0f, sy = (p.hi[1] - p.lo[1]) / 1024.0f, sz = (p.hi[2] - p.lo[2]) / 1024.0f;
-    morton_kernel<<<(n + 255) / 256, 256, 0, stream>>>(dVerts, dTris, n, p.lo[0], p.lo[1], p.lo[2], sx, sy, sz, keysA, idxA);
+    morton_kernel<<<(n + 255) / 256, 256, 0, stream>>>(dVerts, dTris, n, p.lo[0], p.lo[1], p.lo[2], sx, sy, sz, keysA, idxA,
+                                                        sc.pack.as<u64>(), sc.counters.as<int>());
     launches++;
     NT_TRY(cudaGetLastError());
 
@@ -1001,6 +1033,7 @@ cudaError_t build_bvh_device(const float* dVerts, int numVerts, const int* dTris
         single_triangle_kernel<<<1, 1, 0, stream>>>(dVerts, dTris, idxA, p.epsilon, out.nodes->as<int>(), out.woop->as<float4>(), out.triIndex->as<int>());
         launches++;
         NT_TRY(cudaGetLastError());
+        if (doneEvent) NT_TRY(cudaEventRecord(doneEvent, stream));
         out.nodeBytes = 64; out.woopBytes = 80; out.idxBytes = 20;
         *outLaunches = launches;
         return cudaSuccess;
@@ -1009,9 +1042,10 @@ cudaError_t build_bvh_device(const float* dVerts, int numVerts, const int* dTris
     // ---- stable LSD radix sort, 4 x 8-bit digits over the 30-bit codes (four passes: sorted data ends in keysA / idxA)
     NT_TRY(sc.keysB.reserve((size_t)n * 4));
     NT_TRY(sc.idxB.reserve((size_t)n * 4));
-    NT_TRY(sc.hist.reserve(radix_hist_bytes(n)));
+    if (!oneSweep) NT_TRY(sc.hist.reserve(radix_hist_bytes(n)));
     NT_TRY(sc.blockSums.reserve(scan_block_sums_bytes((long long)radix_hist_bytes(n) / 4) + scan_block_sums_bytes(n)));
-    NT_TRY(radix_sort_pairs<uint>(keysA, idxA, sc.keysB.as<uint>(), sc.idxB.as<int>(), n, 4, sc.hist.as<uint>(), sc.blockSums.as<uint>(), stream, &launches));
+    NT_TRY(radix_sort_pairs<uint>(keysA, idxA, sc.keysB.as<uint>(), sc.idxB.as<int>(), n, 4, sc.hist.as<uint>(), sc.blockSums.as<uint>(), stream, &launches,
+                                  oneSweep ? reinterpret_cast<uint*>(zone + zSort) : nullptr, true));
 
     // per-triangle boxes in sorted order.  HLBVH (cluster boxes) and the SAH collapse need them before the leaves are
     // numbered: one early gather pass; the plain LBVH gets them from leaf_emit_kernel, its only gather.
@@ -1022,13 +1056,6 @@ cudaError_t build_bvh_device(const float* dVerts, int numVerts, const int* dTris
         launches++;
     }
 
-    NT_TRY(sc.scalars.reserve(64));
-    NT_TRY(cudaMemsetAsync(sc.scalars.p, 0, 64, stream));
-    int* rootGap = sc.scalars.as<int>();                 // int [0]
-    u64* totals = sc.scalars.as<u64>() + 1;              // bytes 8..15: (leaves << 32 | inner gap nodes)
-    int* topScal = sc.scalars.as<int>() + 4;             // ints [4] numTasks, [5] top-level nodes written
-    uint* clusterCount = sc.scalars.as<uint>() + 6;      // int [6]
-
     // ---- HLBVH: clusters + top-level SAH (one cooperative kernel)
     int hb = 30, C = 0;
     if (hl) {
@@ -1036,7 +1063,8 @@ cudaError_t build_bvh_device(const float* dVerts, int numVerts, const int* dTris
         NT_TRY(sc.clsHead.reserve((size_t)n * 4)); NT_TRY(sc.clusterOf.reserve((size_t)n * 4));
         cluster_mark_kernel<<<(n + 255) / 256, 256, 0, stream>>>(keysA, n, d, sc.clsHead.as<uint>());
         launches++;
-        NT_TRY(exclusive_scan<uint>(sc.clsHead.as<uint>(), sc.clusterOf.as<uint>(), n, sc.blockSums.as<uint>(), clusterCount, stream, &launches));
+        if (chainedScan) NT_TRY(exclusive_scan_chained<uint>(sc.clsHead.as<uint>(), sc.clusterOf.as<uint>(), n, reinterpret_cast<uint*>(zone + zDescU), scanTickets, clusterCount, stream, &launches));
+        else NT_TRY(exclusive_scan<uint>(sc.clsHead.as<uint>(), sc.clusterOf.as<uint>(), n, sc.blockSums.as<uint>(), clusterCount, stream, &launches));
         uint hc = 0;
         NT_TRY(cudaMemcpyAsync(&hc, clusterCount, 4, cudaMemcpyDeviceToHost, stream));     // readback 1 of 2: cluster count sizes the top-level buffers
         NT_TRY(cudaStreamSynchronize(stream));
@@ -1100,10 +1128,7 @@ cudaError_t build_bvh_device(const float* dVerts, int numVerts, const int* dTris
     // ---- topology, forced leaves, numbering
     const int gaps = n - 1;
     NT_TRY(sc.nodeS.reserve((size_t)n * 4)); NT_TRY(sc.nodeE.reserve((size_t)n * 4)); NT_TRY(sc.parent.reserve((size_t)n * 4));
-    NT_TRY(sc.flags.reserve((size_t)n * 4)); NT_TRY(sc.pack.reserve((size_t)n * 8)); NT_TRY(sc.ex.reserve((size_t)n * 8)); NT_TRY(sc.keptGap.reserve((size_t)n * 4));
-    NT_TRY(sc.counters.reserve((size_t)n * 4));
-    NT_TRY(cudaMemsetAsync(sc.pack.p, 0, (size_t)n * 8, stream));
-    NT_TRY(cudaMemsetAsync(sc.counters.p, 0, (size_t)n * 4, stream));
+    NT_TRY(sc.flags.reserve((size_t)n * 4)); NT_TRY(sc.ex.reserve((size_t)n * 8)); NT_TRY(sc.keptGap.reserve((size_t)n * 4));
     const bool collapse = (p.collapse != 0);
     const int emitLeaf = collapse ? 1 : p.leafSize;          // SAH collapse starts from single-triangle leaves
     topology_kernel<<<(gaps + 255) / 256, 256, 0, stream>>>(keysA, n, emitLeaf, hb, hl ? sc.clusterOf.as<uint>() : nullptr,
@@ -1131,12 +1156,44 @@ cudaError_t build_bvh_device(const float* dVerts, int numVerts, const int* dTris
         launches++;
     }
     NT_TRY(cudaGetLastError());
-    NT_TRY(exclusive_scan<u64>(sc.pack.as<u64>(), sc.ex.as<u64>(), n, sc.blockSums.as<u64>(), totals, stream, &launches));
+    if (chainedScan) NT_TRY(exclusive_scan_chained<u64>(sc.pack.as<u64>(), sc.ex.as<u64>(), n, reinterpret_cast<u64*>(zone + zDescP), scanTickets + 1, totals, stream, &launches));
+    else NT_TRY(exclusive_scan<u64>(sc.pack.as<u64>(), sc.ex.as<u64>(), n, sc.blockSums.as<u64>(), totals, stream, &launches));
 
-    // the (last) host readback of the build: node and leaf counts size the output buffers
+    // No host readback here: the output buffers are sized for the largest tree this input can produce (n - 1 gap nodes plus the
+    // top-level nodes; one terminator per triangle), the emit kernels take the node / leaf counts from the device scalars, and
+    // the counts come back with the one copy at the end of the pipeline.
+    const size_t maxInner = (size_t)(n - 1) + (hl ? (size_t)C : 0), maxRows = (size_t)n * 4;
+    NT_TRY(out.nodes->reserve(maxInner * 64));
+    NT_TRY(out.woop->reserve(maxRows * 16));
+    NT_TRY(out.triIndex->reserve(maxRows * 4));
+
+    ClimbCtx cc;
+    cc.nodes = out.nodes->as<int>(); cc.parent = sc.parent.as<int>(); cc.ex = sc.ex.as<u64>(); cc.gapCounters = sc.counters.as<int>();
+    cc.topParent = hl ? sc.topParent.as<int>() : nullptr; cc.topCounters = hl ? sc.topCounters.as<int>() : nullptr;
+    cc.nb.numTop = 0; cc.nb.rootGap = 0; cc.nb.rootRank = 0; cc.nb.linkMul = linkMul;
+    if (hl) NT_TRY(cudaMemcpyAsync(out.nodes->p, sc.topNodes.p, (size_t)C * 64, cudaMemcpyDeviceToDevice, stream));   // >= the top-level nodes written (scalars[5])
+
+    // Woop rows / indices / terminators.  Without an earlier tri_box pass (plain LBVH) this kernel is the one gather of the
+    // geometry and also leaves the per-triangle boxes behind for emit_kernel, so it runs first.
+    leaf_emit_kernel<<<(n + 255) / 256, 256, 0, stream>>>(n, sc.ex.as<u64>(), sc.pack.as<uint>(), dVerts, dTris, idxA,
+                                                           out.woop->as<float4>(), out.triIndex->as<int>(), earlyTriBox ? nullptr : sc.triBox.as<float>(),
+                                                           sc.keptGap.as<int>());
+    emit_kernel<<<(gaps + 255) / 256, 256, 0, stream>>>(sc.keptGap.as<int>(), sc.nodeS.as<int>(), sc.nodeE.as<int>(), sc.flags.as<uint>(),
+                                                         scalars, sc.triBox.as<float>(), p.epsilon, cc);
+    launches += 2;
+    if (hl) {
+        cluster_leaf_emit_kernel<<<(C + 255) / 256, 256, 0, stream>>>(C, p.leafSize, sc.clsStart.as<int>(), sc.clsParent.as<int>(), scalars,
+                                                                       sc.triBox.as<float>(), p.epsilon, cc);
+        launches++;
+    }
+    NT_TRY(cudaGetLastError());
+    if (doneEvent) NT_TRY(cudaEventRecord(doneEvent, stream));
+
+    // the one host readback of an LBVH build (HLBVH: the second of two): node and leaf counts = the sizes of what was written
     int hs[8];
-    NT_TRY(cudaMemcpyAsync(hs, sc.scalars.p, 32, cudaMemcpyDeviceToHost, stream));
+    NT_TRY(cudaMemcpyAsync(hs, scalars, 32, cudaMemcpyDeviceToHost, stream));
     NT_TRY(cudaStreamSynchronize(stream));
+    *outLaunches = launches;
     u64 tot; memcpy(&tot, &hs[2], 8);
     const size_t numTop = hl ? (size_t)hs[5] : 0;
     const size_t numInner = (size_t)(tot & 0xffffffffull) + numTop, numLeaves = (size_t)(tot >> 32);
@@ -1150,33 +1207,6 @@ cudaError_t build_bvh_device(const float* dVerts, int numVerts, const int* dTris
     out.nodeBytes = numInner * 64;
     out.woopBytes = ((size_t)n * 3 + numLeaves) * 16;
     out.idxBytes = ((size_t)n * 3 + numLeaves) * 4;
-    NT_TRY(out.nodes->reserve(out.nodeBytes));
-    NT_TRY(out.woop->reserve(out.woopBytes));
-    NT_TRY(out.triIndex->reserve(out.idxBytes));
-
-    ClimbCtx cc;
-    cc.nodes = out.nodes->as<int>(); cc.parent = sc.parent.as<int>(); cc.ex = sc.ex.as<u64>(); cc.gapCounters = sc.counters.as<int>();
-    cc.topParent = hl ? sc.topParent.as<int>() : nullptr; cc.topCounters = hl ? sc.topCounters.as<int>() : nullptr;
-    cc.nb.numTop = (int)numTop; cc.nb.rootGap = 0; cc.nb.rootRank = 0; cc.nb.linkMul = linkMul;
-    if (hl) NT_TRY(cudaMemcpyAsync(out.nodes->p, sc.topNodes.p, numTop * 64, cudaMemcpyDeviceToDevice, stream));
-
-    // Woop rows / indices / terminators.  Without an earlier tri_box pass (plain LBVH) this kernel is the one gather of the
-    // geometry and also leaves the per-triangle boxes behind for emit_kernel, so it runs first.
-    leaf_emit_kernel<<<(n + 255) / 256, 256, 0, stream>>>(n, sc.ex.as<u64>(), sc.pack.as<uint>(), dVerts, dTris, idxA,
-                                                           out.woop->as<float4>(), out.triIndex->as<int>(), earlyTriBox ? nullptr : sc.triBox.as<float>(),
-                                                           sc.keptGap.as<int>());
-    const int numKept = (int)(numInner - numTop);
-    if (numKept > 0)
-        emit_kernel<<<(numKept + 255) / 256, 256, 0, stream>>>(numKept, sc.keptGap.as<int>(), sc.nodeS.as<int>(), sc.nodeE.as<int>(), sc.flags.as<uint>(),
-                                                                rootGap, sc.triBox.as<float>(), p.epsilon, cc);
-    launches += 2;
-    if (hl) {
-        cluster_leaf_emit_kernel<<<(C + 255) / 256, 256, 0, stream>>>(C, p.leafSize, sc.clsStart.as<int>(), sc.clsParent.as<int>(),
-                                                                       sc.triBox.as<float>(), p.epsilon, cc);
-        launches++;
-    }
-    NT_TRY(cudaGetLastError());
-    *outLaunches = launches;
     return cudaSuccess;
 #undef NT_TRY
 }

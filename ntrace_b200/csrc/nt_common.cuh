@@ -116,10 +116,11 @@ struct BuildOutput {          // device buffers owned by the context
 // nt_shutdown: free the grow-only scratch of the builder / the ray sorter (it belongs to the device it was allocated on)
 void release_build_scratch();
 void release_sort_scratch();
-// verts/tris are device pointers. Returns cudaSuccess and fills sizes; launches counted into *outLaunches.
+// verts/tris are device pointers. Returns cudaSuccess and fills sizes; launches counted into *outLaunches.  `doneEvent` (optional) is
+// recorded behind the last kernel, before the copy that brings the sizes back to the host.
 cudaError_t build_bvh_device(const float* dVerts, int numVerts, const int* dTris, int numTris,
                              const BuildParams& p, BuildOutput& out, cudaStream_t stream,
-                             int numSMs, int* outLaunches, std::string* err);
+                             int numSMs, int* outLaunches, std::string* err, cudaEvent_t doneEvent = nullptr);
 
 // ---- basic CudaBVH layouts (nt_layout.cu): AOS/SOA buffers on the device -> Compact / Compact2 form in `out`
 cudaError_t rescale_compact_links(int4* dNodes, size_t numNodes, int mulNum, int mulDen, cudaStream_t stream);

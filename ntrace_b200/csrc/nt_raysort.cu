@@ -10,6 +10,7 @@
 // Rays with identical keys keep their original relative order (the reference's quicksort leaves that case unspecified).
 #include "nt_common.cuh"
 #include "nt_sort.cuh"
+#include <cstdlib>
 
 namespace nt {
 namespace {
@@ -105,7 +106,7 @@ __global__ void __launch_bounds__(256) ray_reorder_kernel(int n, const int* __re
     outSlotToID[i] = id;
 }
 
-struct SortScratch { DevBuf keysA, keysB, idxA, idxB, hist, blockSums, box, oldRays, oldS2I, word1, word2; };
+struct SortScratch { DevBuf keysA, keysB, idxA, idxB, hist, blockSums, box, oldRays, oldS2I, word1, word2, sortAux; };
 SortScratch g_ss;
 static_assert(sizeof(SortScratch) % sizeof(DevBuf) == 0, "SortScratch holds DevBuf members only");
 
@@ -129,6 +130,10 @@ cudaError_t ray_sort_device(float4* rays, int* idToSlot, int* slotToID, int n, c
     NT_TRY(s.blockSums.reserve(scan_block_sums_bytes((long long)radix_hist_bytes(n) / 4)));
     NT_TRY(s.box.reserve(64)); NT_TRY(s.oldRays.reserve((size_t)n * 32)); NT_TRY(s.oldS2I.reserve((size_t)n * 4));
     NT_TRY(s.word1.reserve((size_t)n * 8)); NT_TRY(s.word2.reserve((size_t)n * 8));
+    static const int oneSweepMode = [] { const char* e = getenv("NT_SORT_ONESWEEP"); return e ? (atoi(e) != 0 ? 1 : 0) : -1; }();
+    const bool oneSweep = oneSweepMode < 0 ? (n <= 2400000) : (oneSweepMode != 0);      // as the builder: while a pass's tiles are all resident
+    if (oneSweep) NT_TRY(s.sortAux.reserve(onesweep_zone_bytes(n, 8)));
+    uint* aux = oneSweep ? s.sortAux.as<uint>() : nullptr;
 
     ray_aabb_init_kernel<<<1, 32, 0, stream>>>(s.box.as<int>());
     int grid = (n + 255) / 256;
@@ -139,7 +144,7 @@ cudaError_t ray_sort_device(float4* rays, int* idToSlot, int* slotToID, int n, c
     NT_TRY(cudaGetLastError());
     // least significant word first; every round is stable, so after the last one the order is that of the whole 192-bit key
     NT_TRY(radix_sort_pairs<u64>(s.keysA.as<u64>(), s.idxA.as<int>(), s.keysB.as<u64>(), s.idxB.as<int>(), n, 8,
-                                 s.hist.as<uint>(), s.blockSums.as<uint>(), stream, &launches));
+                                 s.hist.as<uint>(), s.blockSums.as<uint>(), stream, &launches, aux));
     const u64* words[2] = {s.word1.as<u64>(), s.word2.as<u64>()};
     const int passes[2] = {8, 4};
     for (int r = 0; r < 2; r++) {
@@ -147,7 +152,7 @@ cudaError_t ray_sort_device(float4* rays, int* idToSlot, int* slotToID, int n, c
         launches++;
         NT_TRY(cudaGetLastError());
         NT_TRY(radix_sort_pairs<u64>(s.keysA.as<u64>(), s.idxA.as<int>(), s.keysB.as<u64>(), s.idxB.as<int>(), n, passes[r],
-                                     s.hist.as<uint>(), s.blockSums.as<uint>(), stream, &launches));
+                                     s.hist.as<uint>(), s.blockSums.as<uint>(), stream, &launches, aux));
     }
     NT_TRY(cudaMemcpyAsync(s.oldRays.p, rays, (size_t)n * 32, cudaMemcpyDeviceToDevice, stream));
     NT_TRY(cudaMemcpyAsync(s.oldS2I.p, slotToID, (size_t)n * 4, cudaMemcpyDeviceToDevice, stream));
