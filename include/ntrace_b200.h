@@ -147,6 +147,11 @@ int nt_bvh_convert(int layout);
  * outWideNodes may be NULL to query *outWideBytes; *outMaxDepth (optional) = depth of the Wide4 tree. */
 int nt_bvh_wide4_convert_host(int layout, const void* nodes, size_t nodeBytes, size_t woopBytes,
                               void* outWideNodes, size_t outCapacityBytes, size_t* outWideBytes, int* outMaxDepth);
+/* NEW: the Wide4 node array of the RESIDENT BVH as the library derived it ON THE DEVICE (csrc/nt_wide.cu, wide4_convert_kernel: the
+ * conversion the "b200_wide4*" / "b200_auto" kernels actually trace; derived here if no such kernel has run yet), copied to a host
+ * or device buffer.  Same nodes, plane bytes and child-slot order as nt_bvh_wide4_convert_host produces from the same tree; only the
+ * numbering of the nodes differs.  outWideNodes may be NULL to query *outWideBytes. */
+int nt_bvh_wide4_download(void* outWideNodes, size_t outCapacityBytes, size_t* outWideBytes, int* outMaxDepth);
 /* SAH cost of the resident BVH as the reference reports it in BVH::Stats (BVH.cpp:67-70: BVHNode::computeSubtreeProbabilities,
  * BVHNode.cpp:79-94, Platform costs 1 / 1: an inner node costs 2, a leaf its triangle count, each weighted by area / root area), computed
  * on the device in one parallel pass (the reference's GPU twin, calcSAH, is a single-thread recursion with inner cost 1,

@@ -97,7 +97,7 @@ struct Context {
     size_t srcNodeBytes = 0, srcWoopBytes = 0, srcIdxBytes = 0;
     bool basic = false, converted = false;
     // Wide4 form of the resident (Compact / Compact2) node buffer, derived on demand for the b200_wide4* kernels (nt_wide.cu)
-    DevBuf wideNodes;
+    DevBuf wideNodes, wideScratch;
     size_t wideBytes = 0;
     bool wideValid = false;
     int wideDepth = 0;
@@ -202,21 +202,20 @@ int ensure_traversal_form()
     return 0;
 }
 
-// derive the Wide4 node array from the resident Compact / Compact2 nodes (host conversion: nt_wide.cu); caller holds the mutex
+// derive the Wide4 node array from the resident Compact / Compact2 nodes, on the device (nt_wide.cu); caller holds the mutex
 int ensure_wide_form()
 {
-    if ((g.kernel != Kernel_Wide4Persistent && g.kernel != Kernel_Wide4Mr && g.kernel != Kernel_Auto) || g.wideValid) return 0;
-    std::vector<int32_t> h(g.nodeBytes / 4);
-    NT_CUDA(cudaMemcpyAsync(h.data(), g.nodes.p, g.nodeBytes, cudaMemcpyDeviceToHost, g.stream));
-    NT_CUDA(cudaStreamSynchronize(g.stream));
-    std::vector<uint32_t> w;
+    if ((g.kernel != Kernel_Wide4Persistent && g.kernel != Kernel_Wide4Mr && g.kernel != Kernel_Wide4Sw && g.kernel != Kernel_Auto) || g.wideValid) return 0;
     std::string err;
     const int srcLayout = g.basic ? (int)Layout_Compact : g.bvhLayout;
-    if (convert_compact_to_wide4_host(h.data(), g.nodeBytes, srcLayout, g.woopBytes / 16, w, &g.wideDepth, &err)) { set_error("ntrace_b200: " + err); return 1; }
-    NT_CUDA(g.wideNodes.reserve(w.size() * 4));
-    NT_CUDA(cudaMemcpyAsync(g.wideNodes.p, w.data(), w.size() * 4, cudaMemcpyHostToDevice, g.stream));
-    NT_CUDA(cudaStreamSynchronize(g.stream));
-    g.wideBytes = w.size() * 4;
+    int launches = 0;
+    cudaError_t e = convert_compact_to_wide4_device(g.nodes.p, g.nodeBytes, srcLayout, g.woopBytes / 16, g.wideNodes, g.wideScratch, &g.wideBytes,
+                                                    &g.wideDepth, g.numSMs, g.stream, &launches, &err);
+    g.launches += launches;
+    if (e != cudaSuccess) {
+        if (!err.empty()) { set_error("ntrace_b200: " + err); cudaGetLastError(); return 1; }
+        NT_CUDA(e);
+    }
     g.wideValid = true;
     return 0;
 }
@@ -401,7 +400,7 @@ void nt_shutdown(void)
     for (int i = 0; i < Context::kRing; i++) { cudaEventDestroy(g.ring[i].ev); cudaEventDestroy(g.prod[i].ev); }
     DevBuf* bufs[] = {&g.nodes, &g.woop, &g.triIndex, &g.sortedKeys, &g.sortedIdx, &g.stRays, &g.stResults, &g.stA, &g.stB,
                       &g.stC, &g.stD, &g.stE, &g.counters, &g.pixelTable, &g.sceneVerts, &g.sceneTris,
-                      &g.srcNodes, &g.srcWoop, &g.srcIdx, &g.layoutScratch, &g.wideNodes};
+                      &g.srcNodes, &g.srcWoop, &g.srcIdx, &g.layoutScratch, &g.wideNodes, &g.wideScratch};
     for (DevBuf* b : bufs) b->release();
     release_build_scratch();
     release_sort_scratch();
@@ -547,6 +546,12 @@ int nt_set_kernel(const char* name)
         // any-hit triangle is the reference's too), closest-hit batches through Wide4 (their result does not depend on the visiting order)
         {"b200_auto", Kernel_Auto, Layout_Compact, false},
         {"b200_auto_compact2", Kernel_Auto, Layout_Compact2, false},
+        {"b200_sw", Kernel_BinarySw, Layout_Compact, false},
+        {"b200_sw_fastmath", Kernel_BinarySw, Layout_Compact, true},
+        {"b200_sw_compact2", Kernel_BinarySw, Layout_Compact2, false},
+        {"b200_wide4_sw", Kernel_Wide4Sw, Layout_Compact, false},
+        {"b200_wide4_sw_fastmath", Kernel_Wide4Sw, Layout_Compact, true},
+        {"b200_wide4_sw_compact2", Kernel_Wide4Sw, Layout_Compact2, false},
         {"b200_wide4_mr", Kernel_Wide4Mr, Layout_Compact, false},
         {"b200_wide4_mr_fastmath", Kernel_Wide4Mr, Layout_Compact, true},
         {"b200_wide4_mr_compact2", Kernel_Wide4Mr, Layout_Compact2, false},
@@ -739,6 +744,31 @@ int nt_bvh_wide4_convert_host(int layout, const void* nodes, size_t nodeBytes, s
     if (outWideNodes) {
         if (outCapacityBytes < w.size() * 4) { set_error("ntrace_b200: output buffer too small for the Wide4 node array"); return 1; }
         memcpy(outWideNodes, w.data(), w.size() * 4);
+    }
+    return 0;
+}
+
+int nt_bvh_wide4_download(void* outWideNodes, size_t outCapacityBytes, size_t* outWideBytes, int* outMaxDepth)
+{
+    std::lock_guard<std::mutex> lock(g_mutex);
+    if (require_init()) return 1;
+    if (!outWideBytes) { set_error("ntrace_b200: null pointer in nt_bvh_wide4_download"); return 1; }
+    if (!g.haveBVH) { set_error("CudaBVHTracer: No BVH!"); return 1; }
+    if (join_kernel_streams()) return 1;
+    if (g.basic && ensure_traversal_form()) return 1;
+    if (!g.wideValid) {
+        const int keep = g.kernel;
+        g.kernel = Kernel_Wide4Persistent;
+        const int rc = ensure_wide_form();
+        g.kernel = keep;
+        if (rc) return 1;
+    }
+    *outWideBytes = g.wideBytes;
+    if (outMaxDepth) *outMaxDepth = g.wideDepth;
+    if (outWideNodes) {
+        if (outCapacityBytes < g.wideBytes) { set_error("ntrace_b200: output buffer too small for the Wide4 node array"); return 1; }
+        NT_CUDA(cudaMemcpyAsync(outWideNodes, g.wideNodes.p, g.wideBytes, cudaMemcpyDefault, g.stream));
+        NT_CUDA(cudaStreamSynchronize(g.stream));
     }
     return 0;
 }

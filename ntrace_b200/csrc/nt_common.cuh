@@ -35,6 +35,8 @@ enum TraceKernelId : int {
     Kernel_BinaryMr = 3,                // two rays per lane, phase-scheduled (nt_wide.cu "mr"), binary Compact / Compact2 nodes
     Kernel_Wide4Mr = 4,                 // the same over the Wide4 node array
     Kernel_Auto = 5,                    // per batch: any-hit -> Kernel_PersistentSpeculative, closest-hit -> Kernel_Wide4Persistent (API level only)
+    Kernel_BinarySw = 6,                // one active + one parked ray per lane, exchanged at the phase boundaries (nt_wide.cu "sw"), binary nodes
+    Kernel_Wide4Sw = 7,                 // the same over the Wide4 node array
     Kernel_Count
 };
 
@@ -63,8 +65,12 @@ void reset_launch_caches();
 constexpr int kWideMaxDepth = 42;       // three pushes per level at most: 1 + 3 * depth entries fit the kernel's 128-entry stack
 int convert_compact_to_wide4_host(const int32_t* nodes, size_t nodeBytes, int layout, size_t woopRows,
                                   std::vector<uint32_t>& out, int* outMaxDepth, std::string* err);
+struct DevBuf;
+cudaError_t convert_compact_to_wide4_device(const void* dNodes, size_t nodeBytes, int layout, size_t woopRows, DevBuf& wide, DevBuf& scratch,
+                                            size_t* outWideBytes, int* outMaxDepth, int numSMs, cudaStream_t stream, int* launches, std::string* err);
 cudaError_t launch_trace_wide4(const TraceLaunch& a, int* outNumLaunches);
 cudaError_t launch_trace_mr(const TraceLaunch& a, int* outNumLaunches);
+cudaError_t launch_trace_sw(const TraceLaunch& a, int* outNumLaunches);
 KernelConfig trace_kernel_config(int kernel, int layout);
 
 // ---- ray generation (nt_raygen.cu) ------------------------------------------------------------

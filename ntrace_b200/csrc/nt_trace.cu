@@ -347,6 +347,9 @@ cudaError_t launch_trace(const TraceLaunch& a, int* launches)
     case Kernel_BinaryMr:
     case Kernel_Wide4Mr:
         return launch_trace_mr(a, launches);
+    case Kernel_BinarySw:
+    case Kernel_Wide4Sw:
+        return launch_trace_sw(a, launches);
     default:
         return cudaErrorInvalidValue;
     }

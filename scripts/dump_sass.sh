@@ -22,6 +22,7 @@ KEEP = {
     'trace_kernel': lambda a: a.split(', ')[1:3] == ['128', '8'] and a.split(', ')[-1] in ('1', 'true'),
     'trace_wide4_kernel': lambda a: a.startswith('128, 8,') and a.split(', ')[-1] in ('1', 'true'),
     'trace_mr_kernel': lambda a: a.startswith('128, 8,'),
+    'trace_sw_kernel': lambda a: a.startswith('128, 8,'),
 }
 summary, manifest, seen = [], [], collections.Counter()
 for p, dem in zip(parts, names):
@@ -33,7 +34,7 @@ for p, dem in zip(parts, names):
     entry = {'kernel': base + (f'<{targs_n}>' if targs_n else '')}
     if base in KEEP and not KEEP[base](targs_n):
         entry['listing'] = None
-        entry['why'] = 'tuning variant (NT_TRACE_* / NT_WIDE_* / NT_MR_* experiment knobs); the default variant of the family is listed'
+        entry['why'] = 'tuning variant (NT_TRACE_* / NT_WIDE_* / NT_MR_* / NT_SW_* experiment knobs); the default variant of the family is listed'
         manifest.append(entry)
         continue
     tag = base + ('_' + re.sub(r'[^0-9a-zA-Z]+', '_', targs_n).strip('_') if targs_n else '')

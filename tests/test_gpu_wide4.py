@@ -47,7 +47,7 @@ def _trace(gpu_host, frame, kernel, bvh):
     return out
 
 
-@pytest.mark.parametrize("kernel", ["b200_wide4", "b200_wide4_mr", "b200_wide4_fastmath"])
+@pytest.mark.parametrize("kernel", ["b200_wide4", "b200_wide4_mr", "b200_wide4_sw", "b200_wide4_fastmath"])
 def test_wide4_kernels_are_bit_identical_to_the_emulation(gpu_host, orc, frame, kernel):
     bvh = gpu_host.CudaBVH(frame["nodes"], frame["woop"], frame["idx"])
     got = _trace(gpu_host, frame, kernel, bvh)
@@ -71,7 +71,7 @@ def test_wide4_kernels_are_bit_identical_to_the_emulation(gpu_host, orc, frame, 
             assert np.array_equal(got[name][hit, 1], flat[hit, 1])
 
 
-@pytest.mark.parametrize("kernel", ["b200_mr", "b200_mr_fastmath"])
+@pytest.mark.parametrize("kernel", ["b200_mr", "b200_mr_fastmath", "b200_sw", "b200_sw_fastmath"])
 def test_multi_ray_lane_kernel_equals_the_one_ray_kernel(gpu_host, frame, kernel):
     bvh = gpu_host.CudaBVH(frame["nodes"], frame["woop"], frame["idx"])
     base = "b200_persistent_speculative_while_while" + ("_fastmath" if "fastmath" in kernel else "")
@@ -79,6 +79,36 @@ def test_multi_ray_lane_kernel_equals_the_one_ray_kernel(gpu_host, frame, kernel
     b = _trace(gpu_host, frame, kernel, bvh)
     for name in a:
         assert np.array_equal(a[name], b[name]), name          # id, t, u, v: every bit, any-hit included
+
+
+def _canonical_wide(wn):
+    """numbering-independent form of a Wide4 tree: node payloads in depth-first slot order, inner links replaced by a marker"""
+    wn = wn.reshape(-1, 16)
+    out, stack = [], [0]
+    while stack:
+        w = wn[stack.pop()]
+        links = w[12:16].view(np.int32)
+        out.append(w[:12].tobytes() + np.where(links < 0, links, 0).astype(np.int32).tobytes())
+        stack.extend(int(l) for l in links[::-1] if l >= 0)
+    return out
+
+
+@pytest.mark.parametrize("layout", [capi.LAYOUT_COMPACT, capi.LAYOUT_COMPACT2])
+def test_device_conversion_equals_the_host_statement_of_the_format(gpu_host, frame, layout):
+    # what the library traces (wide4_convert_kernel, derived on the device) against nt_bvh_wide4_convert_host on the same tree:
+    # same nodes, plane bytes, child slots and leaves; only the numbering may differ
+    capi.bvh_set_build_layout(layout)
+    try:
+        bvh = gpu_host.HLBVHBuilder(frame["scene"], gpu_host.HLBVHParams(True, 4, 8, 0.001))
+        nodes, woop, idx, lay = capi.bvh_download()
+        assert lay == layout
+        dev, dev_depth = capi.bvh_wide4_download()
+        ref, ref_depth = capi.bvh_wide4_convert_host(layout, nodes, woop.nbytes)
+    finally:
+        capi.bvh_set_build_layout(capi.LAYOUT_COMPACT)
+    assert dev.size == ref.size and dev_depth == ref_depth
+    assert _canonical_wide(dev) == _canonical_wide(ref)
+    del bvh
 
 
 def test_wide4_on_a_gpu_built_compact2_tree(gpu_host, orc, frame):
