@@ -2,6 +2,7 @@
 // (no CUB / thrust; replaces thrust::sort_by_key, src/rt/bvh/HLBVH/radixSort.cu:22-46).
 #pragma once
 #include "nt_common.cuh"
+#include <cstdlib>
 
 namespace nt {
 namespace {
@@ -223,7 +224,30 @@ __global__ void __launch_bounds__(kSortThreads) radix_hist_kernel(const KeyT* __
 // the per-warp counters carry the running count, so the order inside a digit is the input order (stable).  The tile is then
 // put in digit order in shared memory and written out by consecutive threads, so each digit's run leaves as contiguous
 // segments instead of 32 scattered 4-byte stores per warp.
-template <class KeyT>
+// TMA experiment (north_star: "TMA/shared-memory staging where it measurably helps"): the tile's keys arrive in shared memory through ONE
+// bulk asynchronous copy (cp.async.bulk global -> shared, completion on an mbarrier) issued by one thread, instead of eight coalesced
+// 128-byte-per-warp loads per thread.  BULK = true selects it for full tiles (the copy needs 16-byte granularity); NT_SORT_BULK=1 at run
+// time.  Measured on the B200 (scripts/tma_experiments.sh, profiles/r2i_tma_experiments.txt): 10 M-triangle LBVH build 1.731 vs 1.736 ms,
+// 10.5 M scene 1.625 vs 1.626 ms, sorted output identical -- the pass is bound by the ranking arithmetic and the scattered stores, not by
+// the latency of its (already coalesced) tile load -- so the default stays the plain loads.
+__device__ __forceinline__ uint smem_u32(const void* p) { return (uint)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bulk_load_tile(void* smemDst, const void* gmemSrc, uint bytes, unsigned long long* bar)
+{
+    // one thread: arm the barrier with the byte count, start the copy
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_u32(smemDst)), "l"(gmemSrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_wait(unsigned long long* bar, uint phase)
+{
+    uint ok;
+    do {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(phase) : "memory");
+    } while (!ok);
+}
+
+template <class KeyT, bool BULK>
 __global__ void __launch_bounds__(kSortThreads) radix_scatter_kernel(const KeyT* __restrict__ keysIn, const int* __restrict__ idxIn,
                                                                      KeyT* __restrict__ keysOut, int* __restrict__ idxOut,
                                                                      int n, int shift, const uint* __restrict__ histScan, int numBlocks)
@@ -234,13 +258,25 @@ __global__ void __launch_bounds__(kSortThreads) radix_scatter_kernel(const KeyT*
     __shared__ uint s_digitBase[256];          // first local position of each digit
     __shared__ uint s_outOfs[256];             // global position = s_outOfs[digit] + local position (mod 2^32)
     __shared__ uint s_warp[kSortThreads / 32];
-    __shared__ KeyT s_key[TILE];
+    __shared__ __align__(16) KeyT s_key[TILE];
     __shared__ int  s_idx[TILE];
+    __shared__ __align__(8) unsigned long long s_bar;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int tileBase = blockIdx.x * TILE;
+    const bool bulk = BULK && (tileBase + TILE <= n);
+    if (BULK) {
+        if (threadIdx.x == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&s_bar)) : "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        }
+    }
     for (int i = threadIdx.x; i < (kSortThreads / 32) * 256; i += kSortThreads) (&s_cnt[0][0])[i] = 0;
     __syncthreads();
+    if (bulk) {
+        if (threadIdx.x == 0) bulk_load_tile(s_key, keysIn + tileBase, (uint)(TILE * sizeof(KeyT)), &s_bar);
+        bulk_wait(&s_bar, 0);
+    }
 
-    const int tileBase = blockIdx.x * TILE;
     const int segBase = tileBase + w * (ITEMS * 32);
     KeyT key[ITEMS];
     uint rank[ITEMS];
@@ -248,7 +284,7 @@ __global__ void __launch_bounds__(kSortThreads) radix_scatter_kernel(const KeyT*
     for (int r = 0; r < ITEMS; r++) {
         const int i = segBase + r * 32 + lane;
         const bool valid = i < n;
-        key[r] = valid ? keysIn[i] : KeyT(0);
+        key[r] = bulk ? s_key[i - tileBase] : (valid ? keysIn[i] : KeyT(0));
         const uint digit = valid ? ((uint)(key[r] >> shift) & 255u) : 256u;
         const uint peers = match_digit(digit);
         uint pre = 0;
@@ -480,7 +516,9 @@ cudaError_t radix_sort_pairs(KeyT* keysA, int* idxA, KeyT* keysB, int* idxB, int
         *launches += 1;
         cudaError_t e = exclusive_scan<uint>(hist, hist, histLen, blockSums, nullptr, stream, launches);
         if (e != cudaSuccess) return e;
-        radix_scatter_kernel<KeyT><<<nb, kSortThreads, 0, stream>>>(kin, iin, kout, iout, n, shift, hist, nb);
+        static const bool bulkTile = [] { const char* e = getenv("NT_SORT_BULK"); return e && atoi(e) != 0; }();
+        if (bulkTile) radix_scatter_kernel<KeyT, true><<<nb, kSortThreads, 0, stream>>>(kin, iin, kout, iout, n, shift, hist, nb);
+        else radix_scatter_kernel<KeyT, false><<<nb, kSortThreads, 0, stream>>>(kin, iin, kout, iout, n, shift, hist, nb);
         *launches += 1;
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;

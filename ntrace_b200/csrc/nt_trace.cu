@@ -66,7 +66,14 @@ __device__ __forceinline__ const float4* node_ptr(const float4* nodes, int addr)
     return reinterpret_cast<const float4*>(reinterpret_cast<const char*>(nodes) + addr);
 }
 
-template <int LAYOUT, int BLOCK, int SMEM_N, bool PERSISTENT, bool FAST, bool WIDE>
+// BULKRAYS: TMA experiment on the warp ray fetch (north_star: "TMA/shared-memory staging where it measurably helps").  The n <= 32 rays a
+// warp reserves are contiguous (n * 32 bytes): the reserving lane starts ONE bulk asynchronous copy (cp.async.bulk global -> shared,
+// completion on a per-warp mbarrier) into a 1 KB per-warp staging area and every lane then reads its ray from shared memory, instead
+// of one 256-bit streaming load per lane.  NT_TRACE_BULKRAYS=1 selects it.  Measured on the bench frame (scripts/tma_experiments.sh,
+// profiles/r2i_tma_experiments.txt): primary 4 713 vs 4 759, AO 3 455 vs 3 874, diffuse 2 103 vs 2 364 Mrays/s, results identical -- the per-lane
+// loads of contiguous rays already coalesce into full 128-byte lines, the copy adds an mbarrier round trip on the critical path of every
+// refill and its 4 KB per CTA come out of the L1 that serves the BVH -- so the default stays the direct loads.
+template <int LAYOUT, int BLOCK, int SMEM_N, bool PERSISTENT, bool FAST, bool WIDE, bool BULKRAYS = false>
 __global__ void __launch_bounds__(BLOCK)
 trace_kernel(int numRays, int anyHit, int fetchThreshold,
              const float4* __restrict__ rays, int4* __restrict__ results,
@@ -80,6 +87,16 @@ trace_kernel(int numRays, int anyHit, int fetchThreshold,
     const int tid = threadIdx.x;
     const unsigned lane = tid & 31;
     int* const sbase = s_stack + tid;
+    __shared__ __align__(128) float4 s_rays[BULKRAYS ? (BLOCK / 32) * 64 : 1];
+    __shared__ __align__(8) unsigned long long s_bar[BULKRAYS ? BLOCK / 32 : 1];
+    unsigned bulkPhase = 0;
+    if (BULKRAYS) {
+        if (lane == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"((unsigned)__cvta_generic_to_shared(&s_bar[tid >> 5])) : "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        }
+        __syncwarp();
+    }
 
     // the bound check sits on the spill path only (taken on ~1e-4 of the pushes): a tree deeper than the stack drops the entry and
     // raises the error flag instead of writing past l_stack
@@ -100,6 +117,7 @@ trace_kernel(int numRays, int anyHit, int fetchThreshold,
     for (;;) {
         // ---------------- ray fetch ----------------
         const bool need = alive && (nodeAddr == kEntrypointSentinel);
+        int fetchRank = 0;
         if (PERSISTENT) {
             // One atomicAdd per warp refill: rank the lanes that need a ray, the first of them
             // reserves a contiguous range and broadcasts its base (reference: kepler...cu:96-115).
@@ -112,6 +130,25 @@ trace_kernel(int numRays, int anyHit, int fetchThreshold,
                 if ((int)lane == leader) base = atomicAdd(warpCounter, n);
                 base = __shfl_sync(0xffffffffu, base, leader);
                 if (need) rayidx = base + rank;
+                fetchRank = rank;
+                if (BULKRAYS) {
+                    const int cnt = min(n, numRays - base);                 // warp-uniform
+                    if (cnt > 0) {
+                        const unsigned bar = (unsigned)__cvta_generic_to_shared(&s_bar[tid >> 5]);
+                        if ((int)lane == leader) {
+                            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // earlier generic reads of the staging area before the async write
+                            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(cnt * 32) : "memory");
+                            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                         :: "r"((unsigned)__cvta_generic_to_shared(&s_rays[(tid >> 5) * 64])), "l"(rays + (size_t)base * 2), "r"(cnt * 32), "r"(bar) : "memory");
+                        }
+                        unsigned ok;
+                        do {
+                            asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                                         : "=r"(ok) : "r"(bar), "r"(bulkPhase) : "memory");
+                        } while (!ok);
+                        bulkPhase ^= 1u;
+                    }
+                }
             }
         } else {
             if (need) rayidx = (rayidx == -1) ? (int)(blockIdx.x * BLOCK + tid) : numRays;
@@ -120,7 +157,10 @@ trace_kernel(int numRays, int anyHit, int fetchThreshold,
             if (rayidx >= numRays) { alive = false; rayidx = -1; }
             else {
                 float4 o, d;
-                if (WIDE) ld256_cs(rays + rayidx * 2, o, d);        // 32-byte aligned ray buffer (checked by the launcher)
+                if (BULKRAYS) {
+                    o = s_rays[(tid >> 5) * 64 + fetchRank * 2]; d = s_rays[(tid >> 5) * 64 + fetchRank * 2 + 1];
+                }
+                else if (WIDE) ld256_cs(rays + rayidx * 2, o, d);        // 32-byte aligned ray buffer (checked by the launcher)
                 else { o = __ldcs(rays + rayidx * 2 + 0); d = __ldcs(rays + rayidx * 2 + 1); }
                 origx = o.x; origy = o.y; origz = o.z; tmin = o.w;
                 dirx = d.x; diry = d.y; dirz = d.z; hitT = d.w;
@@ -277,10 +317,10 @@ Tuning tuning()
     return t;
 }
 
-template <int LAYOUT, int SMEM_N, bool PERSISTENT, bool FAST, bool WIDE>
+template <int LAYOUT, int SMEM_N, bool PERSISTENT, bool FAST, bool WIDE, bool BULKRAYS = false>
 cudaError_t launch_variant(const TraceLaunch& a, int* launches)
 {
-    auto kern = trace_kernel<LAYOUT, kBlock, SMEM_N, PERSISTENT, FAST, WIDE>;
+    auto kern = trace_kernel<LAYOUT, kBlock, SMEM_N, PERSISTENT, FAST, WIDE, BULKRAYS>;
     static int blocksPerSM = 0, epoch = -1;
     if (epoch != launch_epoch()) {
         epoch = launch_epoch();
@@ -303,7 +343,12 @@ cudaError_t launch_stack(const TraceLaunch& a, int* launches)
     switch (tuning().smemStack) {            // 8 unless an experiment asks otherwise
     case 0:  return launch_variant<LAYOUT, 0, PERSISTENT, FAST, WIDE>(a, launches);
     case 16: return launch_variant<LAYOUT, 16, PERSISTENT, FAST, WIDE>(a, launches);
-    default: return launch_variant<LAYOUT, 8, PERSISTENT, FAST, WIDE>(a, launches);
+    default:
+        if (PERSISTENT && WIDE && !FAST && LAYOUT == Layout_Compact) {
+            static const bool bulkRays = [] { const char* e = getenv("NT_TRACE_BULKRAYS"); return e && atoi(e) != 0; }();
+            if (bulkRays) return launch_variant<LAYOUT, 8, PERSISTENT, FAST, WIDE, (PERSISTENT && WIDE && !FAST && LAYOUT == Layout_Compact)>(a, launches);
+        }
+        return launch_variant<LAYOUT, 8, PERSISTENT, FAST, WIDE>(a, launches);
     }
 }
 

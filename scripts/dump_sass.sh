@@ -19,7 +19,7 @@ parts = re.split(r'\n\s*Function : ', txt)[1:]
 names = subprocess.run(['c++filt'], input='\n'.join(p.split('\n', 1)[0] for p in parts), capture_output=True, text=True).stdout.split('\n')
 # default variants of the tunable families: <layout, 128, smem 8, persistent, fast 0, wide 1> etc.
 KEEP = {
-    'trace_kernel': lambda a: a.split(', ')[1:3] == ['128', '8'] and a.split(', ')[-1] in ('1', 'true'),
+    'trace_kernel': lambda a: a.split(', ')[1:3] == ['128', '8'] and a.split(', ')[5] in ('1', 'true') and a.split(', ')[6] in ('0', 'false'),
     'trace_wide4_kernel': lambda a: a.startswith('128, 8,') and a.split(', ')[-1] in ('1', 'true'),
     'trace_mr_kernel': lambda a: a.startswith('128, 8,'),
     'trace_sw_kernel': lambda a: a.startswith('128, 8,'),
