@@ -485,6 +485,12 @@ def run_b200(args):
         config3 = config3_leg(torch, dist, capi, host, multigpu, camera, rank, world, dev, args, barrier, all_max)
         capi.set_kernel(args.kernel)
 
+    # ---- builder figures next to the trace figures (rank 0, single-GPU runs): the bench tree, the plain LBVH of the same scene and a
+    # 10 M-triangle soup (the north_star's build target), each with the algorithmic-bytes fraction of the measured HBM peak
+    build_block = None
+    if rank == 0 and world == 1 and args.build_leg:
+        build_block = build_leg(torch, capi, scene, bits, args)
+
     out = None
     if rank == 0:
         peak, peak_src = load_peaks()
@@ -554,6 +560,7 @@ def run_b200(args):
                               "all-gathered over NCCL and compared with the single-GPU trace" if world > 1 else "single GPU: the deferred, overlapped submission against synchronous calls"},
             "weak": None if weak_value is None else {"value": weak_value, "unit": "Mrays/s", "what": "every rank traces a whole frame (per-GPU work fixed)"},
             "config3": config3,
+            "build": build_block,
             "cpu_baseline": cpu["baseline"],
             "reference_gpu": ref_gpu_rows,
         }
@@ -686,6 +693,41 @@ def config3_leg(torch, dist, capi, host, multigpu, camera, rank, world, dev, arg
 
 
 # --------------------------------------------------------------------------------------------------
+LBVH_BYTES_PER_TRI = 350.0            # 330 + 150 / leafSize algorithmic bytes per triangle at leaf size 8
+
+
+def build_leg(torch, capi, scene, bits, args):
+    """GPU build times (CUDA events around the whole pipeline, mean of 5 after one warm-up) and what they are of the HBM roofline."""
+    from ntrace_b200 import scenes
+    peak, _ = load_peaks()
+
+    def timed(builder, verts, tris, lo, hi, b, collapse):
+        capi.bvh_set_collapse(collapse, LEAF_SIZE)
+        ts = [capi.bvh_build(builder, verts, tris, lo, hi, b, LEAF_SIZE, EPSILON) for _ in range(6)][1:]
+        n = int(tris.shape[0])
+        row = {"ms": float(np.mean(ts) * 1e3), "ms_best": float(np.min(ts) * 1e3), "mtris": n / float(np.mean(ts)) * 1e-6}
+        if builder == capi.BUILDER_LBVH:
+            row["algorithmic_gbs"] = n * LBVH_BYTES_PER_TRI / float(np.mean(ts)) * 1e-9
+            row["frac_of_hbm_peak"] = row["algorithmic_gbs"] / peak
+        return row
+
+    out = {"bytes_per_tri_lbvh": LBVH_BYTES_PER_TRI, "hbm_peak_gbs": peak,
+           "how": "nt_bvh_build, CUDA events around the whole pipeline (device-resident vertices / indices), mean of 5 builds after one warm-up; "
+                  "frac_of_hbm_peak = triangles x algorithmic bytes per triangle (DESIGN.md 3.2) / time / measured HBM peak"}
+    v, t, lo, hi = scene.vtxPos, scene.triVtxIndex, scene.bboxMin, scene.bboxMax
+    out["conference_283k_bench_tree"] = timed(capi.BUILDER_HLBVH, v, t, lo, hi, bits, args.collapse)
+    out["conference_283k_hlbvh4_reference_renderer"] = timed(capi.BUILDER_HLBVH, v, t, lo, hi, 4, 0)
+    out["conference_283k_lbvh"] = timed(capi.BUILDER_LBVH, v, t, lo, hi, 10, 0)
+    sv, st = scenes.soup_uniform(10_000_000, 5)
+    slo, shi = scenes.bbox(sv)
+    dv, dt = torch.from_numpy(sv).cuda(), torch.from_numpy(st).cuda()
+    out["soup_10m_lbvh"] = timed(capi.BUILDER_LBVH, dv, dt, slo, shi, 10, 0)
+    out["soup_10m_hlbvh4"] = timed(capi.BUILDER_HLBVH, dv, dt, slo, shi, 4, 0)
+    del dv, dt
+    capi.bvh_set_collapse(args.collapse, LEAF_SIZE)
+    return out
+
+
 def cpu_baseline_leg(verts, tris, cam, args, gpu_bvh=None, sample_batches=None, gpu_results=None, kernel=None):
     """The ONLY place bench.py touches the oracle: (a) times the reference's CPU path (restated SplitBVHBuilder +
     BVH::trace) on a bounded sample, (b) counts nodes/triangles per ray on the GPU-built BVH for the roofline."""
@@ -856,6 +898,7 @@ def main():
     ap.add_argument("--partition", default="deal", choices=["deal", "slices"], help="N > 1: how a ray type's frame buffer is split over the GPUs (see rank_ranges)")
     ap.add_argument("--config3", type=int, default=1, help="N > 1 only: also strong-scale BASELINE.json configs[3] (10.5 M triangles, diffuse) with the NCCL broadcast timed")
     ap.add_argument("--reference-gpu", type=int, default=1, help="rank 0: also time the reference's own kernels recompiled for sm_100a (oracle/_ref), when present")
+    ap.add_argument("--build-leg", type=int, default=1, help="N = 1: also report GPU build times (bench tree, LBVH, 10 M-triangle soup) in the line")
     ap.add_argument("--profile", action="store_true", help="dev: only the device-timed region (for runs under ncu); prints no JSON")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -59,8 +59,10 @@ struct Context {
     // persistent CTAs of the current one run out of rays (the tail of one launch overlaps the head of the next)
     bool overlap = false, overlapPending = false;
     int overlapNext = 0;
-    cudaStream_t kStream[2] = {};
-    cudaEvent_t kDone[2] = {}, kFork = nullptr;
+    static constexpr int kMaxKernelStreams = 4;
+    int numKernelStreams = 2;            // deferred mode 2: launches alternate over this many kernel streams (NT_OVERLAP_STREAMS, experiment knob)
+    cudaStream_t kStream[kMaxKernelStreams] = {};
+    cudaEvent_t kDone[kMaxKernelStreams] = {}, kFork = nullptr;
     // what the overlapped launches still in flight read and write, so that a later call waits only for the launches whose buffers it
     // touches (a ray generator filling buffer B does not wait for the trace of buffer A)
     struct InFlight { const char* rLo = nullptr; const char* rHi = nullptr; const char* wLo = nullptr; const char* wHi = nullptr; cudaEvent_t ev = nullptr; bool live = false; };
@@ -225,7 +227,7 @@ int ensure_wide_form()
 int join_kernel_streams()
 {
     if (!g.overlapPending) return 0;
-    for (int k = 0; k < 2; k++) NT_CUDA(cudaStreamWaitEvent(g.stream, g.kDone[k], 0));
+    for (int k = 0; k < g.numKernelStreams; k++) NT_CUDA(cudaStreamWaitEvent(g.stream, g.kDone[k], 0));
     for (int i = 0; i < Context::kRing; i++) g.ring[i].live = false;
     g.overlapPending = false;
     return 0;
@@ -356,7 +358,8 @@ int nt_init(int device_ordinal)
     NT_CUDA(cudaEventCreate(&g.evA));
     NT_CUDA(cudaEventCreate(&g.evB));
     for (int i = 0; i < 8; i++) NT_CUDA(cudaEventCreate(&g.userEv[i]));
-    for (int k = 0; k < 2; k++) {
+    if (const char* e = getenv("NT_OVERLAP_STREAMS")) { const int v = atoi(e); if (v >= 2 && v <= Context::kMaxKernelStreams) g.numKernelStreams = v; }
+    for (int k = 0; k < Context::kMaxKernelStreams; k++) {
         NT_CUDA(cudaStreamCreateWithFlags(&g.kStream[k], cudaStreamNonBlocking));
         NT_CUDA(cudaEventCreateWithFlags(&g.kDone[k], cudaEventDisableTiming));
     }
@@ -395,7 +398,7 @@ void nt_shutdown(void)
     cudaStreamSynchronize(g.stream);
     cudaStreamSynchronize(g.sIn);
     cudaStreamSynchronize(g.sOut);
-    for (int k = 0; k < 2; k++) { cudaStreamSynchronize(g.kStream[k]); cudaStreamDestroy(g.kStream[k]); cudaEventDestroy(g.kDone[k]); }
+    for (int k = 0; k < Context::kMaxKernelStreams; k++) { cudaStreamSynchronize(g.kStream[k]); cudaStreamDestroy(g.kStream[k]); cudaEventDestroy(g.kDone[k]); }
     cudaEventDestroy(g.kFork);
     for (int i = 0; i < Context::kRing; i++) { cudaEventDestroy(g.ring[i].ev); cudaEventDestroy(g.prod[i].ev); }
     DevBuf* bufs[] = {&g.nodes, &g.woop, &g.triIndex, &g.sortedKeys, &g.sortedIdx, &g.stRays, &g.stResults, &g.stA, &g.stB,
@@ -1043,7 +1046,7 @@ int nt_trace_batch(const float* rays, int32_t* results, int numRays, int needClo
 
     a.numRays = numRays; a.rays = (const float4*)raysDev; a.results = (int4*)resDev;
     if (overlapped) {
-        const int k = g.overlapNext; g.overlapNext ^= 1;
+        const int k = g.overlapNext; g.overlapNext = (g.overlapNext + 1) % g.numKernelStreams;
         a.stream = g.kStream[k];
         // the rays' generator comes first.  When it was a queued nt_raygen_ao the launch waits for that kernel alone; otherwise for
         // everything the main stream has queued so far

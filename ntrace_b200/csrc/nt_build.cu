@@ -549,6 +549,9 @@ __device__ __forceinline__ void fill_bins_one(const TopArgs& a, int c, int t, co
     }
 }
 
+// Measured and dropped (scripts/top_level_bench.py, profiles/r2_summary.md): a hand-written grid barrier (monotonic counter, one arrival
+// per CTA, acquire spin) instead of cooperative_groups' grid.sync(): 0.906 vs 0.879 ms for the bench tree -- the ~85 barriers of a build are
+// not what the kernel waits for, the dependent loads inside its phases are; two CTAs per SM: 0.914-0.935 ms.
 __global__ void __launch_bounds__(kTopThreads) hlbvh_top_kernel(TopArgs a)
 {
     namespace cg = cooperative_groups;
@@ -1098,7 +1101,10 @@ cudaError_t build_bvh_device(const float* dVerts, int numVerts, const int* dTris
         if (!topBlocksPerSM) {
             NT_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&topBlocksPerSM, hlbvh_top_kernel, kTopThreads, 0));
             if (topBlocksPerSM < 1) topBlocksPerSM = 1;
-            if (topBlocksPerSM > 1) topBlocksPerSM = 1;       // fewer CTAs = cheaper grid.sync; the phases are latency bound
+            int want = 1;                                     // fewer CTAs = cheaper grid barrier; the phases are latency bound
+            if (const char* e = getenv("NT_TOP_CTAS")) want = atoi(e);
+            if (want < 1) want = 1;
+            if (topBlocksPerSM > want) topBlocksPerSM = want;
         }
         const int grid = numSMs * topBlocksPerSM;
         NT_TRY(sc.blockSum.reserve((size_t)grid * 4));

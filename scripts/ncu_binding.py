@@ -101,12 +101,13 @@ def main():
     ap.add_argument("--batch", type=int, default=12)
     ap.add_argument("--out", required=True)
     ap.add_argument("--regex", default="trace_")
+    ap.add_argument("--hlbvh-bits", type=int, default=2)
     args = ap.parse_args()
     os.makedirs(os.path.dirname(os.path.abspath(args.out)), exist_ok=True)
     raw = os.path.splitext(args.out)[0] + "_ncu.csv"
     l2_peak = measure_l2_peak()
     cmd = ["ncu", "--metrics", ",".join(METRICS), "--clock-control", "none", "-k", f"regex:{args.regex}", "--csv", "--log-file", raw,
-           sys.executable, os.path.join(ROOT, "scripts", "profile_kernel.py"), "--kernel", args.kernel, "--scene", args.scene, "--batch", str(args.batch)]
+           sys.executable, os.path.join(ROOT, "scripts", "profile_kernel.py"), "--kernel", args.kernel, "--scene", args.scene, "--batch", str(args.batch), "--hlbvh-bits", str(args.hlbvh_bits)]
     r = subprocess.run(cmd, capture_output=True, text=True)
     sys.stdout.write(r.stdout[-2000:])
     if r.returncode != 0:

@@ -26,6 +26,9 @@ def krays(path):
 def main():
     out = {}
     tmp = tempfile.mkdtemp()
+    kernel = os.environ.get("NT_BENCH_KERNEL", "b200_auto")          # the bench's default kernel
+    COMMON.append(f"-DBenchmark.kernel={kernel}")
+    out["kernel"] = kernel
     for pipelined in (False, True):
         stats = os.path.join(tmp, f"py_{int(pipelined)}.log")
         env = Environment()
@@ -45,10 +48,11 @@ def main():
                 out["cpp_error"] = (r.stdout + r.stderr)[-500:]
                 break
             out["cpp_ntrace_bench_" + ("pipelined" if pipelined else "synchronous")] = dict(zip(("primary", "AO", "diffuse"), [x * 1e-3 for x in krays(stats)]))
-    for k, v in out.items():
+    # frame rate of the three ray types together, as bench.py counts it: rays / (sum of times); 786 432 primary hits -> 24 x 1 Mi rays per secondary type
+    for k, v in list(out.items()):
         if isinstance(v, dict):
-            # frame rate of the three ray types together, as bench.py counts it: rays / (sum of times); rays per type are equal for AO and diffuse
-            pass
+            n = {"primary": 786432.0, "AO": 786432.0 * 32, "diffuse": 786432.0 * 32}
+            out[k]["frame_mrays"] = sum(n.values()) / sum(n[t] / v[t] for t in n)
     print(json.dumps(out, indent=1))
     if len(sys.argv) > 1:
         json.dump(out, open(sys.argv[1], "w"), indent=1)
