@@ -459,11 +459,11 @@ __global__ void __launch_bounds__(256) cluster_box_kernel(int n, const uint* __r
 
 constexpr int kBins = 8;            // BIN_CNT (emitTreeKernel.cuh:9)
 constexpr int kTopThreads = 256;
-constexpr int kSmemTasks = 32;      // levels with at most this many tasks bin through shared memory first
+constexpr int kSmemTasksDefault = 256;   // levels with at most this many tasks bin through (dynamic) shared memory first: 168 ints per task
 constexpr int kTrackFirst = 64;     // tasks with at most this many clusters know their lowest cluster index (one atomicMin per member)
 
 struct TopArgs {
-    int C, leafSize, linkMul;
+    int C, leafSize, linkMul, smemTasks;
     const int* clsStart; const int* clsBoxI;
     int* clsTask[2];          // current / next task of each cluster (-1 = done)
     int* clsBin;              // C * 3
@@ -519,32 +519,47 @@ __device__ __forceinline__ int distribute_one(const TopArgs& a, int c, int task,
 
 // fillBins for one cluster that belongs to task t (box tb = 6 floats) of the level being prepared (emitTreeKernel.cu:735-790):
 // bin of the cluster's centre per axis, kept in clsBin for the coming distribute, and the bin's box / count updated.
-__device__ __forceinline__ void fill_bins_one(const TopArgs& a, int c, int t, const float* tb, bool inSmem, int* s_binBox, int* s_binCnt)
+// `cb` = the cluster's box (ordered ints), loaded by the caller before anything that depends on the task.  The three bins are computed
+// first and read together, so the L2 path costs one round trip for the three axes instead of three (the phase is a chain of dependent
+// loads: task label -> task record -> bins; see profiles/r2_summary.md, builder section).
+__device__ __forceinline__ void fill_bins_one(const TopArgs& a, int c, int t, const float* tb, bool inSmem, int* s_binBox, int* s_binCnt,
+                                              int c0, int c1, int c2, int c3, int c4, int c5)
 {
-    const int* cb = a.clsBoxI + (size_t)c * 6;
-    const int c0 = cb[0], c1 = cb[1], c2 = cb[2], c3 = cb[3], c4 = cb[4], c5 = cb[5];
     const float lo[3] = {i2f_ord(c0), i2f_ord(c1), i2f_ord(c2)}, hi[3] = {i2f_ord(c3), i2f_ord(c4), i2f_ord(c5)};
+    const float t0 = tb[0], t1 = tb[1], t2 = tb[2], t3 = tb[3], t4 = tb[4], t5 = tb[5];
+    const float tl[3] = {t0, t1, t2}, th[3] = {t3, t4, t5};
+    int slot[3];
 #pragma unroll
     for (int k = 0; k < 3; k++) {
         const float mid = __fadd_rn(lo[k], __fdiv_rn(__fsub_rn(hi[k], lo[k]), 2.0f));
-        const float tl = tb[k], th = tb[3 + k];
-        const float step = __fdiv_rn(__fsub_rn(th, tl), 8.0f);
-        const int bid = quantise(mid, tl, step, kBins);
+        const float step = __fdiv_rn(__fsub_rn(th[k], tl[k]), 8.0f);
+        const int bid = quantise(mid, tl[k], step, kBins);
         a.clsBin[c * 3 + k] = bid;
-        const int slot = (t * 3 + k) * kBins + bid;
-        if (inSmem) {
-            int* b = s_binBox + slot * 6;
+        slot[k] = (t * 3 + k) * kBins + bid;
+    }
+    if (inSmem) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            int* b = s_binBox + slot[k] * 6;
             atomicMin(b + 0, c0); atomicMin(b + 1, c1); atomicMin(b + 2, c2);
             atomicMax(b + 3, c3); atomicMax(b + 4, c4); atomicMax(b + 5, c5);
-            atomicAdd(s_binCnt + slot, 1);
-        } else {
-            // a bin only ever shrinks / grows within a level, so a value read from L2 that already covers ours makes the atomic
-            // redundant (a stale read can only cost an unnecessary atomic, never skip a necessary one)
-            int* b = a.binBoxI + (size_t)slot * 6;
-            const int2 q0 = __ldcg(reinterpret_cast<const int2*>(b)), q1 = __ldcg(reinterpret_cast<const int2*>(b) + 1), q2 = __ldcg(reinterpret_cast<const int2*>(b) + 2);
-            if (c0 < q0.x) atomicMin(b + 0, c0); if (c1 < q0.y) atomicMin(b + 1, c1); if (c2 < q1.x) atomicMin(b + 2, c2);
-            if (c3 > q1.y) atomicMax(b + 3, c3); if (c4 > q2.x) atomicMax(b + 4, c4); if (c5 > q2.y) atomicMax(b + 5, c5);
-            atomicAdd(a.binCnt + slot, 1);
+            atomicAdd(s_binCnt + slot[k], 1);
+        }
+    } else {
+        // a bin only ever shrinks / grows within a level, so a value read from L2 that already covers ours makes the atomic
+        // redundant (a stale read can only cost an unnecessary atomic, never skip a necessary one)
+        int2 q[3][3];
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            const int2* b = reinterpret_cast<const int2*>(a.binBoxI + (size_t)slot[k] * 6);
+            q[k][0] = __ldcg(b); q[k][1] = __ldcg(b + 1); q[k][2] = __ldcg(b + 2);
+        }
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            int* b = a.binBoxI + (size_t)slot[k] * 6;
+            if (c0 < q[k][0].x) atomicMin(b + 0, c0); if (c1 < q[k][0].y) atomicMin(b + 1, c1); if (c2 < q[k][1].x) atomicMin(b + 2, c2);
+            if (c3 > q[k][1].y) atomicMax(b + 3, c3); if (c4 > q[k][2].x) atomicMax(b + 4, c4); if (c5 > q[k][2].y) atomicMax(b + 5, c5);
+            atomicAdd(a.binCnt + slot[k], 1);
         }
     }
 }
@@ -558,8 +573,9 @@ __global__ void __launch_bounds__(kTopThreads) hlbvh_top_kernel(TopArgs a)
     cg::grid_group grid = cg::this_grid();
     __shared__ int s_warp[kTopThreads / 32];
     __shared__ int s_red[2];
-    __shared__ int s_binBox[kSmemTasks * 3 * kBins * 6];
-    __shared__ int s_binCnt[kSmemTasks * 3 * kBins];
+    extern __shared__ int s_bins[];                                  // a.smemTasks x (3 x kBins x 6 box words, then 3 x kBins counts)
+    int* const s_binBox = s_bins;
+    int* const s_binCnt = s_bins + a.smemTasks * 3 * kBins * 6;
     const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
     const int gsize = gridDim.x * blockDim.x;
     int cur = 0;
@@ -603,7 +619,11 @@ __global__ void __launch_bounds__(kTopThreads) hlbvh_top_kernel(TopArgs a)
 
     // ---- fillBins of the root task (every later level is binned by the distribute phase of its parent level)
     smemBinsInit(1);
-    for (int c = gtid; c < a.C; c += gsize) fill_bins_one(a, c, 0, a.tBox[0], true, s_binBox, s_binCnt);
+    for (int c = gtid; c < a.C; c += gsize) {
+        const int2* cb = reinterpret_cast<const int2*>(a.clsBoxI + (size_t)c * 6);
+        const int2 b0 = __ldg(cb), b1 = __ldg(cb + 1), b2 = __ldg(cb + 2);
+        fill_bins_one(a, c, 0, a.tBox[0], true, s_binBox, s_binCnt, b0.x, b0.y, b1.x, b1.y, b2.x, b2.y);
+    }
     smemBinsFlush(1);
     grid.sync();
 
@@ -739,20 +759,25 @@ __global__ void __launch_bounds__(kTopThreads) hlbvh_top_kernel(TopArgs a)
 
         // ---- distribute + fillBins of the next level: plane splits per cluster; object-split fallback per task with clusters
         // ranked by index.  A cluster that descends is binned into its child task right away (the child boxes were written in phase b).
-        const bool nextInSmem = (created <= kSmemTasks);
+        const bool nextInSmem = (created <= a.smemTasks);
         if (nextInSmem) smemBinsInit(created);
         for (int c = gtid; c < a.C; c += gsize) {
             const int t = clsTask[c];
+            // what does not depend on the task is requested at once: the cluster's box and its three bin ids of this level
+            const int2* cb = reinterpret_cast<const int2*>(a.clsBoxI + (size_t)c * 6);
+            const int2 b0 = __ldg(cb), b1 = __ldg(cb + 1), b2 = __ldg(cb + 2);
+            const int bin0 = __ldcg(a.clsBin + c * 3), bin1 = __ldcg(a.clsBin + c * 3 + 1), bin2 = __ldcg(a.clsBin + c * 3 + 2);
             if (t < 0) { clsNext[c] = -1; continue; }
             const int split = a.rSplit[t];
             if (split < 0) continue;                       // handled below
-            const bool goLeft = a.clsBin[c * 3 + a.rAxis[t]] <= split;
-            const int cntL = a.rCntL[t], cntR = a.rCntR[t];
-            const int nt = distribute_one(a, c, t, goLeft, cntL, cntR, tId[t]);
+            const int axis = a.rAxis[t];
+            const int cntL = a.rCntL[t], cntR = a.rCntR[t], topId = tId[t];
+            const bool goLeft = (axis == 0 ? bin0 : axis == 1 ? bin1 : bin2) <= split;
+            const int nt = distribute_one(a, c, t, goLeft, cntL, cntR, topId);
             clsNext[c] = nt;
             if (nt >= 0) {
                 if ((goLeft ? cntL : cntR) <= kTrackFirst) atomicMin(oFirst + nt, c);
-                fill_bins_one(a, c, nt, oBox + (size_t)nt * 6, nextInSmem, s_binBox, s_binCnt);
+                fill_bins_one(a, c, nt, oBox + (size_t)nt * 6, nextInSmem, s_binBox, s_binCnt, b0.x, b0.y, b1.x, b1.y, b2.x, b2.y);
             }
         }
         {
@@ -775,7 +800,9 @@ __global__ void __launch_bounds__(kTopThreads) hlbvh_top_kernel(TopArgs a)
                         clsNext[c] = nt;
                         if (nt >= 0) {
                             if ((goLeft ? cntL : cntR) <= kTrackFirst) atomicMin(oFirst + nt, c);
-                            fill_bins_one(a, c, nt, oBox + (size_t)nt * 6, nextInSmem, s_binBox, s_binCnt);
+                            const int2* cb = reinterpret_cast<const int2*>(a.clsBoxI + (size_t)c * 6);
+                            const int2 b0 = __ldg(cb), b1 = __ldg(cb + 1), b2 = __ldg(cb + 2);
+                            fill_bins_one(a, c, nt, oBox + (size_t)nt * 6, nextInSmem, s_binBox, s_binCnt, b0.x, b0.y, b1.x, b1.y, b2.x, b2.y);
                         }
                     }
                     seen += __popc(mask);
@@ -1097,19 +1124,25 @@ cudaError_t build_bvh_device(const float* dVerts, int numVerts, const int* dTris
         launches += 3;
         NT_TRY(cudaGetLastError());
 
-        static int topBlocksPerSM = 0;
+        // Shared-memory staging of the bins while a level has at most `smemTasks` tasks (measured on the bench tree, scripts/top_level_bench.py:
+        // 16 tasks 0.932 ms, 32 0.890, 64 0.864, 128 0.855, 256 0.841 (172 KB, one CTA per SM anyway), 320 0.867).  NT_TOP_SMEM_TASKS overrides.
+        static int topBlocksPerSM = 0, smemTasks = kSmemTasksDefault;
         if (!topBlocksPerSM) {
-            NT_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&topBlocksPerSM, hlbvh_top_kernel, kTopThreads, 0));
+            if (const char* e = getenv("NT_TOP_SMEM_TASKS")) { const int v = atoi(e); if (v >= 1 && v <= 320) smemTasks = v; }
+            const int smemBytes = smemTasks * 3 * kBins * 7 * 4;
+            NT_TRY(cudaFuncSetAttribute(hlbvh_top_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smemBytes));
+            NT_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&topBlocksPerSM, hlbvh_top_kernel, kTopThreads, smemBytes));
             if (topBlocksPerSM < 1) topBlocksPerSM = 1;
             int want = 1;                                     // fewer CTAs = cheaper grid barrier; the phases are latency bound
             if (const char* e = getenv("NT_TOP_CTAS")) want = atoi(e);
             if (want < 1) want = 1;
             if (topBlocksPerSM > want) topBlocksPerSM = want;
         }
+        const int topSmemBytes = smemTasks * 3 * kBins * 7 * 4;
         const int grid = numSMs * topBlocksPerSM;
         NT_TRY(sc.blockSum.reserve((size_t)grid * 4));
         TopArgs ta;
-        ta.C = C; ta.leafSize = p.leafSize; ta.linkMul = linkMul;
+        ta.C = C; ta.leafSize = p.leafSize; ta.linkMul = linkMul; ta.smemTasks = smemTasks;
         ta.clsStart = sc.clsStart.as<int>(); ta.clsBoxI = sc.clsBox.as<int>();
         ta.clsTask[0] = sc.clsTask0.as<int>(); ta.clsTask[1] = sc.clsTask1.as<int>();
         ta.clsBin = sc.clsBin.as<int>(); ta.clsParent = sc.clsParent.as<int>();
@@ -1127,7 +1160,7 @@ cudaError_t build_bvh_device(const float* dVerts, int numVerts, const int* dTris
         ta.scal = topScal;
         for (int k = 0; k < 3; k++) { ta.sceneLo[k] = p.lo[k]; ta.sceneHi[k] = p.hi[k]; }
         void* kargs[] = {&ta};
-        NT_TRY(cudaLaunchCooperativeKernel((const void*)hlbvh_top_kernel, dim3(grid), dim3(kTopThreads), kargs, 0, stream));
+        NT_TRY(cudaLaunchCooperativeKernel((const void*)hlbvh_top_kernel, dim3(grid), dim3(kTopThreads), kargs, topSmemBytes, stream));
         launches++;
     }
 
