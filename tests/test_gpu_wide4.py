@@ -185,3 +185,43 @@ def test_traversal_stack_overflow_is_reported_not_silent(gpu_host):
     with pytest.raises(capi.NtError, match="too deep"):
         capi.trace_batch(rays, res, 64, True)
     capi.set_kernel("b200_persistent_speculative_while_while")
+
+
+@pytest.mark.timeout(120)
+def test_device_conversion_refuses_malformed_trees(gpu_host):
+    # the same malformed inputs tests/test_wide4.py gives the host routine, through the conversion the library itself runs (on the device):
+    # a cycle must end in an error, not in a kernel that waits for ever
+    nodes = np.zeros((4, 16), dtype=np.int32)
+    f = nodes.view(np.float32)
+    f[:, 0:12:2] = 0.0
+    f[:, 1:12:2] = 1.0
+    for i in range(4):
+        nodes[i, 12] = (i + 1) * 64 if i + 1 < 4 else ~0
+        nodes[i, 13] = ~0
+    woop = np.full(4, np.int32(-2**31), dtype=np.int32)
+    idx = np.zeros(1, dtype=np.int32)
+    rays = np.zeros((64, 8), dtype=np.float32)
+    rays[:, 0:3] = (0.5, 0.5, -1.0)
+    rays[:, 4:7] = (0.0, 0.0, 1.0)
+    rays[:, 7] = 10.0
+    res = np.zeros((64, 4), dtype=np.int32)
+    try:
+        for word, value, pattern in ((3, 64, "cycle|outside"), (2, 4096, "outside"), (3, ~50, "outside")):
+            bad = nodes.copy()
+            bad[word, 12] = value
+            capi.set_kernel("b200_persistent_speculative_while_while")
+            capi.bvh_upload(capi.LAYOUT_COMPACT, bad.reshape(-1), woop, idx)
+            capi.set_kernel("b200_wide4")
+            with pytest.raises(capi.NtError, match=pattern):
+                capi.trace_batch(rays, res, 64, True)
+        # and the well-formed chain converts and traces (every ray misses: the leaves are empty)
+        capi.set_kernel("b200_persistent_speculative_while_while")
+        capi.bvh_upload(capi.LAYOUT_COMPACT, nodes.reshape(-1), woop, idx)
+        capi.set_kernel("b200_wide4")
+        capi.trace_batch(rays, res, 64, True)
+        assert (res[:, 0] == -1).all()
+        wn, depth = capi.bvh_wide4_download()
+        ref, ref_depth = capi.bvh_wide4_convert_host(capi.LAYOUT_COMPACT, nodes.reshape(-1), woop.nbytes)
+        assert depth == ref_depth and _canonical_wide(wn) == _canonical_wide(ref)
+    finally:
+        capi.set_kernel("b200_persistent_speculative_while_while")
