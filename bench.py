@@ -280,6 +280,7 @@ def run_b200(args):
     tracer.setBVH(bvh)
 
     # ---- resident inputs: the frame's primary rays, then every AO / diffuse batch (identical on every rank)
+    capi.raygen_set_order(args.raygen_order)
     rg = host.RayGen(MAX_BATCH)
     prim = host.RayBuffer()
     rg.primary(prim, cam.position, camera.nscreen_to_world(cam, W, H), W, H, cam.far, 0)
@@ -295,6 +296,22 @@ def run_b200(args):
                 break
             batches.append((name, rb.getRayBuffer(), rb.getSize(), closest))
     torch.cuda.synchronize()
+    # what the slot order costs in the generator: one full diffuse batch generated in either order (device time, mean of 5 after a warm-up);
+    # the reference times the trace kernel only (App.cpp:955-958), so this is reported beside the step, per batch of <= 1 Mi rays
+    raygen_us = {}
+    for order in (0, 1):
+        capi.raygen_set_order(order)
+        scratch, g2 = host.RayBuffer(), host.RayGen(MAX_BATCH)
+        g2.ao(scratch, prim, scene, args.spp, cam.far, True, host.FIXED_AO_SEED)
+        capi.synchronize()
+        capi.event_record(2)
+        for _ in range(5):
+            g2.m_aoStartIdx = 0
+            g2.ao(scratch, prim, scene, args.spp, cam.far, True, host.FIXED_AO_SEED)
+        capi.event_record(3)
+        raygen_us["coherent_order" if order else "reference_order"] = capi.event_elapsed(2, 3) / 5 * 1e6
+        del scratch
+    capi.raygen_set_order(args.raygen_order)
     traced = {k: sum(b[2] for b in batches if b[0] == k) for k in ("primary", "AO", "diffuse")}
     counted = {"primary": W * H, "AO": hits * args.spp, "diffuse": hits * args.spp}
     counted_step = sum(counted.values())
@@ -518,6 +535,9 @@ def run_b200(args):
                                    "1024x768, <=1Mi rays/launch, GPU %s leaf 8%s" % ("HLBVH(hlbvhBits %d)" % args.hlbvh_bits if args.builder == "hlbvh" else "LBVH", ", SAH-guided collapse" if args.collapse else ""),
                        "rays_traced_per_step": int(sum(traced.values())), "rays_counted_per_step": int(counted_step),
                        "launches_per_step_per_gpu": len(mine), "kernel": args.kernel,
+                       "ray_order": ("nt_raygen_set_order(1): the generator writes each tile of <= 2048 secondary rays (64 neighbouring hit points x 32 samples) in "
+                                     "direction-cell order (same rays and ids, slot permutation in idToSlot / slotToID, no extra pass; detail.raygen_us_per_batch)"
+                                     if args.raygen_order else "the reference generator's slot order (slot = id)"),
                        "submission": ("nt_set_deferred(2): the step's launches are queued on two kernel streams, consecutive launches overlap at their tails"
                                       if args.overlap else "nt_set_deferred(1): the step's launches are queued on one stream"),
                        "l2": "inputs exceed L2: %.0f MB of rays per step stream from HBM; the %.0f MB BVH is reused within a frame by design"
@@ -531,7 +551,7 @@ def run_b200(args):
                        "build_ms": float(np.mean(build_s[1:]) * 1e3), "build_mtris": len(tris) / float(np.mean(build_s[1:])) * 1e-6,
                        "timed_tree": timed_tree,
                        "bvh_broadcast_ms": bcast_ms, "bvh_broadcast_via": "nt_bvh_broadcast (C ABI, NCCL bound by dlopen)" if multigpu._comm_ready else ("torch.distributed" if world > 1 else None),
-                       "primary_hits": int(hits),
+                       "primary_hits": int(hits), "raygen_us_per_batch": raygen_us,
                        "one_stream_value": counted_step * args.steps / sec_serial * 1e-6,
                        "overlap_gain": sec_serial / sec},
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": int(ray_bytes), "d2h_bytes_per_step": int(ray_bytes // 2),
@@ -898,6 +918,9 @@ def main():
     ap.add_argument("--partition", default="deal", choices=["deal", "slices"], help="N > 1: how a ray type's frame buffer is split over the GPUs (see rank_ranges)")
     ap.add_argument("--config3", type=int, default=1, help="N > 1 only: also strong-scale BASELINE.json configs[3] (10.5 M triangles, diffuse) with the NCCL broadcast timed")
     ap.add_argument("--reference-gpu", type=int, default=1, help="rank 0: also time the reference's own kernels recompiled for sm_100a (oracle/_ref), when present")
+    ap.add_argument("--raygen-order", type=int, default=1, choices=[0, 1],
+                    help="slot order of the secondary rays (nt_raygen_set_order): 0 = the reference generator's order, 1 (default) = the same rays in "
+                         "direction-coherent order inside tiles of <= 2048 slots (written by the generator itself, no extra pass)")
     ap.add_argument("--build-leg", type=int, default=1, help="N = 1: also report GPU build times (bench tree, LBVH, 10 M-triangle soup) in the line")
     ap.add_argument("--profile", action="store_true", help="dev: only the device-timed region (for runs under ncu); prints no JSON")
     args = ap.parse_args()

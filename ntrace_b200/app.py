@@ -74,6 +74,7 @@ def run_benchmark(env: Environment, out=sys.stdout, device: int = 0):
     scene = host.Scene(verts, tris)
     leaf = env.GetInt("HLBVH.leafSize")
     host.capi.bvh_set_collapse(1 if env.GetBool("HLBVH.collapse") else 0, leaf)
+    host.capi.raygen_set_order(1 if env.GetBool("Raygen.coherentOrder") else 0)          # NEW knob (default: the reference's slot order)
     # Renderer.cacheDataStructure + Benchmark.cachePath (new; the reference hard-codes "bvhcache"): files named <hash>_<builder>.dat
     cache_path = env.GetString("Benchmark.cachePath") if env.Has("Benchmark.cachePath") and env.GetBool("Renderer.cacheDataStructure") else None
     renderer = host.Renderer(host.BuildSettings(builder=builder, hlbvh=host.HLBVHParams(True, env.GetInt("HLBVH.bits"), leaf, 0.001), cachePath=cache_path or None,

@@ -28,7 +28,7 @@ EXPORTS = [
     "nt_event_record", "nt_event_elapsed", "nt_set_deferred", "nt_synchronize",
     "nt_set_kernel", "nt_desired_layout", "nt_kernel_config",
     "nt_bvh_upload", "nt_bvh_alloc", "nt_bvh_build", "nt_bvh_set_collapse", "nt_bvh_set_build_layout", "nt_bvh_convert", "nt_bvh_sizes", "nt_bvh_download",
-    "nt_bvh_device_ptrs", "nt_bvh_build_debug", "nt_bvh_wide4_convert_host", "nt_bvh_wide4_download", "nt_bvh_generation", "nt_bvh_sah", "nt_hash_buffer", "nt_comm_unique_id", "nt_comm_init", "nt_comm_destroy", "nt_comm_allreduce", "nt_bvh_broadcast",
+    "nt_bvh_device_ptrs", "nt_bvh_build_debug", "nt_bvh_wide4_convert_host", "nt_bvh_wide4_download", "nt_raygen_set_order", "nt_bvh_generation", "nt_bvh_sah", "nt_hash_buffer", "nt_comm_unique_id", "nt_comm_init", "nt_comm_destroy", "nt_comm_allreduce", "nt_bvh_broadcast",
     "nt_trace_batch", "nt_trace_batch_async", "nt_trace_wait", "nt_raygen_primary", "nt_raygen_ao", "nt_raygen_shadow", "nt_ray_sort", "nt_count_hits", "nt_tri_normals",
 ]
 
@@ -251,6 +251,11 @@ def bvh_wide4_convert_host(layout: int, nodes, woop_bytes: int):
     _check(lib().nt_bvh_wide4_convert_host(C.c_int(layout), ptr(nodes), C.c_size_t(_nbytes(nodes)), C.c_size_t(woop_bytes), ptr(out), C.c_size_t(out.nbytes),
                                            C.byref(size), C.byref(depth)))
     return out, int(depth.value)
+
+
+def raygen_set_order(mode: int):
+    """0: nt_raygen_ao writes the reference's slot order; 1: direction-coherent order inside tiles of <= 2048 rays."""
+    _check(lib().nt_raygen_set_order(C.c_int(mode)))
 
 
 def bvh_wide4_download():

@@ -100,6 +100,7 @@ struct Context {
     bool basic = false, converted = false;
     // Wide4 form of the resident (Compact / Compact2) node buffer, derived on demand for the b200_wide4* kernels (nt_wide.cu)
     DevBuf wideNodes, wideScratch;
+    int raygenOrder = 0;                 // nt_raygen_set_order
     size_t wideBytes = 0;
     bool wideValid = false;
     int wideDepth = 0;
@@ -1241,6 +1242,7 @@ int nt_raygen_ao(float* outRays, int32_t* outIDToSlot, int32_t* outSlotToID, con
     a.outRays = (float4*)dOut; a.outIDToSlot = (int*)dA; a.outSlotToID = (int*)dB;
     a.inRays = (const float4*)dInRays; a.inResults = (const int4*)dInRes; a.normals = (const float*)dNormals;
     a.firstInputSlot = first; a.numInputRays = numInputRays; a.numSamples = numSamples; a.maxDist = maxDist; a.seed = randomSeed;
+    a.order = g.raygenOrder;
     NT_CUDA(launch_raygen_ao(a, g.stream));
     g.launches += 1;
     if (fine) {                               // queued on the main stream; the trace of these rays waits for this kernel (see nt_trace_batch)
@@ -1253,6 +1255,14 @@ int nt_raygen_ao(float* outRays, int32_t* outIDToSlot, int32_t* outSlotToID, con
     }
     if (copy_back(hOut, dOut, nOut * 32) || copy_back(hA, dA, nOut * 4) || copy_back(hB, dB, nOut * 4)) return 1;
     NT_CUDA(cudaStreamSynchronize(g.stream));
+    return 0;
+}
+
+int nt_raygen_set_order(int mode)
+{
+    std::lock_guard<std::mutex> lock(g_mutex);
+    if (mode != 0 && mode != 1) { set_error("ntrace_b200: ray generation order must be 0 (reference slot order) or 1 (direction-coherent tiles)"); return 1; }
+    g.raygenOrder = mode;
     return 0;
 }
 

@@ -141,6 +141,9 @@ static void runBenchmark(Environment& env)
     bool collapse = false;
     env.GetBoolValue("HLBVH.collapse", collapse);
     ntCheck(nt_bvh_set_collapse(collapse ? 1 : 0, leafSize));
+    bool coherent = false;                                                    // NEW knob: slot order of the secondary rays (nt_raygen_set_order)
+    env.GetBoolValue("Raygen.coherentOrder", coherent);
+    ntCheck(nt_raygen_set_order(coherent ? 1 : 0));
 
     FILE* stats = fopen(statsFile.c_str(), "a");
     if (!stats) fail("Cannot open stats file '%s'", statsFile.c_str());

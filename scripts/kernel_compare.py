@@ -26,6 +26,7 @@ def main():
     ap.add_argument("--collapse", type=int, default=1)
     ap.add_argument("--max-leaf", type=int, default=8)
     ap.add_argument("--leaf", type=int, default=8)
+    ap.add_argument("--raygen-order", type=int, default=0, help="nt_raygen_set_order: 0 reference slot order, 1 direction-coherent tiles")
     ap.add_argument("--check", action="store_true")
     ap.add_argument("--out", default=None)
     args = ap.parse_args()
@@ -40,6 +41,7 @@ def main():
     bvh.resident = True
     tracer = host.CudaBVHTracer()
     tracer.setBVH(bvh)
+    capi.raygen_set_order(args.raygen_order)
     rg = host.RayGen(1 << 20)
     prim = host.RayBuffer()
     rg.primary(prim, cam.position, camera.nscreen_to_world(cam, W, H), W, H, cam.far, 0)

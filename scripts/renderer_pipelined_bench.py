@@ -13,7 +13,7 @@ sys.path.insert(0, ROOT)
 from ntrace_b200 import app, mesh_io, scenes  # noqa: E402
 from ntrace_b200.environment import Environment  # noqa: E402
 
-COMMON = ["-DApp.frameWidth=1024", "-DApp.frameHeight=768", "-DBenchmark.camera=conference", "-DBenchmark.warmupRepeats=2", "-DBenchmark.measureRepeats=10",
+COMMON = [f"-DRaygen.coherentOrder={os.environ.get('NT_BENCH_COHERENT', 'true')}", "-DApp.frameWidth=1024", "-DApp.frameHeight=768", "-DBenchmark.camera=conference", "-DBenchmark.warmupRepeats=2", "-DBenchmark.measureRepeats=10",
           "-DRenderer.dataStructure=BVH", "-DRenderer.builder=HLBVH", "-DRenderer.rayType=primary;AO;diffuse", "-DRenderer.samples=32", "-DRenderer.sortRays=false",
           "-DHLBVH.bits=2", "-DHLBVH.collapse=true"]
 
