@@ -218,7 +218,7 @@ int nt_raygen_ao(float* outRays, int32_t* outIDToSlot, int32_t* outSlotToID,
                  float maxDist, uint32_t randomSeed);
 /* NEW (the reference's only reordering is RayBuffer::mortonSort, a CPU sort of 192-bit keys, RayBuffer.cpp:103-163): slot order of the
  * rays nt_raygen_ao writes.  0 (default) = the reference kernel's order, slot == id (RayGenKernels.cu:129-236).  1 = the same rays, but
- * inside every tile of <= 2048 consecutive outputs (neighbouring hit points x their samples) slots are handed out by direction cell
+ * inside every tile of <= 1024 consecutive outputs (neighbouring hit points x their samples) slots are handed out by direction cell
  * (stable counting sort on a 16 x 16 octahedral map of the direction), idToSlot / slotToID carrying the permutation as mortonSort's do:
  * the warps of the trace kernel then fetch rays that leave neighbouring points in one direction.  Costs no extra pass over the rays. */
 int nt_raygen_set_order(int mode);

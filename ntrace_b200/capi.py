@@ -254,7 +254,7 @@ def bvh_wide4_convert_host(layout: int, nodes, woop_bytes: int):
 
 
 def raygen_set_order(mode: int):
-    """0: nt_raygen_ao writes the reference's slot order; 1: direction-coherent order inside tiles of <= 2048 rays."""
+    """0: nt_raygen_ao writes the reference's slot order; 1: direction-coherent order inside tiles of <= 1024 rays."""
     _check(lib().nt_raygen_set_order(C.c_int(mode)))
 
 

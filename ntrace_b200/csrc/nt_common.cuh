@@ -83,7 +83,7 @@ struct AOArgs {
     float4* outRays; int* outIDToSlot; int* outSlotToID;
     const float4* inRays; const int4* inResults; const float* normals;
     int firstInputSlot, numInputRays, numSamples; float maxDist; unsigned seed;
-    int order = 0;            // 0: the reference's slot order (slot = id); 1: direction-coherent order inside tiles of <= 2048 rays (nt_raygen.cu)
+    int order = 0;            // 0: the reference's slot order (slot = id); 1: direction-coherent order inside tiles of <= 1024 rays (nt_raygen.cu)
 };
 cudaError_t launch_raygen_ao(const AOArgs& a, cudaStream_t s);
 struct ShadowArgs {

@@ -164,13 +164,13 @@ __global__ void __launch_bounds__(256) raygen_ao_kernel(AOArgs a)
     if (a.outSlotToID) a.outSlotToID[o] = o;
 }
 
-// Coherent slot order (AOArgs::order == 1; nt_raygen_set_order): the same rays, but inside every tile of <= 2048 consecutive outputs
-// (2048 / numSamples input hit points x numSamples samples: neighbouring pixels) the slots are handed out by direction cell -- a stable
+// Coherent slot order (AOArgs::order == 1; nt_raygen_set_order): the same rays, but inside every tile of <= 1024 consecutive outputs
+// (1024 / numSamples input hit points x numSamples samples: neighbouring pixels) the slots are handed out by direction cell -- a stable
 // counting sort on the Morton index of the direction's cell in a 16 x 16 octahedral map -- so that the 32 rays a warp of the trace
 // kernel fetches leave a few neighbouring surface points in ONE direction instead of one point in 32 directions.  idToSlot / slotToID
 // carry the permutation exactly like RayBuffer::mortonSort's (RayBuffer.cpp:103-163); the set of rays, their ids and every result per id
 // are unchanged.  This is the cheap reorder VERDICT round 1 asked for (item 1c): no extra pass over the rays, + a few microseconds in
-// the generator.
+// the generator (+13 us per 1 Mi rays).
 constexpr int kTileThreads = 1024;
 // direction -> cell of a res x res octahedral map, cells numbered along a Morton curve (neighbouring numbers = neighbouring directions)
 __device__ __forceinline__ unsigned dir_cell(float x, float y, float z, int res)
@@ -217,13 +217,30 @@ __global__ void __launch_bounds__(kTileThreads) raygen_ao_tiled_kernel(AOArgs a,
         if (rank[r] == 0) s_cnt[(r * (kTileThreads / 32) + w) * stride + key[r]] = (unsigned short)__popc(peers);
     }
     __syncthreads();
-    for (int k = tid; k <= cells; k += kTileThreads) {
+    // per cell: exclusive prefix over the segments (thread k owns cell k), then an exclusive prefix over the cells (<= 257 values:
+    // warp scans by the first nine warps + a scan of their nine totals)
+    __shared__ int s_wsum[16];
+    int cellTotal = 0;
+    if (tid <= cells) {
         int run = 0;
-        for (int sg = 0; sg < segs; sg++) { const int c = s_cnt[sg * stride + k]; s_cnt[sg * stride + k] = (unsigned short)run; run += c; }
-        s_base[k] = run;
+        for (int sg = 0; sg < segs; sg++) { const int c = s_cnt[sg * stride + tid]; s_cnt[sg * stride + tid] = (unsigned short)run; run += c; }
+        cellTotal = run;
+    }
+    int inc = cellTotal;
+    if (w < 9) {
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const int y = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += y; }
+        if (lane == 31) s_wsum[w] = inc;
     }
     __syncthreads();
-    if (tid == 0) { int run = 0; for (int k = 0; k <= cells; k++) { const int c = s_base[k]; s_base[k] = run; run += c; } }
+    if (w == 0) {
+        int x = (lane < 9) ? s_wsum[lane] : 0;
+#pragma unroll
+        for (int d = 1; d < 16; d <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, d); if (lane >= d) x += y; }
+        if (lane < 9) s_wsum[lane] = x;                         // inclusive over the nine warps
+    }
+    __syncthreads();
+    if (tid <= cells) s_base[tid] = inc - cellTotal + (w ? s_wsum[w - 1] : 0);
     __syncthreads();
 #pragma unroll
     for (int r = 0; r < R; r++) {
@@ -352,9 +369,11 @@ cudaError_t launch_raygen_ao(const AOArgs& a, cudaStream_t s)
     // tile size (1024 x R rays) and direction grid (res x res cells) of the coherent order, measured on the bench frame with b200_auto
     // (scripts/raygen_order_sweep.sh, profiles/r2_summary.md section 11; reference order: AO 4 661 / diffuse 2 673 Mrays/s):
     //   R 1: 4 x 4 4 992 / 2 769, 8 x 8 5 176 / 2 860, 16 x 16 5 170 / 2 860;  R 2: 5 051 / 2 786, 5 221 / 2 865, 5 261 / 2 895;
-    //   R 4: 5 042 / 2 791, 5 252 / 2 874, 5 238 / 2 899.  Default R 2 (64 hit points x 32 samples), 16 x 16 cells.
+    //   R 4: 5 042 / 2 791, 5 252 / 2 874, 5 238 / 2 899.  Device time of the generator per 1 Mi rays (scripts/raygen_cost.py): reference
+    //   order 42 us; R 1 55 us, R 2 70-73 us, R 4 68-70 us (two or four rays per thread cost the 1024-thread block its second resident
+    //   block).  Default R 1 (32 hit points x 32 samples), 16 x 16 cells: +13 us in the generator for -23 us (AO) / -26 us (diffuse) in the trace.
     // NT_RAYGEN_TILE_R / NT_RAYGEN_CELLS are experiment knobs
-    static const int tileR = [] { const char* e = getenv("NT_RAYGEN_TILE_R"); const int v = e ? atoi(e) : 2; return (v == 1 || v == 4) ? v : 2; }();
+    static const int tileR = [] { const char* e = getenv("NT_RAYGEN_TILE_R"); const int v = e ? atoi(e) : 1; return (v == 2 || v == 4) ? v : 1; }();
     static const int gridRes = [] { const char* e = getenv("NT_RAYGEN_CELLS"); const int v = e ? atoi(e) : 16; return (v == 4 || v == 8) ? v : 16; }();
     if (a.order == 1 && a.numSamples <= kTileThreads) {
         if (tileR == 4) return launch_ao_tiled<4>(a, n, gridRes, s);

@@ -40,7 +40,7 @@ OPTIONS = {
     "HLBVH.collapse": ("bool", "hlbvh_collapse=", "false"),
     "Raygen.random": ("bool", "raygen_random=", "false"),
     "Raygen.aoRadius": ("float", "raygen_aoradius=", "5.0"),
-    "Raygen.coherentOrder": ("bool", "raygen_coherent=", "false"),          # new: nt_raygen_set_order(1), direction-coherent slot order inside tiles of <= 2048 rays
+    "Raygen.coherentOrder": ("bool", "raygen_coherent=", "false"),          # new: nt_raygen_set_order(1), direction-coherent slot order inside tiles of <= 1024 rays
     "SBVH.alpha": ("float", "sbvh_alpha=", "1.0e-5"),
 }
 

@@ -102,12 +102,13 @@ def main():
     ap.add_argument("--out", required=True)
     ap.add_argument("--regex", default="trace_")
     ap.add_argument("--hlbvh-bits", type=int, default=2)
+    ap.add_argument("--raygen-order", type=int, default=1, help="slot order of the secondary rays (nt_raygen_set_order), as bench.py's default")
     args = ap.parse_args()
     os.makedirs(os.path.dirname(os.path.abspath(args.out)), exist_ok=True)
     raw = os.path.splitext(args.out)[0] + "_ncu.csv"
     l2_peak = measure_l2_peak()
     cmd = ["ncu", "--metrics", ",".join(METRICS), "--clock-control", "none", "-k", f"regex:{args.regex}", "--csv", "--log-file", raw,
-           sys.executable, os.path.join(ROOT, "scripts", "profile_kernel.py"), "--kernel", args.kernel, "--scene", args.scene, "--batch", str(args.batch), "--hlbvh-bits", str(args.hlbvh_bits)]
+           sys.executable, os.path.join(ROOT, "scripts", "profile_kernel.py"), "--kernel", args.kernel, "--scene", args.scene, "--batch", str(args.batch), "--hlbvh-bits", str(args.hlbvh_bits), "--raygen-order", str(args.raygen_order)]
     r = subprocess.run(cmd, capture_output=True, text=True)
     sys.stdout.write(r.stdout[-2000:])
     if r.returncode != 0:
@@ -122,7 +123,7 @@ def main():
         hbm_peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
     except Exception:
         pass
-    out = {"kernel": args.kernel, "scene": args.scene, "lib_sha16": lib_sha(), "l2_peak_gbs_measured": l2_peak, "hbm_peak_gbs": hbm_peak,
+    out = {"kernel": args.kernel, "scene": args.scene, "raygen_order": args.raygen_order, "lib_sha16": lib_sha(), "l2_peak_gbs_measured": l2_peak, "hbm_peak_gbs": hbm_peak,
            "how": "ncu --metrics (list in scripts/ncu_binding.py) --clock-control none over scripts/profile_kernel.py: one launch per ray type on the bench frame; "
                   "L2 peak = torch copy of a 2 x 24 MB L2-resident working set, best of 20 (read + write bytes)",
            "per_type": {}}

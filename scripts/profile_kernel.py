@@ -20,6 +20,7 @@ def main():
     ap.add_argument("--hlbvh-bits", type=int, default=2)
     ap.add_argument("--collapse", type=int, default=1)
     ap.add_argument("--max-leaf", type=int, default=8)
+    ap.add_argument("--raygen-order", type=int, default=1)
     args = ap.parse_args()
     import torch
     host.init(0)
@@ -34,6 +35,7 @@ def main():
     tracer.setKernel(args.kernel)
     tracer.setBVH(bvh)
     W, H = 1024, 768
+    capi.raygen_set_order(args.raygen_order)
     rg = host.RayGen(1 << 20)
     prim = host.RayBuffer()
     rg.primary(prim, cam.position, camera.nscreen_to_world(cam, W, H), W, H, cam.far, 0)

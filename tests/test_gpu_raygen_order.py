@@ -1,4 +1,4 @@
-"""GPU: nt_raygen_set_order(1) writes the SAME rays as the reference order, permuted inside tiles of <= 2048 slots, with consistent
+"""GPU: nt_raygen_set_order(1) writes the SAME rays as the reference order, permuted inside tiles of <= 1024 slots, with consistent
 id <-> slot maps; tracing them gives the same result per ray id."""
 import numpy as np
 import pytest
@@ -39,7 +39,7 @@ def test_coherent_order_is_a_tile_local_permutation_with_identical_results(gpu_h
     assert np.array_equal(i2s0, np.arange(n)) and np.array_equal(s2i0, np.arange(n))           # the reference order is the identity
     assert np.array_equal(np.sort(i2s1), np.arange(n)) and np.array_equal(s2i1[i2s1], np.arange(n))   # a permutation and its inverse
     assert np.array_equal(rays1[i2s1], rays0)                                                  # ray id -> the same 32 bytes
-    per_tile = (2048 // spp) * spp
+    per_tile = (1024 // spp) * spp
     assert np.array_equal(i2s1 // per_tile, np.arange(n) // per_tile)                          # nothing leaves its tile
     assert not np.array_equal(i2s1, np.arange(n))                                              # and something did move
     assert np.array_equal(res1[i2s1], res0)                                                    # same hit, t, u, v per ray id
