@@ -97,7 +97,8 @@ int nt_synchronize(void);
  * (csrc/nt_wide.cu): same leaves, same triangle test, so closest-hit t/u/v are bit-identical per (ray, triangle) and ids differ
  * from the binary kernels only on exact-t ties; any-hit rays report A hit (possibly another triangle than the binary order finds).
  * "b200_auto" (/ "_compact2") picks per batch: any-hit batches go through the binary kernel (reference visiting order), closest-hit batches
- * through Wide4.  "b200_mr*" / "b200_wide4_mr*" (both rays of a lane in shared memory, phase vote per step) and "b200_sw*" /
+ * through Wide4 -- except camera rays the library generated itself (nt_raygen_primary into a device buffer that is then traced in place):
+ * rays with one origin stay together far down the tree, where the cheaper binary node step wins.  "b200_mr*" / "b200_wide4_mr*" (both rays of a lane in shared memory, phase vote per step) and "b200_sw*" /
  * "b200_wide4_sw*" (one ray in registers, one parked in shared memory, exchanged at the phase boundaries) are the two-rays-per-lane
  * experiments: bit-identical to their one-ray twins, slower.
  * Unknown names fail. */

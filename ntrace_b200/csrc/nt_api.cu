@@ -101,6 +101,10 @@ struct Context {
     // Wide4 form of the resident (Compact / Compact2) node buffer, derived on demand for the b200_wide4* kernels (nt_wide.cu)
     DevBuf wideNodes, wideScratch;
     int raygenOrder = 0;                 // nt_raygen_set_order
+    // b200_auto: the device buffer the library's own primary-ray generator wrote last.  Camera rays share one origin and stay together
+    // far down the tree, where the cheaper binary node step wins over Wide4 (4.6 vs 4.1 Grays/s on the bench frame); a stale range can
+    // only cost speed, never change a result.
+    const char* primLo = nullptr; const char* primHi = nullptr;
     size_t wideBytes = 0;
     bool wideValid = false;
     int wideDepth = 0;
@@ -221,6 +225,17 @@ int ensure_wide_form()
     }
     g.wideValid = true;
     return 0;
+}
+
+// b200_auto: any-hit batches -> binary kernel (the reference's visiting order), closest-hit batches -> Wide4, except the camera rays the
+// library generated itself (see Context::primLo)
+inline int auto_kernel(const void* raysDev, int numRays, int needClosestHit)
+{
+    if (g.kernel != Kernel_Auto) return g.kernel;
+    if (!needClosestHit) return Kernel_PersistentSpeculative;
+    const char* p = (const char*)raysDev;
+    if (p && g.primLo && p >= g.primLo && p + (size_t)numRays * 32 <= g.primHi) return Kernel_PersistentSpeculative;
+    return Kernel_Wide4Persistent;
 }
 
 // every entry point but an overlapped deferred launch orders the main stream behind the launches still in flight on the two
@@ -998,7 +1013,7 @@ int nt_trace_batch(const float* rays, int32_t* results, int numRays, int needClo
     const bool raysOnHost = (raysDev == nullptr), resOnHost = (resDev == nullptr);
 
     TraceLaunch a;
-    a.kernel = (g.kernel == Kernel_Auto) ? (needClosestHit ? (int)Kernel_Wide4Persistent : (int)Kernel_PersistentSpeculative) : g.kernel;
+    a.kernel = auto_kernel(raysDev, numRays, needClosestHit);
     a.fast = g.fastMath ? 1 : 0; a.layout = g.basic ? (int)Layout_Compact : g.kernelLayout; a.anyHit = needClosestHit ? 0 : 1;
     a.nodes = g.nodes.as<float4>(); a.woop = g.woop.as<float4>(); a.triIndices = g.triIndex.as<int>();
     a.wideNodes = g.wideNodes.as<float4>();
@@ -1137,7 +1152,7 @@ int nt_trace_batch_async(const float* rays, int32_t* results, int numRays, int n
         else { NT_CUDA(s.results.reserve((size_t)numRays * 16)); dRes = s.results.as<int4>(); s.copyOut = true; }
     }
     TraceLaunch a;
-    a.kernel = (g.kernel == Kernel_Auto) ? (needClosestHit ? (int)Kernel_Wide4Persistent : (int)Kernel_PersistentSpeculative) : g.kernel;
+    a.kernel = auto_kernel(nullptr, numRays, needClosestHit);          // host-side batches carry no generator hint
     a.fast = g.fastMath ? 1 : 0; a.layout = g.basic ? (int)Layout_Compact : g.kernelLayout; a.anyHit = needClosestHit ? 0 : 1;
     a.nodes = g.nodes.as<float4>(); a.woop = g.woop.as<float4>(); a.triIndices = g.triIndex.as<int>();
     a.wideNodes = g.wideNodes.as<float4>();
@@ -1197,6 +1212,7 @@ int nt_raygen_primary(float* rays, int32_t* idToSlot, int32_t* slotToID, const f
     a.w = w; a.h = h; a.maxDist = maxDist; a.seed = randomSeed;
     NT_CUDA(launch_raygen_primary(a, g.pixelTable.as<int>(), g.stream));
     g.launches += 1;
+    if (!hRays) { g.primLo = (const char*)dRays; g.primHi = g.primLo + n * 32; } else { g.primLo = g.primHi = nullptr; }
     if (copy_back(hRays, dRays, n * 32) || copy_back(hI2S, dI2S, n * 4) || copy_back(hS2I, dS2I, n * 4)) return 1;
     NT_CUDA(cudaStreamSynchronize(g.stream));
     return 0;
@@ -1243,6 +1259,7 @@ int nt_raygen_ao(float* outRays, int32_t* outIDToSlot, int32_t* outSlotToID, con
     a.inRays = (const float4*)dInRays; a.inResults = (const int4*)dInRes; a.normals = (const float*)dNormals;
     a.firstInputSlot = first; a.numInputRays = numInputRays; a.numSamples = numSamples; a.maxDist = maxDist; a.seed = randomSeed;
     a.order = g.raygenOrder;
+    if (g.primLo && (const char*)dOut < g.primHi && g.primLo < (const char*)dOut + nOut * 32) g.primLo = g.primHi = nullptr;
     NT_CUDA(launch_raygen_ao(a, g.stream));
     g.launches += 1;
     if (fine) {                               // queued on the main stream; the trace of these rays waits for this kernel (see nt_trace_batch)
