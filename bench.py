@@ -413,10 +413,13 @@ def run_b200(args):
         capi.set_deferred(False)
 
     # ---- per-type kernel time (synchronous calls, CUDA events around each launch: the reference's accounting), rank 0's whole frame
+    # three passes over the frame, mean per launch (the primary type is ONE launch per frame: a single sample of 0.2 ms is noise)
     type_sec = {"primary": 0.0, "AO": 0.0, "diffuse": 0.0}
     res_dev = res_alt[0]
-    for name, rays, n, closest in batches:
-        type_sec[name] += capi.trace_batch(rays, res_dev[:n], n, closest)
+    TYPE_PASSES = 3
+    for _ in range(TYPE_PASSES):
+        for name, rays, n, closest in batches:
+            type_sec[name] += capi.trace_batch(rays, res_dev[:n], n, closest) / TYPE_PASSES
 
     # ---- e2e: this rank's share of the frame through the C ABI with HOST buffers (pinned), H2D of the rays and D2H of the results
     # inside the timed region, every step
