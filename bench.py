@@ -325,7 +325,24 @@ def run_b200(args):
     res_full = {k: torch.full((type_total[k], 4), -7, dtype=torch.int32, device=dev) for k in type_total}     # results in place, per type
     res_alt = [torch.empty((MAX_BATCH, 4), dtype=torch.int32, device=dev) for _ in range(2)]
 
-    def step_strong(keep=False):
+    CLOSEST = {"primary": True, "AO": False, "diffuse": True}
+
+    def frame_launches(share, dst_of):
+        """--submission frame: this rank's share of a ray type in ONE persistent launch (nt_trace_batches); a single batch of camera rays
+        keeps the plain call (b200_auto recognises the buffer its own generator wrote)."""
+        for name in ("primary", "AO", "diffuse"):
+            grp = [(rays, n, off) for (nm, rays, n, closest, off) in share if nm == name]
+            if not grp:
+                continue
+            if name == "primary" and len(grp) == 1:
+                capi.trace_batch(grp[0][0], dst_of(name, grp[0][2], grp[0][1]), grp[0][1], True)
+            else:
+                capi.trace_batches([g_[0] for g_ in grp], [dst_of(name, g_[2], g_[1]) for g_ in grp], [g_[1] for g_ in grp], CLOSEST[name])
+
+    def step_strong(keep=False, submission=None):
+        if (submission or args.submission) == "frame":
+            frame_launches(mine, lambda name, off, n: res_full[name][off:off + n])        # every batch needs its own result range
+            return
         for i, (name, rays, n, closest, off) in enumerate(mine):
             dst = res_full[name][off:off + n] if keep else res_alt[i & 1][:n]
             capi.trace_batch(rays, dst, n, closest)
@@ -352,13 +369,23 @@ def run_b200(args):
             print(f"profile run: {counted_step * args.steps / sec * 1e-6:.1f} Mrays/s (number taken under a profiler is not a bench value)")
         return None
 
-    # the same submission with one stream (no tail overlap), to report the overlap gain separately
-    capi.set_deferred(1)
-    step_strong()
+    # one launch per <= 1 Mi-ray batch (the reference's loop), queued on two kernel streams (the headline before nt_trace_batches) ...
+    capi.set_deferred(2)
+    step_strong(submission="batches")
     barrier()
     capi.event_record(0)
     for _ in range(args.steps):
-        step_strong()
+        step_strong(submission="batches")
+    capi.event_record(1)
+    sec_two_streams = capi.event_elapsed(0, 1)
+    barrier()
+    # ... and on one stream (no tail overlap)
+    capi.set_deferred(1)
+    step_strong(submission="batches")
+    barrier()
+    capi.event_record(0)
+    for _ in range(args.steps):
+        step_strong(submission="batches")
     capi.event_record(1)
     sec_serial = capi.event_elapsed(0, 1)
     barrier()
@@ -395,7 +422,16 @@ def run_b200(args):
         gathered_ok = bool(g.item() > 0.5)
 
     # ---- WEAK scaling beside it: every rank traces a whole frame (per-GPU work fixed)
+    whole = []
+    offs = {"primary": 0, "AO": 0, "diffuse": 0}
+    for name, rays, n, closest in batches:
+        whole.append((name, rays, n, closest, offs[name]))
+        offs[name] += n
+
     def step_weak():
+        if args.submission == "frame":
+            frame_launches(whole, lambda name, off, n: res_full[name][off:off + n])
+            return
         for i, (_, rays, n, closest) in enumerate(batches):
             capi.trace_batch(rays, res_alt[i & 1][:n], n, closest)
 
@@ -420,6 +456,17 @@ def run_b200(args):
     for _ in range(TYPE_PASSES):
         for name, rays, n, closest in batches:
             type_sec[name] += capi.trace_batch(rays, res_dev[:n], n, closest) / TYPE_PASSES
+
+    # ---- the same per type with the whole frame's batches in ONE launch (nt_trace_batches, synchronous: events around the launch)
+    frame_launch_mrays = {}
+    for name in ("AO", "diffuse"):
+        grp = [(rays, n, off) for (nm, rays, n, closest, off) in whole if nm == name]
+        if not grp:
+            continue
+        lists = ([g_[0] for g_ in grp], [res_full[name][g_[2]:g_[2] + g_[1]] for g_ in grp], [g_[1] for g_ in grp])
+        capi.trace_batches(*lists, CLOSEST[name])
+        t = float(np.mean([capi.trace_batches(*lists, CLOSEST[name]) for _ in range(3)]))
+        frame_launch_mrays[name] = counted[name] / t * 1e-6
 
     # ---- e2e: this rank's share of the frame through the C ABI with HOST buffers (pinned), H2D of the rays and D2H of the results
     # inside the timed region, every step
@@ -470,7 +517,7 @@ def run_b200(args):
         os.sched_setaffinity(0, prev_affinity)                        # the CPU baseline leg uses every core again
 
     # ---- max over ranks
-    sec, sec_serial, e2e_sec, e2e_sync_sec = all_max([sec, sec_serial, e2e_sec, e2e_sync_sec])
+    sec, sec_serial, sec_two_streams, e2e_sec, e2e_sync_sec = all_max([sec, sec_serial, sec_two_streams, e2e_sec, e2e_sync_sec])
     launches_all = int(all_sum([launches])[0])
     h2d_all, d2h_all, bi_h2d_all, bi_d2h_all = all_sum([pcie["h2d_gbs"], pcie["d2h_gbs"], pcie["bidir_h2d_gbs"], pcie["bidir_d2h_gbs"]])
     # rays/s the host link allows for this traffic mix (32 B in, 16 B out per ray): each direction alone, and their sum when both are busy
@@ -539,12 +586,16 @@ def run_b200(args):
             "config": {"workload": "conference stand-in room(283000, seed=2): primary + AO(32spp, r=5, any-hit) + diffuse(32spp, closest-hit), "
                                    "1024x768, <=1Mi rays/launch, GPU %s leaf 8%s" % ("HLBVH(hlbvhBits %d)" % args.hlbvh_bits if args.builder == "hlbvh" else "LBVH", ", SAH-guided collapse" if args.collapse else ""),
                        "rays_traced_per_step": int(sum(traced.values())), "rays_counted_per_step": int(counted_step),
-                       "launches_per_step_per_gpu": len(mine), "kernel": args.kernel,
+                       "launches_per_step_per_gpu": launches // max(1, args.steps), "batches_per_step_per_gpu": len(mine), "kernel": args.kernel,
                        "ray_order": ("nt_raygen_set_order(1): the generator writes each tile of <= 1024 secondary rays (32 neighbouring hit points x 32 samples) in "
                                      "direction-cell order (same rays and ids, slot permutation in idToSlot / slotToID, no extra pass; detail.raygen_us_per_batch)"
                                      if args.raygen_order else "the reference generator's slot order (slot = id)"),
-                       "submission": ("nt_set_deferred(2): the step's launches are queued on two kernel streams, consecutive launches overlap at their tails"
-                                      if args.overlap else "nt_set_deferred(1): the step's launches are queued on one stream"),
+                       "submission": (("nt_trace_batches: a rank's share of each ray type (its <= 1 Mi-ray batches, each with its own ray and result buffer) is ONE persistent "
+                                       "launch, so only one ramp-up / drain per type remains; detail.per_batch_two_streams_value / one_stream_value are the same step with one "
+                                       "launch per batch" if args.submission == "frame" else
+                                       "one launch per <= 1 Mi-ray batch (the reference's loop), ") +
+                                      ("; nt_set_deferred(2): launches are queued, consecutive per-batch launches alternate between two kernel streams"
+                                       if args.overlap else "; nt_set_deferred(1): launches are queued on one stream")),
                        "l2": "inputs exceed L2: %.0f MB of rays per step stream from HBM; the %.0f MB BVH is reused within a frame by design"
                              % (ray_bytes / 1e6, (node_b + woop_b + idx_b) / 1e6),
                        "parallelism": ("the frame is fixed (strong scaling): BVH built on rank 0 and replicated by NCCL broadcast; each ray type's frame buffer is split over the GPUs "
@@ -553,6 +604,9 @@ def run_b200(args):
                                        + "; no collective on the ray path") if world > 1 else "single GPU"},
             "detail": {"primary_mrays": counted["primary"] / type_sec["primary"] * 1e-6, "ao_mrays": counted["AO"] / type_sec["AO"] * 1e-6,
                        "diffuse_mrays": counted["diffuse"] / type_sec["diffuse"] * 1e-6,
+                       # the three figures above: one synchronous launch per <= 1 Mi-ray batch (the reference's accounting), ramp-up and drain of
+                       # every launch included; the same rays with the frame's batches of a type in one launch:
+                       "ao_mrays_frame_launch": frame_launch_mrays.get("AO"), "diffuse_mrays_frame_launch": frame_launch_mrays.get("diffuse"),
                        "build_ms": float(np.mean(build_s[1:]) * 1e3), "build_mtris": len(tris) / float(np.mean(build_s[1:])) * 1e-6,
                        "timed_tree": timed_tree,
                        "bvh_broadcast_ms": bcast_ms, "bvh_broadcast_via": "nt_bvh_broadcast (C ABI, NCCL bound by dlopen)" if multigpu._comm_ready else ("torch.distributed" if world > 1 else None),
@@ -561,6 +615,7 @@ def run_b200(args):
                        # accounting, App.cpp:955-958, times the trace kernels only)
                        "value_charging_raygen_delta": (counted_step / (sec / args.steps + (len(mine) - 1) * max(0.0, raygen_us["coherent_order"] - raygen_us["reference_order"]) * 1e-6) * 1e-6
                                                        if args.raygen_order else value),
+                       "per_batch_two_streams_value": counted_step * args.steps / sec_two_streams * 1e-6,
                        "one_stream_value": counted_step * args.steps / sec_serial * 1e-6,
                        "overlap_gain": sec_serial / sec},
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": int(ray_bytes), "d2h_bytes_per_step": int(ray_bytes // 2),
@@ -927,6 +982,8 @@ def main():
     ap.add_argument("--partition", default="deal", choices=["deal", "slices"], help="N > 1: how a ray type's frame buffer is split over the GPUs (see rank_ranges)")
     ap.add_argument("--config3", type=int, default=1, help="N > 1 only: also strong-scale BASELINE.json configs[3] (10.5 M triangles, diffuse) with the NCCL broadcast timed")
     ap.add_argument("--reference-gpu", type=int, default=1, help="rank 0: also time the reference's own kernels recompiled for sm_100a (oracle/_ref), when present")
+    ap.add_argument("--submission", default="frame", choices=["frame", "batches"],
+                    help="frame (default): a rank's share of each ray type in one persistent launch (nt_trace_batches); batches: one launch per <= 1 Mi-ray batch")
     ap.add_argument("--raygen-order", type=int, default=1, choices=[0, 1],
                     help="slot order of the secondary rays (nt_raygen_set_order): 0 = the reference generator's order, 1 (default) = the same rays in "
                          "direction-coherent order inside tiles of <= 1024 slots (written by the generator itself, no extra pass)")

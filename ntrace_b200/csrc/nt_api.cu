@@ -101,6 +101,10 @@ struct Context {
     // Wide4 form of the resident (Compact / Compact2) node buffer, derived on demand for the b200_wide4* kernels (nt_wide.cu)
     DevBuf wideNodes, wideScratch;
     int raygenOrder = 0;                 // nt_raygen_set_order
+    // nt_trace_batches: device tables of the launches in flight, a ring per stream (main stream: index kMaxKernelStreams); a table is
+    // written by a copy on the stream of the launch that reads it, so a slot is only reused behind the launch that used it before
+    static constexpr int kBatchTableSlots = 8;
+    DevBuf batchTables; int batchTableNext[kMaxKernelStreams + 1] = {};
     // b200_auto: the device buffer the library's own primary-ray generator wrote last.  Camera rays share one origin and stay together
     // far down the tree, where the cheaper binary node step wins over Wide4 (4.6 vs 4.1 Grays/s on the bench frame); a stale range can
     // only cost speed, never change a result.
@@ -419,7 +423,7 @@ void nt_shutdown(void)
     for (int i = 0; i < Context::kRing; i++) { cudaEventDestroy(g.ring[i].ev); cudaEventDestroy(g.prod[i].ev); }
     DevBuf* bufs[] = {&g.nodes, &g.woop, &g.triIndex, &g.sortedKeys, &g.sortedIdx, &g.stRays, &g.stResults, &g.stA, &g.stB,
                       &g.stC, &g.stD, &g.stE, &g.counters, &g.pixelTable, &g.sceneVerts, &g.sceneTris,
-                      &g.srcNodes, &g.srcWoop, &g.srcIdx, &g.layoutScratch, &g.wideNodes, &g.wideScratch};
+                      &g.srcNodes, &g.srcWoop, &g.srcIdx, &g.layoutScratch, &g.wideNodes, &g.wideScratch, &g.batchTables};
     for (DevBuf* b : bufs) b->release();
     release_build_scratch();
     release_sort_scratch();
@@ -1112,6 +1116,111 @@ int nt_trace_batch(const float* rays, int32_t* results, int numRays, int needClo
     float ms = 0.0f;
     NT_CUDA(cudaEventElapsedTime(&ms, g.evA, g.evB));
     if (outSeconds) *outSeconds = ms * 1.0e-3f;
+    return check_trace_error();
+}
+
+// Several device-resident batches in ONE persistent launch.  A persistent launch on its own spends its last ~20 % waiting for the
+// rays still in flight (profiles/r2_summary.md, section 12: 24 launches of 1 Mi diffuse rays 2 851 Mrays/s, the same rays in one launch
+// 3 673); nt_set_deferred(2) hides most of that by overlapping consecutive launches on two streams, one launch over the frame's batches
+// removes it.  The kernels are the same: ray index i of the launch is looked up in a small device table at ray fetch and at result store.
+int nt_trace_batches(int numBatches, const float* const* rays, int32_t* const* results, const int32_t* numRays, int needClosestHit, float* outSeconds)
+{
+    std::lock_guard<std::mutex> lock(g_mutex);
+    if (outSeconds) *outSeconds = 0.0f;
+    const bool overlapped = g.inited && g.deferred && g.overlap;
+    if (require_init(!overlapped)) return 1;
+    if (numBatches == 0) return 0;
+    if (numBatches < 0 || !rays || !results || !numRays) { set_error("ntrace_b200: invalid batch list"); return 1; }
+    if (!g.haveBVH) { set_error("CudaBVHTracer: No BVH!"); return 1; }
+    if (g.bvhLayout != g.kernelLayout) { set_error("CudaBVHTracer: Incorrect BVH layout!"); return 1; }
+    const int kernel = auto_kernel(nullptr, 0, needClosestHit);
+    if (kernel != Kernel_PersistentSpeculative && kernel != Kernel_Wide4Persistent) {
+        set_error("ntrace_b200: nt_trace_batches needs a persistent one-ray kernel (b200_persistent_speculative_while_while*, b200_wide4*, b200_auto*)");
+        return 1;
+    }
+    if (ensure_traversal_form() || ensure_wide_form()) return 1;
+    NT_CUDA(g.batchTables.reserve(sizeof(BatchTable) * Context::kBatchTableSlots * (Context::kMaxKernelStreams + 1)));
+    float totalMs = 0.0f;
+    int launches = 0;
+    for (int first = 0; first < numBatches; first += kMaxBatches) {
+        const int cnt = (numBatches - first < kMaxBatches) ? numBatches - first : kMaxBatches;
+        BatchTable t;
+        memset(&t, 0, sizeof(t));
+        long long total = 0;
+        int used = 0;
+        Range rd[kMaxBatches], wr[kMaxBatches];
+        const char *rLo = nullptr, *rHi = nullptr, *wLo = nullptr, *wHi = nullptr;
+        for (int i = 0; i < cnt; i++) {
+            const int n = numRays[first + i];
+            if (n < 0) { set_error("ntrace_b200: negative batch size"); return 1; }
+            if (n == 0) continue;
+            const float* r = rays[first + i]; int32_t* o = results[first + i];
+            if (!r || !o || !is_device_ptr(r) || !is_device_ptr(o)) { set_error("ntrace_b200: nt_trace_batches takes device buffers (use nt_trace_batch / nt_trace_batch_async for host memory)"); return 1; }
+            if ((reinterpret_cast<size_t>(r) & 31) || (reinterpret_cast<size_t>(o) & 15)) { set_error("ntrace_b200: ray buffers must be 32-byte aligned, result buffers 16-byte aligned"); return 1; }
+            t.start[used] = (int)total; t.rays[used] = (const float4*)r; t.results[used] = (int4*)o;
+            rd[used] = Range{r, (size_t)n * 32}; wr[used] = Range{o, (size_t)n * 16};
+            const char *a0 = (const char*)r, *a1 = a0 + (size_t)n * 32, *b0 = (const char*)o, *b1 = b0 + (size_t)n * 16;
+            if (!rLo || a0 < rLo) rLo = a0; if (!rHi || a1 > rHi) rHi = a1;
+            if (!wLo || b0 < wLo) wLo = b0; if (!wHi || b1 > wHi) wHi = b1;
+            total += n; used++;
+            if (total > 0x3fffffffLL) { set_error("ntrace_b200: a launch holds at most 2^30 - 1 rays (32-bit ray indexing in the kernels)"); return 1; }
+        }
+        if (used == 0) continue;
+        t.count = used; t.start[used] = (int)total;
+        TraceLaunch a;
+        a.kernel = kernel;
+        a.fast = g.fastMath ? 1 : 0; a.layout = g.basic ? (int)Layout_Compact : g.kernelLayout; a.anyHit = needClosestHit ? 0 : 1;
+        a.nodes = g.nodes.as<float4>(); a.woop = g.woop.as<float4>(); a.triIndices = g.triIndex.as<int>();
+        a.wideNodes = g.wideNodes.as<float4>();
+        a.errorFlag = g.errDev;
+        a.numSMs = g.numSMs;
+        a.numRays = (int)total; a.rays = nullptr; a.results = nullptr;
+        // overlapped mode: the launch goes to one of the kernel streams like a queued nt_trace_batch -- behind what the main stream has queued
+        // and behind the launches in flight that touch its buffers -- so that its CTAs move in while the launch before it drains
+        const int k = overlapped ? g.overlapNext : Context::kMaxKernelStreams;
+        if (overlapped) {
+            g.overlapNext = (g.overlapNext + 1) % g.numKernelStreams;
+            a.stream = g.kStream[k];
+            NT_CUDA(cudaEventRecord(g.kFork, g.stream));
+            NT_CUDA(cudaStreamWaitEvent(a.stream, g.kFork, 0));
+            a.warpCounter = g.counters.as<int>() + 4 + k;
+        } else {
+            a.stream = g.stream;
+            a.warpCounter = g.counters.as<int>();
+        }
+        if (join_for(a.stream, rd, used, wr, used)) return 1;
+        BatchTable* dT = g.batchTables.as<BatchTable>() + k * Context::kBatchTableSlots + g.batchTableNext[k];
+        g.batchTableNext[k] = (g.batchTableNext[k] + 1) % Context::kBatchTableSlots;
+        NT_CUDA(cudaMemcpyAsync(dT, &t, sizeof(BatchTable), cudaMemcpyHostToDevice, a.stream));     // pageable source: staged before the call returns
+        a.batches = dT;
+        NT_CUDA(cudaMemsetAsync(a.warpCounter, 0, sizeof(int), a.stream));
+        int l = 0;
+        if (overlapped) {
+            NT_CUDA(launch_trace(a, &l));
+            NT_CUDA(cudaEventRecord(g.kDone[k], a.stream));
+            Context::InFlight& slot = g.ring[g.ringNext];
+            g.ringNext = (g.ringNext + 1) % Context::kRing;
+            if (slot.live) NT_CUDA(cudaStreamWaitEvent(g.stream, slot.ev, 0));
+            slot.rLo = rLo; slot.rHi = rHi; slot.wLo = wLo; slot.wHi = wHi;        // the hull of the launch's buffers: conservative
+            NT_CUDA(cudaEventRecord(slot.ev, a.stream));
+            slot.live = true;
+            g.overlapPending = true;
+        } else if (g.deferred) {
+            NT_CUDA(launch_trace(a, &l));
+        } else {
+            NT_CUDA(cudaEventRecord(g.evA, g.stream));
+            NT_CUDA(launch_trace(a, &l));
+            NT_CUDA(cudaEventRecord(g.evB, g.stream));
+            NT_CUDA(cudaStreamSynchronize(g.stream));
+            float ms = 0.0f;
+            NT_CUDA(cudaEventElapsedTime(&ms, g.evA, g.evB));
+            totalMs += ms;
+        }
+        launches += l;
+    }
+    g.launches += launches;
+    if (g.deferred) return 0;
+    if (outSeconds) *outSeconds = totalMs * 1.0e-3f;
     return check_trace_error();
 }
 

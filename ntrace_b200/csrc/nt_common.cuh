@@ -40,6 +40,24 @@ enum TraceKernelId : int {
     Kernel_Count
 };
 
+// Several ray batches traced by ONE persistent launch (nt_trace_batches): ray index i of the launch belongs to batch b with
+// start[b] <= i < start[b + 1] and is ray i - start[b] of it.  Lives in device memory; read at ray fetch and result store only.
+constexpr int kMaxBatches = 64;
+struct BatchTable {
+    int count; int pad;
+    int start[kMaxBatches + 2];
+    const float4* rays[kMaxBatches];
+    int4* results[kMaxBatches];
+};
+#ifdef __CUDACC__
+__device__ __forceinline__ int batch_of(const BatchTable* __restrict__ bt, int idx)
+{
+    int lo = 0, hi = __ldg(&bt->count);
+    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (idx >= __ldg(&bt->start[mid])) lo = mid; else hi = mid; }
+    return lo;
+}
+#endif
+
 struct TraceLaunch {
     int kernel;               // TraceKernelId
     int layout;               // Layout_Compact or Layout_Compact2
@@ -54,6 +72,7 @@ struct TraceLaunch {
     const int* triIndices;    // device
     int* warpCounter;         // device, zeroed before launch (persistent kernels only)
     int* errorFlag = nullptr; // device-visible (mapped host) word; a kernel ORs 1 into it when a ray's traversal stack would overflow
+    const BatchTable* batches = nullptr;   // device; non-null: numRays = rays of all batches, `rays` / `results` unused (one-ray persistent kernels only)
     int numSMs;
     cudaStream_t stream;
 };

@@ -78,7 +78,8 @@ __global__ void __launch_bounds__(BLOCK)
 trace_kernel(int numRays, int anyHit, int fetchThreshold,
              const float4* __restrict__ rays, int4* __restrict__ results,
              const float4* __restrict__ nodes, const float4* __restrict__ woop,
-             const int* __restrict__ triIndices, int* __restrict__ warpCounter, int* __restrict__ errorFlag)
+             const int* __restrict__ triIndices, int* __restrict__ warpCounter, int* __restrict__ errorFlag,
+             const BatchTable* __restrict__ batches)
 {
     static_assert(SMEM_N >= 0 && SMEM_N <= kStackSize, "stack split");
     __shared__ int s_stack[(SMEM_N > 0 ? SMEM_N : 1) * BLOCK];
@@ -160,8 +161,12 @@ trace_kernel(int numRays, int anyHit, int fetchThreshold,
                 if (BULKRAYS) {
                     o = s_rays[(tid >> 5) * 64 + fetchRank * 2]; d = s_rays[(tid >> 5) * 64 + fetchRank * 2 + 1];
                 }
-                else if (WIDE) ld256_cs(rays + rayidx * 2, o, d);        // 32-byte aligned ray buffer (checked by the launcher)
-                else { o = __ldcs(rays + rayidx * 2 + 0); d = __ldcs(rays + rayidx * 2 + 1); }
+                else {
+                    const float4* rp = rays + rayidx * 2;
+                    if (batches) { const int b = batch_of(batches, rayidx); rp = batches->rays[b] + (size_t)(rayidx - __ldg(&batches->start[b])) * 2; }
+                    if (WIDE) ld256_cs(rp, o, d);                        // 32-byte aligned ray buffers (checked by the launcher)
+                    else { o = __ldcs(rp + 0); d = __ldcs(rp + 1); }
+                }
                 origx = o.x; origy = o.y; origz = o.z; tmin = o.w;
                 dirx = d.x; diry = d.y; dirz = d.z; hitT = d.w;
                 const float ooeps = exp2f(-80.0f);                      // fermi...cu:94-98
@@ -290,7 +295,9 @@ trace_kernel(int numRays, int anyHit, int fetchThreshold,
         if (rayidx >= 0 && nodeAddr == kEntrypointSentinel) {
             int id = hitIndex;
             if (id != -1) id = __ldg(triIndices + id);          // fermi...cu:260-261
-            __stcs(results + rayidx, make_int4(id, __float_as_int(hitT), __float_as_int(hitU), __float_as_int(hitV)));
+            int4* op = results + rayidx;
+            if (batches) { const int b = batch_of(batches, rayidx); op = batches->results[b] + (rayidx - __ldg(&batches->start[b])); }
+            __stcs(op, make_int4(id, __float_as_int(hitT), __float_as_int(hitU), __float_as_int(hitV)));
             if (PERSISTENT) rayidx = -1;
         }
         if (!PERSISTENT) break;
@@ -332,7 +339,8 @@ cudaError_t launch_variant(const TraceLaunch& a, int* launches)
     }
     int grid = (a.numRays + kBlock - 1) / kBlock;
     if (PERSISTENT && grid > a.numSMs * blocksPerSM) grid = a.numSMs * blocksPerSM;   // one resident wave
-    kern<<<grid, kBlock, 0, a.stream>>>(a.numRays, a.anyHit, tuning().fetchThreshold, a.rays, a.results, a.nodes, a.woop, a.triIndices, a.warpCounter, a.errorFlag);
+    if (a.batches && !PERSISTENT) return cudaErrorInvalidValue;                         // a batch table needs the global ray counter
+    kern<<<grid, kBlock, 0, a.stream>>>(a.numRays, a.anyHit, tuning().fetchThreshold, a.rays, a.results, a.nodes, a.woop, a.triIndices, a.warpCounter, a.errorFlag, a.batches);
     if (launches) *launches = 1;
     return cudaGetLastError();
 }
@@ -356,7 +364,8 @@ template <int LAYOUT, bool PERSISTENT>
 cudaError_t launch_one(const TraceLaunch& a, int* launches)
 {
     // 256-bit loads need a 32-byte aligned ray buffer and 64-byte aligned nodes (true for everything nt_mem_alloc returns)
-    const bool wide = (reinterpret_cast<size_t>(a.rays) & 31) == 0 && (reinterpret_cast<size_t>(a.nodes) & 63) == 0;
+    // (the ray buffers of a batch table are checked by nt_trace_batches)
+    const bool wide = (a.batches || (reinterpret_cast<size_t>(a.rays) & 31) == 0) && (reinterpret_cast<size_t>(a.nodes) & 63) == 0;
     if (a.fast) return wide ? launch_stack<LAYOUT, PERSISTENT, true, true>(a, launches) : launch_stack<LAYOUT, PERSISTENT, true, false>(a, launches);
     return wide ? launch_stack<LAYOUT, PERSISTENT, false, true>(a, launches) : launch_stack<LAYOUT, PERSISTENT, false, false>(a, launches);
 }
@@ -391,9 +400,11 @@ cudaError_t launch_trace(const TraceLaunch& a, int* launches)
         return launch_trace_wide4(a, launches);
     case Kernel_BinaryMr:
     case Kernel_Wide4Mr:
+        if (a.batches) return cudaErrorInvalidValue;
         return launch_trace_mr(a, launches);
     case Kernel_BinarySw:
     case Kernel_Wide4Sw:
+        if (a.batches) return cudaErrorInvalidValue;
         return launch_trace_sw(a, launches);
     default:
         return cudaErrorInvalidValue;

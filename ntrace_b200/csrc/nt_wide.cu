@@ -383,7 +383,8 @@ __global__ void __launch_bounds__(BLOCK)
 trace_wide4_kernel(int numRays, int anyHit, int fetchThreshold, int nodeExit, unsigned oneBits,
                    const float4* __restrict__ rays, int4* __restrict__ results,
                    const float4* __restrict__ wnodes, const float4* __restrict__ woop,
-                   const int* __restrict__ triIndices, int* __restrict__ warpCounter, int* __restrict__ errorFlag)
+                   const int* __restrict__ triIndices, int* __restrict__ warpCounter, int* __restrict__ errorFlag,
+                   const BatchTable* __restrict__ batches)
 {
     __shared__ int s_stack[(SMEM_N > 0 ? SMEM_N : 1) * BLOCK];
     int l_stack[(kWideStackSize > SMEM_N) ? (kWideStackSize - SMEM_N) : 1];
@@ -423,8 +424,10 @@ trace_wide4_kernel(int numRays, int anyHit, int fetchThreshold, int nodeExit, un
             if (rayidx >= numRays) { alive = false; rayidx = -1; }
             else {
                 float4 o, d;
-                if (WIDE_RAYS) wld256_cs(rays + rayidx * 2, o, d);
-                else { o = __ldcs(rays + rayidx * 2 + 0); d = __ldcs(rays + rayidx * 2 + 1); }
+                const float4* rp = rays + rayidx * 2;
+                if (batches) { const int b = batch_of(batches, rayidx); rp = batches->rays[b] + (size_t)(rayidx - __ldg(&batches->start[b])) * 2; }
+                if (WIDE_RAYS) wld256_cs(rp, o, d);
+                else { o = __ldcs(rp + 0); d = __ldcs(rp + 1); }
                 origx = o.x; origy = o.y; origz = o.z; tmin = o.w;
                 dirx = d.x; diry = d.y; dirz = d.z; hitT = d.w;
                 const float ooeps = exp2f(-80.0f);                      // fermi_speculative_while_while.cu:94-98
@@ -560,7 +563,9 @@ trace_wide4_kernel(int numRays, int anyHit, int fetchThreshold, int nodeExit, un
         if (rayidx >= 0 && nodeAddr == kEntrypointSentinel) {
             int id = hitIndex;
             if (id != -1) id = __ldg(triIndices + id);
-            __stcs(results + rayidx, make_int4(id, __float_as_int(hitT), __float_as_int(hitU), __float_as_int(hitV)));
+            int4* op = results + rayidx;
+            if (batches) { const int b = batch_of(batches, rayidx); op = batches->results[b] + (rayidx - __ldg(&batches->start[b])); }
+            __stcs(op, make_int4(id, __float_as_int(hitT), __float_as_int(hitU), __float_as_int(hitV)));
             rayidx = -1;
         }
     }
@@ -1206,7 +1211,7 @@ cudaError_t launch_wide_variant(const TraceLaunch& a, int* launches)
     }
     int grid = (a.numRays + kWideBlock - 1) / kWideBlock;
     if (grid > a.numSMs * blocksPerSM) grid = a.numSMs * blocksPerSM;
-    kern<<<grid, kWideBlock, 0, a.stream>>>(a.numRays, a.anyHit, wide_tuning().fetchThreshold, wide_tuning().nodeExit, 0x3F800000u, a.rays, a.results, a.wideNodes, a.woop, a.triIndices, a.warpCounter, a.errorFlag);
+    kern<<<grid, kWideBlock, 0, a.stream>>>(a.numRays, a.anyHit, wide_tuning().fetchThreshold, wide_tuning().nodeExit, 0x3F800000u, a.rays, a.results, a.wideNodes, a.woop, a.triIndices, a.warpCounter, a.errorFlag, a.batches);
     if (launches) *launches = 1;
     return cudaGetLastError();
 }
@@ -1252,7 +1257,7 @@ cudaError_t launch_trace_wide4(const TraceLaunch& a, int* launches)
 {
     if (a.numRays <= 0) { if (launches) *launches = 0; return cudaSuccess; }
     if (!a.wideNodes || (reinterpret_cast<size_t>(a.wideNodes) & 63)) return cudaErrorInvalidValue;
-    const bool wideRays = (reinterpret_cast<size_t>(a.rays) & 31) == 0;
+    const bool wideRays = a.batches || (reinterpret_cast<size_t>(a.rays) & 31) == 0;       // the buffers of a batch table are checked by nt_trace_batches
     if (a.fast) return wideRays ? launch_wide_stack<true, true>(a, launches) : launch_wide_stack<true, false>(a, launches);
     return wideRays ? launch_wide_stack<false, true>(a, launches) : launch_wide_stack<false, false>(a, launches);
 }

@@ -313,6 +313,24 @@ class CudaBVHTracer:
         _sync()
         return capi.trace_batch(rays.getRayBuffer(), rays.getResultBuffer(), n, rays.getNeedClosestHit())
 
+    def traceBatches(self, batches) -> float:
+        """NEW (nt_trace_batches): several RayBuffers with the same closest / any-hit flag in ONE persistent launch; same results per ray as
+        traceBatch on each, without the ramp-up and drain of every launch but one.  Returns the kernel time in seconds."""
+        batches = [b for b in batches if b.getSize() > 0]
+        if not batches:
+            return 0.0
+        if self._bvh is None:
+            raise NtError("CudaBVHTracer: No BVH!")
+        if self._bvh.getLayout() != self.getDesiredBVHLayout():
+            raise NtError("CudaBVHTracer: Incorrect BVH layout!")
+        if len({b.getNeedClosestHit() for b in batches}) != 1:
+            raise NtError("CudaBVHTracer: the batches of one launch share the closest / any-hit flag")
+        if self._bvh.generation and capi.bvh_generation() != self._bvh.generation:
+            self.setBVH(self._bvh)
+        _sync()
+        return capi.trace_batches([b.getRayBuffer() for b in batches], [b.getResultBuffer() for b in batches], [b.getSize() for b in batches],
+                                  batches[0].getNeedClosestHit())
+
 
 # --------------------------------------------------------------------------------------------------
 class RayGen:

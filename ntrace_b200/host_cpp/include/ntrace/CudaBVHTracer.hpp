@@ -2,6 +2,7 @@
 // Reference: src/rt/cuda/CudaVirtualTracer.hpp:11-26 (interface), src/rt/cuda/CudaBVHTracer.cpp:52-84 (setKernel +
 // queryConfig), :88-168 (traceBatch: empty batch -> 0, "No BVH!", "Incorrect BVH layout!", GPU seconds around the kernel).
 #pragma once
+#include <vector>
 #include "ntrace/CudaBVH.hpp"
 #include "ntrace/RayBuffer.hpp"
 
@@ -62,6 +63,31 @@ public:
         float sec = 0.0f;
         ntCheck(nt_trace_batch((const float*)rays.getRayBuffer().getCudaPtr(), (int32_t*)rays.getResultBuffer().getMutableCudaPtrDiscard(),
                                rays.getSize(), rays.getNeedClosestHit() ? 1 : 0, &sec));
+        return sec;
+    }
+
+    // NEW (nt_trace_batches): several RayBuffers with the same closest / any-hit flag in ONE persistent launch; same results per ray as
+    // traceBatch on each, without the ramp-up and drain of every launch but one.  Device-resident buffers.
+    F32 traceBatches(const std::vector<RayBuffer*>& batches)
+    {
+        std::vector<const float*> rays; std::vector<int32_t*> results; std::vector<int32_t> counts;
+        int closest = -1;
+        for (size_t i = 0; i < batches.size(); i++) {
+            RayBuffer& b = *batches[i];
+            if (!b.getSize()) continue;
+            if (closest >= 0 && closest != (b.getNeedClosestHit() ? 1 : 0)) fail("CudaBVHTracer: the batches of one launch share the closest / any-hit flag");
+            closest = b.getNeedClosestHit() ? 1 : 0;
+            rays.push_back((const float*)b.getRayBuffer().getCudaPtr());
+            results.push_back((int32_t*)b.getResultBuffer().getMutableCudaPtrDiscard());
+            counts.push_back(b.getSize());
+        }
+        if (rays.empty()) return 0.0f;
+        if (!m_bvh) fail("CudaBVHTracer: No BVH!");
+        if (m_bvh->getLayout() != getDesiredBVHLayout()) fail("CudaBVHTracer: Incorrect BVH layout!");
+        if (CudaBVH* bvh = dynamic_cast<CudaBVH*>(m_bvh))
+            if (bvh->getGeneration() && bvh->getGeneration() != CudaBVH::currentGeneration()) setBVH(m_bvh);
+        float sec = 0.0f;
+        ntCheck(nt_trace_batches((int)rays.size(), rays.data(), results.data(), counts.data(), closest, &sec));
         return sec;
     }
 
