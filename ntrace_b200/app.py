@@ -69,6 +69,7 @@ def run_benchmark(env: Environment, out=sys.stdout, device: int = 0):
     # NEW knob (default off = the reference's loop): whole frames are repeated instead of single batches, the batches of a frame are
     # queued back to back on alternating buffers (Renderer.setPipelined) and the device time of the whole batch loop is what is summed
     pipelined = env.Has("Benchmark.pipelined") and env.GetBool("Benchmark.pipelined")
+    frame_launch = env.Has("Benchmark.frameLaunch") and env.GetBool("Benchmark.frameLaunch")
 
     print(f'Running benchmark for "{env.GetString("Benchmark.scene")}".\n', file=out)
     scene = host.Scene(verts, tris)
@@ -90,6 +91,18 @@ def run_benchmark(env: Environment, out=sys.stdout, device: int = 0):
                 renderer.setParams(host.RendererParams(kernelName=kernel, rayType=RAY_TYPE_NAMES[rt.lower()], numSamples=env.GetInt("Renderer.samples"),
                                                        aoRadius=env.GetFloat("Raygen.aoRadius"), sortSecondary=env.GetBool("Renderer.sortRays")))
                 renderer.setPipelined(pipelined)
+                if frame_launch:
+                    # NEW knob Benchmark.frameLaunch: every batch of the frame is generated into its own buffer, then ONE persistent launch
+                    # traces them (Renderer.prepareFrame / traceFrame); the kernel seconds of that launch are what is summed
+                    renderer.setPipelined(False)
+                    renderer.beginFrame(cam, w, h)
+                    total_rays += renderer.getTotalNumRays() * meas
+                    renderer.prepareFrame()
+                    for _ in range(1 + warm):
+                        renderer.traceFrame()
+                    for _ in range(meas):
+                        total_time += renderer.traceFrame()
+                    continue
                 if pipelined:
                     for rep in range(warm + meas):
                         renderer.beginFrame(cam, w, h)

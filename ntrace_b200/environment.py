@@ -27,6 +27,7 @@ OPTIONS = {
     "Benchmark.measureRepeats": ("int", "benchmark_measure=", "5"),
     "Benchmark.cachePath": ("string", "benchmark_cachepath=", None),        # new: directory of the bvhcache files (reference: "bvhcache")
     "Benchmark.pipelined": ("bool", "benchmark_pipelined=", "false"),      # new: queue a frame's batches back to back (Renderer.setPipelined)
+    "Benchmark.frameLaunch": ("bool", "benchmark_framelaunch=", "false"),  # new: all batches of a frame in one persistent launch (Renderer.prepareFrame / traceFrame)
     "Renderer.dataStructure": ("string", "renderer_ds=", None),
     "Renderer.builder": ("string", "renderer_builder=", None),
     "Renderer.rayType": ("string", "renderer_raytype=", None),

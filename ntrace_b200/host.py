@@ -624,6 +624,49 @@ class Renderer:
             raise NtError("Renderer: no batch")
         return self.m_cudaTracer.traceBatch(self.m_batchRays)
 
+    def prepareFrame(self) -> int:
+        """NEW (no reference counterpart; the reference's Renderer holds ONE secondary RayBuffer, Renderer.hpp).  After beginFrame():
+        generate EVERY batch of the frame for the current ray type, each into its own RayBuffer of a grow-only pool -> number of batches.
+        Same batches, same rays as the nextBatch() loop produces one after the other."""
+        rt = self.m_params.rayType
+        if rt == RayType_Primary:
+            self.m_frameBatches = [self.m_primaryRays]
+            return 1
+        if rt not in (RayType_AO, RayType_Diffuse):
+            raise NtError(f"unsupported ray type {rt}")
+        closest = rt == RayType_Diffuse
+        dist = self.m_cameraFar if closest else self.m_params.aoRadius
+        if not hasattr(self, "m_framePool"):
+            self.m_framePool = []
+        batches, new = [], True
+        self.m_raygen.m_aoStartIdx = 0
+        while True:
+            if len(batches) == len(self.m_framePool):
+                self.m_framePool.append(RayBuffer())
+            rb = self.m_framePool[len(batches)]
+            ok, new = self.m_raygen.ao(rb, self.m_primaryRays, self.m_scene, self.m_params.numSamples, dist, new, FIXED_AO_SEED)
+            if not ok:
+                break
+            rb.setNeedClosestHit(closest)
+            if self.m_params.sortSecondary:
+                rb.mortonSort()
+            batches.append(rb)
+        self.m_frameBatches = batches
+        return len(batches)
+
+    def traceFrame(self) -> float:
+        """NEW: the batches prepareFrame() generated, traced by ONE persistent launch (CudaBVHTracer.traceBatches = nt_trace_batches): the same
+        results per ray as traceBatch() on each, without the ramp-up and drain of every launch but one.  Returns the kernel seconds."""
+        batches = getattr(self, "m_frameBatches", None)
+        if not batches:
+            raise NtError("Renderer: no frame prepared")
+        if len(batches) == 1:
+            return self.m_cudaTracer.traceBatch(batches[0])
+        return self.m_cudaTracer.traceBatches(batches)
+
+    def getFrameBatches(self):
+        return list(getattr(self, "m_frameBatches", []))
+
     def getTotalNumRays(self) -> int:
         """Rays counted by the benchmark: w*h for primary, primary hits x samples otherwise (Renderer.cpp:676-710)."""
         if self.m_params.rayType == RayType_Primary:

@@ -2,6 +2,8 @@
 // Reference: src/rt/cuda/Renderer.hpp:44-190, Renderer.cpp:134-160 (setParams), :168-232 (getCudaBVH incl. the bvhcache file),
 // :405-579 (beginFrame / nextBatch / traceBatch), :676-710 (getTotalNumRays).
 #pragma once
+#include <vector>
+#include <memory>
 #include "ntrace/CameraControls.hpp"
 #include "ntrace/CudaBVHTracer.hpp"
 #include "ntrace/Environment.hpp"
@@ -244,6 +246,41 @@ public:
     }
     RayBuffer* getBatchRays() { return m_batchRays; }
 
+    // NEW (no reference counterpart; the reference's Renderer holds ONE secondary RayBuffer).  After beginFrame(): generate EVERY batch of
+    // the frame for the current ray type (this rank's share with numGpus > 1), each into its own RayBuffer of a grow-only pool; returns the
+    // number of batches.  Same batches, same rays as the nextBatch() loop produces one after the other.
+    int prepareFrame()
+    {
+        m_frameBatches.clear();
+        if (m_params.rayType == RayType_Primary) { if (m_rank == 0) m_frameBatches.push_back(&m_primaryRays); return (int)m_frameBatches.size(); }
+        if (m_params.rayType != RayType_AO && m_params.rayType != RayType_Diffuse) fail("Renderer: unsupported ray type");
+        const bool closest = (m_params.rayType == RayType_Diffuse);
+        bool newBatch = true;
+        int counter = 0;
+        for (;;) {
+            if (m_numGpus > 1 && (counter++ % m_numGpus) != m_rank) {                 // another rank's batch
+                if (!m_raygen.skipAo(m_primaryRays, m_params.numSamples, newBatch)) break;
+                continue;
+            }
+            if (m_frameBatches.size() == m_framePool.size()) m_framePool.push_back(std::unique_ptr<RayBuffer>(new RayBuffer()));
+            RayBuffer& rb = *m_framePool[m_frameBatches.size()];
+            if (!m_raygen.ao(rb, m_primaryRays, *m_scene, m_params.numSamples, closest ? m_cameraFar : m_params.aoRadius, newBatch, FixedSecondarySeed)) break;
+            rb.setNeedClosestHit(closest);
+            if (m_params.sortSecondary) rb.mortonSort();
+            m_frameBatches.push_back(&rb);
+        }
+        return (int)m_frameBatches.size();
+    }
+    // NEW: the batches prepareFrame() generated, traced by ONE persistent launch (CudaBVHTracer::traceBatches = nt_trace_batches): the same
+    // results per ray as traceBatch() on each, without the ramp-up and drain of every launch but one.  Returns the kernel seconds.
+    F32 traceFrame()
+    {
+        if (m_frameBatches.empty()) return 0.0f;
+        if (m_frameBatches.size() == 1) return m_cudaTracer->traceBatch(*m_frameBatches[0]);
+        return m_cudaTracer->traceBatches(m_frameBatches);
+    }
+    const std::vector<RayBuffer*>& getFrameBatches() const { return m_frameBatches; }
+
     S32 getTotalNumRays()                                                   // Renderer.cpp:676-710
     {
         if (m_params.rayType == RayType_Primary) return m_primaryRays.getSize();
@@ -261,6 +298,8 @@ private:
     HLBVHParams m_hlbvh;
     String m_builder, m_cachePath, m_cacheFileOverride;
     RayBuffer m_primaryRays, m_secondary[NumSecondary];
+    std::vector<std::unique_ptr<RayBuffer> > m_framePool;
+    std::vector<RayBuffer*> m_frameBatches;
     bool m_useCachePath;
     int m_rank, m_numGpus, m_batchCounter;
     F32 m_broadcastTime = 0.0f;

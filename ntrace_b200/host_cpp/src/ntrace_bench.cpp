@@ -66,6 +66,8 @@ static void runBenchmark(Environment& env)
     env.GetStringValue("App.stats", statsFile); env.GetStringValue("Benchmark.dumpPrefix", dumpPrefix);
     bool pipelined = false;
     env.GetBoolValue("Benchmark.pipelined", pipelined);
+    bool frameLaunch = false;                                                // NEW knob: all batches of a frame in one persistent launch
+    env.GetBoolValue("Benchmark.frameLaunch", frameLaunch);
     if (env.GetStringValue("Renderer.dataStructure", ds) && ds != "BVH") fail("Incorrect data structure type!  (only Renderer.dataStructure=BVH is on this path)");
     if (!env.GetStringValue("Benchmark.scene", sceneFile) || sceneFile.empty()) fail("Benchmark.scene is not set");
     if (!env.GetStringValue("Benchmark.camera", cameraSpec) || cameraSpec.empty()) fail("Benchmark.camera is empty");
@@ -160,7 +162,17 @@ static void runBenchmark(Environment& env)
                 renderer.setParams(params);
                 renderer.setPipelined(pipelined);
                 RayBuffer* last = NULL;
-                if (pipelined) {
+                if (frameLaunch) {
+                    // NEW knob Benchmark.frameLaunch: every batch of the frame is generated into its own buffer (Renderer::prepareFrame), then
+                    // ONE persistent launch traces them (traceFrame = nt_trace_batches); the kernel seconds of that launch are what is summed
+                    renderer.setPipelined(false);
+                    renderer.beginFrame(cameras[c], w, h);
+                    totalRays += (long long)renderer.getTotalNumRays() * measureRepeats;
+                    renderer.prepareFrame();
+                    for (int i = 0; i < 1 + warmupRepeats; i++) renderer.traceFrame();
+                    for (int i = 0; i < measureRepeats; i++) totalTime += renderer.traceFrame();
+                    if (!renderer.getFrameBatches().empty()) last = renderer.getFrameBatches().back();
+                } else if (pipelined) {
                     // NEW knob Benchmark.pipelined: whole frames are repeated instead of single batches; the batches of a frame are queued
                     // back to back on alternating buffers and the device time of the whole batch loop is what is summed
                     for (int rep = 0; rep < warmupRepeats + measureRepeats; rep++) {

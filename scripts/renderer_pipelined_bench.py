@@ -29,25 +29,26 @@ def main():
     kernel = os.environ.get("NT_BENCH_KERNEL", "b200_auto")          # the bench's default kernel
     COMMON.append(f"-DBenchmark.kernel={kernel}")
     out["kernel"] = kernel
-    for pipelined in (False, True):
-        stats = os.path.join(tmp, f"py_{int(pipelined)}.log")
+    MODES = (("synchronous", []), ("pipelined", ["-DBenchmark.pipelined=true"]), ("frame_launch", ["-DBenchmark.frameLaunch=true"]))
+    for mode, extra in MODES:
+        stats = os.path.join(tmp, f"py_{mode}.log")
         env = Environment()
-        env.Parse(COMMON + [f"-DApp.stats={stats}", "-DBenchmark.scene=synthetic:conference", f"-DBenchmark.pipelined={'true' if pipelined else 'false'}"], default_env_file=None)
+        env.Parse(COMMON + [f"-DApp.stats={stats}", "-DBenchmark.scene=synthetic:conference"] + extra, default_env_file=None)
         app.run_benchmark(env, out=io.StringIO())
         k = krays(stats)
-        out["python_app_" + ("pipelined" if pipelined else "synchronous")] = dict(zip(("primary", "AO", "diffuse"), [x * 1e-3 for x in k]))
+        out["python_app_" + mode] = dict(zip(("primary", "AO", "diffuse"), [x * 1e-3 for x in k]))
     exe = os.path.join(ROOT, "ntrace_b200", "host_cpp", "ntrace_bench")
     if os.path.exists(exe):
         verts, tris, _ = scenes.config_scene("conference")
         mesh = os.path.join(tmp, "conference.ntmesh")
         mesh_io.save_ntmesh(mesh, verts, tris)
-        for pipelined in (False, True):
-            stats = os.path.join(tmp, f"cpp_{int(pipelined)}.log")
-            r = subprocess.run([exe] + COMMON + [f"-DApp.stats={stats}", f"-DBenchmark.scene={mesh}", f"-DBenchmark.pipelined={'true' if pipelined else 'false'}"], capture_output=True, text=True)
+        for mode, extra in MODES:
+            stats = os.path.join(tmp, f"cpp_{mode}.log")
+            r = subprocess.run([exe] + COMMON + [f"-DApp.stats={stats}", f"-DBenchmark.scene={mesh}"] + extra, capture_output=True, text=True)
             if r.returncode != 0:
                 out["cpp_error"] = (r.stdout + r.stderr)[-500:]
                 break
-            out["cpp_ntrace_bench_" + ("pipelined" if pipelined else "synchronous")] = dict(zip(("primary", "AO", "diffuse"), [x * 1e-3 for x in krays(stats)]))
+            out["cpp_ntrace_bench_" + mode] = dict(zip(("primary", "AO", "diffuse"), [x * 1e-3 for x in krays(stats)]))
     # frame rate of the three ray types together, as bench.py counts it: rays / (sum of times); 786 432 primary hits -> 24 x 1 Mi rays per secondary type
     for k, v in list(out.items()):
         if isinstance(v, dict):

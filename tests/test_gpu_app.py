@@ -106,3 +106,50 @@ def test_run_benchmark_pipelined_knob(gpu_host, tmp_path):
         gpu_host.capi.bvh_set_collapse(0, 0)
     assert len(res) == 3 and all(r > 0 for r in res)
     assert stats.read_text().split("\n").count("#SUM_RENDER_KRAYS") == 3
+
+
+def test_frame_launch_is_bit_identical_to_the_batch_loop(gpu_host):
+    """Renderer.prepareFrame / traceFrame (all batches of the frame in one persistent launch) against the reference-shaped batch loop."""
+    import numpy as np
+    from ntrace_b200 import camera, scenes
+    verts, tris = scenes.room(12_000, seed=5, wall_frac=0.3)
+    scene = gpu_host.Scene(verts, tris)
+    cam = camera.named_camera("conference")
+    w, h = 320, 240
+    for rt in (gpu_host.RayType_AO, gpu_host.RayType_Diffuse):
+        for kernel in ("b200_persistent_speculative_while_while", "b200_auto"):
+            r = gpu_host.Renderer(gpu_host.BuildSettings(builder="HLBVH"))
+            r.m_raygen = gpu_host.RayGen(1 << 16)
+            r.setScene(scene)
+            r.setParams(gpu_host.RendererParams(kernelName=kernel, rayType=rt, numSamples=8, aoRadius=5.0, sortSecondary=False))
+            r.beginFrame(cam, w, h)
+            want = []
+            while r.nextBatch():
+                assert r.traceBatch() > 0.0
+                want.append(r.m_batchRays.results_host().copy())
+            r.beginFrame(cam, w, h)
+            assert r.prepareFrame() == len(want) >= 4
+            assert r.traceFrame() > 0.0
+            got = [b.results_host() for b in r.getFrameBatches()]
+            for a, b in zip(want, got):
+                assert np.array_equal(a, b)
+    gpu_host.capi.set_kernel("b200_persistent_speculative_while_while")
+
+
+def test_run_benchmark_frame_launch_knob(gpu_host, tmp_path):
+    from ntrace_b200 import app
+    from ntrace_b200.environment import Environment
+    stats = tmp_path / "stats.log"
+    env = Environment()
+    env.Parse([f"-DApp.stats={stats}", "-DApp.frameWidth=256", "-DApp.frameHeight=192", "-DBenchmark.scene=synthetic:room:8000:3", "-DBenchmark.camera=conference",
+               "-DBenchmark.warmupRepeats=1", "-DBenchmark.measureRepeats=2", "-DRenderer.dataStructure=BVH", "-DRenderer.builder=HLBVH",
+               "-DRenderer.rayType=primary;AO;diffuse", "-DRenderer.samples=4", "-DRenderer.sortRays=false", "-DBenchmark.frameLaunch=true",
+               "-DBenchmark.kernel=b200_auto", "-DRaygen.coherentOrder=true", "-DHLBVH.bits=2", "-DHLBVH.collapse=true"], default_env_file=None)
+    try:
+        res = app.run_benchmark(env, out=io.StringIO())
+    finally:
+        gpu_host.capi.bvh_set_collapse(0, 0)
+        gpu_host.capi.raygen_set_order(0)
+        gpu_host.capi.set_kernel("b200_persistent_speculative_while_while")
+    assert len(res) == 3 and all(r > 0 for r in res)
+    assert stats.read_text().split("\n").count("#SUM_RENDER_KRAYS") == 3
