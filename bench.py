@@ -736,6 +736,9 @@ def config3_leg(torch, dist, capi, host, multigpu, camera, rank, world, dev, arg
     res_full = torch.full((n_total, 4), -7, dtype=torch.int32, device=dev)
 
     def frame(parts, keep):
+        if args.submission == "frame" and len(parts) > 1:            # this rank's share of the frame in one persistent launch
+            capi.trace_batches([p_[1] for p_ in parts], [res_full[p_[4]:p_[4] + p_[2]] for p_ in parts], [p_[2] for p_ in parts], True)
+            return
         for i, (_, rays, n, closest, off) in enumerate(parts):
             capi.trace_batch(rays, res_full[off:off + n], n, closest)
 
@@ -756,7 +759,8 @@ def config3_leg(torch, dist, capi, host, multigpu, camera, rank, world, dev, arg
     t_sharded = all_max([timed(mine)])[0]
     out["mrays_sharded"] = hits * args.spp / t_sharded * 1e-6
     out["frame_ms_sharded"] = t_sharded * 1e3
-    out["launches_per_gpu"] = len(mine)
+    out["batches_per_gpu"] = len(mine)
+    out["submission"] = args.submission
     out["partition"] = args.partition
     gathered = torch.zeros_like(res_full)                      # every slot is written by exactly one rank: the NCCL sum assembles the frame
     for _, rays, n, closest, off in mine:
