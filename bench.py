@@ -584,7 +584,7 @@ def run_b200(args):
             "ms_per_step": sec / args.steps * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": "conference stand-in room(283000, seed=2): primary + AO(32spp, r=5, any-hit) + diffuse(32spp, closest-hit), "
-                                   "1024x768, <=1Mi rays/launch, GPU %s leaf 8%s" % ("HLBVH(hlbvhBits %d)" % args.hlbvh_bits if args.builder == "hlbvh" else "LBVH", ", SAH-guided collapse" if args.collapse else ""),
+                                   "1024x768, <= 1 Mi rays per batch (RayBuffer), GPU %s leaf 8%s" % ("HLBVH(hlbvhBits %d)" % args.hlbvh_bits if args.builder == "hlbvh" else "LBVH", ", SAH-guided collapse" if args.collapse else ""),
                        "rays_traced_per_step": int(sum(traced.values())), "rays_counted_per_step": int(counted_step),
                        "launches_per_step_per_gpu": launches // max(1, args.steps), "batches_per_step_per_gpu": len(mine), "kernel": args.kernel,
                        "ray_order": ("nt_raygen_set_order(1): the generator writes each tile of <= 1024 secondary rays (32 neighbouring hit points x 32 samples) in "
